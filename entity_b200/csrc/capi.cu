@@ -1,0 +1,295 @@
+// entity_b200 -- the C ABI (include/entity_b200.h): context, argument checks, dispatch to
+// the strict / fast kernel variants. No compute happens on the host and there is no CPU
+// fallback: without a usable CUDA device every entry point fails.
+#include "launch.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+namespace eb200 {
+  static std::atomic<uint64_t> g_launches { 0 };
+
+  void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+  uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
+} // namespace eb200
+
+struct eb200_ctx {
+  eb200_config_t cfg;
+  eb200::Scratch scratch;
+  std::string    err;
+  uint64_t       launches_at_init;
+};
+
+static std::string g_last_error;
+static std::mutex  g_err_mutex;
+
+static int fail(eb200_ctx* ctx, int code, const std::string& msg) {
+  {
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_last_error = msg;
+  }
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+static int check_cuda(eb200_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return EB200_OK;
+  return fail(ctx, EB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define REQUIRE(ctx, cond, msg)                                                                \
+  do {                                                                                         \
+    if (!(cond)) return fail((ctx), EB200_ERR_ARG, std::string(__func__) + ": " + (msg));      \
+  } while (0)
+
+#define ENTER(ctx)                                                                             \
+  do {                                                                                         \
+    if ((ctx) == nullptr) return fail(nullptr, EB200_ERR_ARG, std::string(__func__) + ": null context"); \
+    cudaError_t e_ = cudaSetDevice((ctx)->cfg.device);                                         \
+    if (e_ != cudaSuccess) return check_cuda((ctx), e_, "cudaSetDevice");                      \
+  } while (0)
+
+// run the variant the context was created for
+#define VARIANT_CALL(ctx, expr)                                                                \
+  ((ctx)->cfg.strict_fp ? eb200::strict_fp::expr : eb200::fast_fp::expr)
+
+extern "C" {
+
+int eb200_version(void) { return EB200_VERSION; }
+
+int eb200_device_count(void) {
+  int         n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* eb200_last_error(const eb200_ctx_t* ctx) {
+  if (ctx) return ctx->err.c_str();
+  return g_last_error.c_str();
+}
+
+uint64_t eb200_launch_count(const eb200_ctx_t* ctx) {
+  return eb200::launches() - (ctx ? ctx->launches_at_init : 0);
+}
+
+int eb200_init(const eb200_config_t* cfg, eb200_ctx_t** out) {
+  if (cfg == nullptr || out == nullptr) return fail(nullptr, EB200_ERR_ARG, "eb200_init: null argument");
+  *out = nullptr;
+  if (eb200_device_count() <= 0) {
+    return fail(nullptr, EB200_ERR_NO_DEVICE,
+                "eb200_init: no CUDA device available (this library has no CPU fallback)");
+  }
+  if (cfg->grid.dim < 1 || cfg->grid.dim > 3) return fail(nullptr, EB200_ERR_ARG, "eb200_init: dim must be 1..3");
+  if (cfg->shape_order < 0 || cfg->shape_order > 3) {
+    return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_init: shape_order must be 0..3");
+  }
+  if (cfg->metric != EB200_METRIC_MINKOWSKI) {
+    return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_init: only the Minkowski metric is built");
+  }
+  const int need_ng = cfg->shape_order == 0 ? 2 : (cfg->shape_order + 1) / 2 + 1;
+  if (cfg->grid.ng < need_ng) {
+    return fail(nullptr, EB200_ERR_ARG, "eb200_init: too few ghost cells for this shape order");
+  }
+  for (int a = 0; a < cfg->grid.dim; ++a) {
+    if (cfg->grid.n[a] < cfg->grid.ng) return fail(nullptr, EB200_ERR_ARG, "eb200_init: n[a] < ng");
+  }
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return check_cuda(nullptr, e, "cudaSetDevice");
+  eb200_ctx* ctx        = new eb200_ctx();
+  ctx->cfg              = *cfg;
+  ctx->launches_at_init = eb200::launches();
+  for (int a = cfg->grid.dim; a < 3; ++a) ctx->cfg.grid.n[a] = 1;
+  *out = ctx;
+  return EB200_OK;
+}
+
+void eb200_finalize(eb200_ctx_t* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  ctx->scratch.release();
+  delete ctx;
+}
+
+int eb200_faraday(eb200_ctx_t* ctx, float* em, float coeff1, float coeff2,
+                  const float* stencil9_host, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, em != nullptr, "em is null");
+  return check_cuda(ctx,
+                    VARIANT_CALL(ctx, faraday(ctx->cfg.grid, em, coeff1, coeff2, stencil9_host,
+                                              (cudaStream_t)stream)),
+                    "faraday");
+}
+
+int eb200_ampere(eb200_ctx_t* ctx, float* em, float coeff1, float coeff2, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, em != nullptr, "em is null");
+  return check_cuda(ctx, VARIANT_CALL(ctx, ampere(ctx->cfg.grid, em, coeff1, coeff2, (cudaStream_t)stream)),
+                    "ampere");
+}
+
+int eb200_currents_ampere(eb200_ctx_t* ctx, float* em, float* cur, float coeff, float ppc0,
+                          eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, em != nullptr && cur != nullptr, "null field");
+  return check_cuda(ctx,
+                    VARIANT_CALL(ctx, currents_ampere(ctx->cfg.grid, em, cur, coeff, ppc0,
+                                                      (cudaStream_t)stream)),
+                    "currents_ampere");
+}
+
+static size_t field_bytes(const eb200_grid_t& g, int ncomp) {
+  size_t n = ncomp;
+  for (int a = 0; a < g.dim; ++a) n *= (size_t)(g.n[a] + 2 * g.ng);
+  return n * sizeof(float);
+}
+
+int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const int* fbc,
+                 eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, cur != nullptr && buff != nullptr && fbc != nullptr, "null argument");
+  REQUIRE(ctx, nfilter >= 0, "nfilter < 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int a = 0; a < 2 * ctx->cfg.grid.dim; ++a) {
+    if (fbc[a] == EB200_FBC_AXIS) {
+      return fail(ctx, EB200_ERR_UNSUPPORTED, "eb200_filter: axis boundaries need a spherical metric");
+    }
+  }
+  const size_t bytes = field_bytes(ctx->cfg.grid, 3);
+  for (int pass = 0; pass < nfilter; ++pass) {
+    // buff <- cur (currents.h:108), filter into cur (:109-116), ghost exchange (:117)
+    cudaError_t e = cudaMemcpyAsync(buff, cur, bytes, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return check_cuda(ctx, e, "filter copy");
+    e = VARIANT_CALL(ctx, filter_pass(ctx->cfg.grid, cur, buff, fbc, st));
+    if (e != cudaSuccess) return check_cuda(ctx, e, "filter pass");
+    e = VARIANT_CALL(ctx, comm_fields_self(ctx->cfg.grid, cur, 0, 3, fbc, st));
+    if (e != cudaSuccess) return check_cuda(ctx, e, "filter ghost exchange");
+  }
+  return EB200_OK;
+}
+
+static int check_prtls(eb200_ctx* ctx, const eb200_prtls_t* p, uint32_t npart) {
+  if (p == nullptr) return fail(ctx, EB200_ERR_ARG, "particle struct is null");
+  if (npart == 0) return EB200_OK;
+  const int d = ctx->cfg.grid.dim;
+  bool      ok = p->i1 && p->dx1 && p->i1_prev && p->dx1_prev && p->ux1 && p->ux2 && p->ux3 &&
+            p->weight && p->tag;
+  if (d > 1) ok = ok && p->i2 && p->dx2 && p->i2_prev && p->dx2_prev;
+  if (d > 2) ok = ok && p->i3 && p->dx3 && p->i3_prev && p->dx3_prev;
+  if (!ok) return fail(ctx, EB200_ERR_ARG, "a required particle array is null");
+  if (ctx->cfg.maxnpart && npart > ctx->cfg.maxnpart) {
+    return fail(ctx, EB200_ERR_CAPACITY, "npart exceeds maxnpart");
+  }
+  return EB200_OK;
+}
+
+static int check_pusher(eb200_ctx* ctx, const eb200_pusher_t* c) {
+  if (c == nullptr) return fail(ctx, EB200_ERR_ARG, "pusher context is null");
+  // kernel::sr::Pusher_kernel ctor: "No particle pusher specified" (sr.hpp:112-114)
+  if (c->pusher_flags == EB200_PUSHER_NONE) return fail(ctx, EB200_ERR_ARG, "No particle pusher specified");
+  if (c->pusher_flags != EB200_PUSHER_PHOTON &&
+      !(c->pusher_flags & (EB200_PUSHER_BORIS | EB200_PUSHER_VAY))) {
+    return fail(ctx, EB200_ERR_ARG, "Invalid pusher algorithm");
+  }
+  if (!(c->dx > 0.0f)) return fail(ctx, EB200_ERR_ARG, "pusher.dx must be positive");
+  return EB200_OK;
+}
+
+int eb200_push_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher, const eb200_prtls_t* prtls,
+                  uint32_t npart, const float* em, eb200_stream_t stream) {
+  ENTER(ctx);
+  int rc = check_pusher(ctx, pusher);
+  if (rc) return rc;
+  rc = check_prtls(ctx, prtls, npart);
+  if (rc) return rc;
+  REQUIRE(ctx, em != nullptr, "em is null");
+  return check_cuda(ctx,
+                    VARIANT_CALL(ctx, push_sr(ctx->cfg.grid, ctx->cfg.shape_order, *pusher,
+                                              *prtls, npart, em, (cudaStream_t)stream)),
+                    "push_sr");
+}
+
+int eb200_deposit(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, float charge,
+                  float dt, float* cur, int mode, eb200_stream_t stream) {
+  ENTER(ctx);
+  int rc = check_prtls(ctx, prtls, npart);
+  if (rc) return rc;
+  REQUIRE(ctx, cur != nullptr, "cur is null");
+  REQUIRE(ctx, dt > 0.0f, "dt must be positive");
+  REQUIRE(ctx, mode == EB200_DEPOSIT_ATOMIC || mode == EB200_DEPOSIT_ORDERED, "bad deposit mode");
+  const float dx = ctx->cfg.metric_params[0];
+  REQUIRE(ctx, dx > 0.0f, "metric_params[0] (dx) must be positive");
+  return check_cuda(ctx,
+                    VARIANT_CALL(ctx, deposit(ctx->cfg.grid, ctx->cfg.shape_order, *prtls, npart,
+                                              charge, dt, dx, cur, mode, ctx->scratch,
+                                              (cudaStream_t)stream)),
+                    "deposit");
+}
+
+int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
+                          const eb200_prtls_t* prtls, uint32_t npart, const float* em, float* cur,
+                          eb200_stream_t stream) {
+  ENTER(ctx);
+  int rc = check_pusher(ctx, pusher);
+  if (rc) return rc;
+  rc = check_prtls(ctx, prtls, npart);
+  if (rc) return rc;
+  REQUIRE(ctx, em != nullptr && cur != nullptr, "null field");
+  return check_cuda(ctx,
+                    VARIANT_CALL(ctx, push_deposit_sr(ctx->cfg.grid, ctx->cfg.shape_order,
+                                                      *pusher, *prtls, npart, em, cur,
+                                                      (cudaStream_t)stream)),
+                    "push_deposit_sr");
+}
+
+int eb200_zero_currents(eb200_ctx_t* ctx, float* cur, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, cur != nullptr, "cur is null");
+  return check_cuda(ctx,
+                    cudaMemsetAsync(cur, 0, field_bytes(ctx->cfg.grid, 3), (cudaStream_t)stream),
+                    "zero_currents");
+}
+
+int eb200_comm_fields(eb200_ctx_t* ctx, float* fld, int ncomp, int c0, int c1, const int* fbc,
+                      eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, fld != nullptr && fbc != nullptr, "null argument");
+  REQUIRE(ctx, 0 <= c0 && c0 < c1 && c1 <= ncomp, "bad component range");
+  return check_cuda(ctx,
+                    VARIANT_CALL(ctx, comm_fields_self(ctx->cfg.grid, fld, c0, c1, fbc,
+                                                       (cudaStream_t)stream)),
+                    "comm_fields");
+}
+
+int eb200_sync_currents(eb200_ctx_t* ctx, float* cur, float* buff, const int* fbc,
+                        eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, cur != nullptr && fbc != nullptr, "null argument");
+  return check_cuda(ctx,
+                    VARIANT_CALL(ctx, sync_currents_self(ctx->cfg.grid, cur, buff, fbc,
+                                                         (cudaStream_t)stream)),
+                    "sync_currents");
+}
+
+int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t* npart_inout,
+                         int remove_dead, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, npart_inout != nullptr, "npart pointer is null");
+  int rc = check_prtls(ctx, prtls, *npart_inout);
+  if (rc) return rc;
+  uint32_t    n_alive = *npart_inout;
+  cudaError_t e = eb200::sort_particles(ctx->cfg.grid, *prtls, *npart_inout, ctx->cfg.maxnpart,
+                                        remove_dead, &n_alive, ctx->scratch, (cudaStream_t)stream);
+  if (e != cudaSuccess) return check_cuda(ctx, e, "sort_particles");
+  if (remove_dead) *npart_inout = n_alive;
+  return EB200_OK;
+}
+
+} // extern "C"

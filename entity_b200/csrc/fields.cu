@@ -1,0 +1,556 @@
+// entity_b200 -- cell kernels: Faraday / Ampere / CurrentsAmpere (Minkowski), the binomial
+// current filter, and the single-domain ghost exchange.
+//
+// Reference behaviour: src/kernels/faraday_mink.hpp:71-166, src/kernels/ampere_mink.hpp:48-215,
+// src/kernels/digital_filter.hpp:99-388, src/framework/domain/metadomain_comm.cpp:122-562,
+// src/framework/domain/comm_nompi.hpp:29-119. Compiled twice (EB200_STRICT=0/1).
+//
+// All kernels are one thread per cell with i1 along threadIdx.x, so every load/store of a
+// warp is a contiguous 128 B line of one component plane; the +-1 / +-2 neighbours of the
+// stencils are served by L1/L2 (a row of the largest configured mesh is 16 KB).
+#include "common.cuh"
+#include "launch.h"
+
+namespace eb200 {
+  namespace EB200_VARIANT {
+
+    struct Box {
+      int n[3]; // active cells
+      int G;
+    };
+
+    // flat thread index -> active cell (ghost-inclusive coordinates)
+    template <int D>
+    __device__ __forceinline__ bool cell_of(const Box& b, long t, int& i, int& j, int& k) {
+      const long total = (long)b.n[0] * (D > 1 ? b.n[1] : 1) * (D > 2 ? b.n[2] : 1);
+      if (t >= total) return false;
+      i = (int)(t % b.n[0]) + b.G;
+      j = 0;
+      k = 0;
+      if constexpr (D > 1) {
+        const long r = t / b.n[0];
+        j            = (int)(r % b.n[1]) + b.G;
+        if constexpr (D > 2) {
+          k = (int)(r / b.n[1]) + b.G;
+        }
+      }
+      return true;
+    }
+
+    struct Stencil {
+      float dx, dy, bxy, byx, dz, bxz, bzx, byz, bzy;
+    };
+
+    /* ------------------------------------------------------------------ Faraday */
+    template <int D, bool EXT>
+    __global__ void __launch_bounds__(256)
+      faraday_kernel(Box box, FieldView<D> F, float coeff1, float coeff2, Stencil s) {
+      int i1, i2, i3;
+      if (!cell_of<D>(box, (long)blockIdx.x * blockDim.x + threadIdx.x, i1, i2, i3)) return;
+      auto EB = [&](int i, int j, int k, int c) -> float { return F.at(i, j, k, c); };
+      if constexpr (D == 1) {
+        if constexpr (EXT) {
+          const float ax = ONE - THREE * s.dx;
+          F.at(i1, 0, 0, bx2) += coeff1 * (+ax * (EB(i1 + 1, 0, 0, ex3) - EB(i1, 0, 0, ex3)) +
+                                           s.dx * (EB(i1 + 2, 0, 0, ex3) - EB(i1 - 1, 0, 0, ex3)));
+          F.at(i1, 0, 0, bx3) += coeff1 * (-ax * (EB(i1 + 1, 0, 0, ex2) - EB(i1, 0, 0, ex2)) -
+                                           s.dx * (EB(i1 + 2, 0, 0, ex2) - EB(i1 - 1, 0, 0, ex2)));
+        } else {
+          F.at(i1, 0, 0, bx2) += coeff1 * (EB(i1 + 1, 0, 0, ex3) - EB(i1, 0, 0, ex3));
+          F.at(i1, 0, 0, bx3) += coeff1 * (EB(i1, 0, 0, ex2) - EB(i1 + 1, 0, 0, ex2));
+        }
+      } else if constexpr (D == 2) {
+        if constexpr (EXT) {
+          const float ax = ONE - TWO * s.bxy - THREE * s.dx;
+          const float ay = ONE - TWO * s.byx - THREE * s.dy;
+          // clang-format off
+          F.at(i1, i2, 0, bx1) += coeff1 * (
+              - ay    * (EB(i1    , i2 + 1, 0, ex3) - EB(i1    , i2    , 0, ex3))
+              - s.dy  * (EB(i1    , i2 + 2, 0, ex3) - EB(i1    , i2 - 1, 0, ex3))
+              - s.byx * (EB(i1 + 1, i2 + 1, 0, ex3) - EB(i1 + 1, i2    , 0, ex3))
+              - s.byx * (EB(i1 - 1, i2 + 1, 0, ex3) - EB(i1 - 1, i2    , 0, ex3)));
+          F.at(i1, i2, 0, bx2) += coeff1 * (
+              + ax    * (EB(i1 + 1, i2    , 0, ex3) - EB(i1    , i2    , 0, ex3))
+              + s.dx  * (EB(i1 + 2, i2    , 0, ex3) - EB(i1 - 1, i2    , 0, ex3))
+              + s.bxy * (EB(i1 + 1, i2 + 1, 0, ex3) - EB(i1    , i2 + 1, 0, ex3))
+              + s.bxy * (EB(i1 + 1, i2 - 1, 0, ex3) - EB(i1    , i2 - 1, 0, ex3)));
+          F.at(i1, i2, 0, bx3) += coeff2 * (
+              + ay    * (EB(i1    , i2 + 1, 0, ex1) - EB(i1    , i2    , 0, ex1))
+              + s.dy  * (EB(i1    , i2 + 2, 0, ex1) - EB(i1    , i2 - 1, 0, ex1))
+              + s.byx * (EB(i1 + 1, i2 + 1, 0, ex1) - EB(i1 + 1, i2    , 0, ex1))
+              + s.byx * (EB(i1 - 1, i2 + 1, 0, ex1) - EB(i1 - 1, i2    , 0, ex1))
+              - ax    * (EB(i1 + 1, i2    , 0, ex2) - EB(i1    , i2    , 0, ex2))
+              - s.dx  * (EB(i1 + 2, i2    , 0, ex2) - EB(i1 - 1, i2    , 0, ex2))
+              - s.bxy * (EB(i1 + 1, i2 + 1, 0, ex2) - EB(i1    , i2 + 1, 0, ex2))
+              - s.bxy * (EB(i1 + 1, i2 - 1, 0, ex2) - EB(i1    , i2 - 1, 0, ex2)));
+          // clang-format on
+        } else {
+          const float e3  = EB(i1, i2, 0, ex3);
+          F.at(i1, i2, 0, bx1) += coeff1 * (e3 - EB(i1, i2 + 1, 0, ex3));
+          F.at(i1, i2, 0, bx2) += coeff1 * (EB(i1 + 1, i2, 0, ex3) - e3);
+          F.at(i1, i2, 0, bx3) += coeff2 * ((EB(i1, i2 + 1, 0, ex1) - EB(i1, i2, 0, ex1)) -
+                                            (EB(i1 + 1, i2, 0, ex2) - EB(i1, i2, 0, ex2)));
+        }
+      } else {
+        if constexpr (EXT) {
+          const float ax = ONE - TWO * s.bxy - TWO * s.bxz - THREE * s.dx;
+          const float ay = ONE - TWO * s.byx - TWO * s.byz - THREE * s.dy;
+          const float az = ONE - TWO * s.bzx - TWO * s.bzy - THREE * s.dz;
+          // clang-format off
+          F.at(i1, i2, i3, bx1) += coeff1 * (
+              + az    * (EB(i1    , i2    , i3 + 1, ex2) - EB(i1    , i2    , i3    , ex2))
+              + s.dz  * (EB(i1    , i2    , i3 + 2, ex2) - EB(i1    , i2    , i3 - 1, ex2))
+              + s.bzx * (EB(i1 + 1, i2    , i3 + 1, ex2) - EB(i1 + 1, i2    , i3    , ex2))
+              + s.bzx * (EB(i1 - 1, i2    , i3 + 1, ex2) - EB(i1 - 1, i2    , i3    , ex2))
+              + s.bzy * (EB(i1    , i2 + 1, i3 + 1, ex2) - EB(i1    , i2 + 1, i3    , ex2))
+              + s.bzy * (EB(i1    , i2 - 1, i3 + 1, ex2) - EB(i1    , i2 - 1, i3    , ex2))
+              - ay    * (EB(i1    , i2 + 1, i3    , ex3) - EB(i1    , i2    , i3    , ex3))
+              - s.dy  * (EB(i1    , i2 + 2, i3    , ex3) - EB(i1    , i2 - 1, i3    , ex3))
+              - s.byx * (EB(i1 + 1, i2 + 1, i3    , ex3) - EB(i1 + 1, i2    , i3    , ex3))
+              - s.byx * (EB(i1 - 1, i2 + 1, i3    , ex3) - EB(i1 - 1, i2    , i3    , ex3))
+              - s.byz * (EB(i1    , i2 + 1, i3 + 1, ex3) - EB(i1    , i2    , i3 + 1, ex3))
+              - s.byz * (EB(i1    , i2 + 1, i3 - 1, ex3) - EB(i1    , i2    , i3 - 1, ex3)));
+          F.at(i1, i2, i3, bx2) += coeff1 * (
+              + ax    * (EB(i1 + 1, i2    , i3    , ex3) - EB(i1    , i2    , i3    , ex3))
+              + s.dx  * (EB(i1 + 2, i2    , i3    , ex3) - EB(i1 - 1, i2    , i3    , ex3))
+              + s.bxy * (EB(i1 + 1, i2 + 1, i3    , ex3) - EB(i1    , i2 + 1, i3    , ex3))
+              + s.bxy * (EB(i1 + 1, i2 - 1, i3    , ex3) - EB(i1    , i2 - 1, i3    , ex3))
+              + s.bxz * (EB(i1 + 1, i2    , i3 + 1, ex3) - EB(i1    , i2    , i3 + 1, ex3))
+              + s.bxz * (EB(i1 + 1, i2    , i3 - 1, ex3) - EB(i1    , i2    , i3 - 1, ex3))
+              - az    * (EB(i1    , i2    , i3 + 1, ex1) - EB(i1    , i2    , i3    , ex1))
+              - s.dz  * (EB(i1    , i2    , i3 + 2, ex1) - EB(i1    , i2    , i3 - 1, ex1))
+              - s.bzx * (EB(i1 + 1, i2    , i3 + 1, ex1) - EB(i1 + 1, i2    , i3    , ex1))
+              - s.bzx * (EB(i1 - 1, i2    , i3 + 1, ex1) - EB(i1 - 1, i2    , i3    , ex1))
+              - s.bzy * (EB(i1    , i2 + 1, i3 + 1, ex1) - EB(i1    , i2 + 1, i3    , ex1))
+              - s.bzy * (EB(i1    , i2 - 1, i3 + 1, ex1) - EB(i1    , i2 - 1, i3    , ex1)));
+          F.at(i1, i2, i3, bx3) += coeff1 * (
+              + ay    * (EB(i1    , i2 + 1, i3    , ex1) - EB(i1    , i2    , i3    , ex1))
+              + s.dy  * (EB(i1    , i2 + 2, i3    , ex1) - EB(i1    , i2 - 1, i3    , ex1))
+              + s.byx * (EB(i1 + 1, i2 + 1, i3    , ex1) - EB(i1 + 1, i2    , i3    , ex1))
+              + s.byx * (EB(i1 - 1, i2 + 1, i3    , ex1) - EB(i1 - 1, i2    , i3    , ex1))
+              + s.byz * (EB(i1    , i2 + 1, i3 + 1, ex1) - EB(i1    , i2    , i3 + 1, ex1))
+              + s.byz * (EB(i1    , i2 + 1, i3 - 1, ex1) - EB(i1    , i2    , i3 - 1, ex1))
+              - ax    * (EB(i1 + 1, i2    , i3    , ex2) - EB(i1    , i2    , i3    , ex2))
+              - s.dx  * (EB(i1 + 2, i2    , i3    , ex2) - EB(i1 - 1, i2    , i3    , ex2))
+              - s.bxy * (EB(i1 + 1, i2 + 1, i3    , ex2) - EB(i1    , i2 + 1, i3    , ex2))
+              - s.bxy * (EB(i1 + 1, i2 - 1, i3    , ex2) - EB(i1    , i2 - 1, i3    , ex2))
+              - s.bxz * (EB(i1 + 1, i2    , i3 + 1, ex2) - EB(i1    , i2    , i3 + 1, ex2))
+              - s.bxz * (EB(i1 + 1, i2    , i3 - 1, ex2) - EB(i1    , i2    , i3 - 1, ex2)));
+          // clang-format on
+        } else {
+          const float e1 = EB(i1, i2, i3, ex1), e2 = EB(i1, i2, i3, ex2), e3 = EB(i1, i2, i3, ex3);
+          F.at(i1, i2, i3, bx1) += coeff1 * ((EB(i1, i2, i3 + 1, ex2) - e2) -
+                                             (EB(i1, i2 + 1, i3, ex3) - e3));
+          F.at(i1, i2, i3, bx2) += coeff1 * ((EB(i1 + 1, i2, i3, ex3) - e3) -
+                                             (EB(i1, i2, i3 + 1, ex1) - e1));
+          F.at(i1, i2, i3, bx3) += coeff1 * ((EB(i1, i2 + 1, i3, ex1) - e1) -
+                                             (EB(i1 + 1, i2, i3, ex2) - e2));
+        }
+      }
+    }
+
+    /* ------------------------------------------------------------------- Ampere */
+    template <int D>
+    __global__ void __launch_bounds__(256)
+      ampere_kernel(Box box, FieldView<D> F, float coeff1, float coeff2) {
+      int i1, i2, i3;
+      if (!cell_of<D>(box, (long)blockIdx.x * blockDim.x + threadIdx.x, i1, i2, i3)) return;
+      auto EB = [&](int i, int j, int k, int c) -> float { return F.at(i, j, k, c); };
+      if constexpr (D == 1) {
+        F.at(i1, 0, 0, ex2) += coeff1 * (EB(i1 - 1, 0, 0, bx3) - EB(i1, 0, 0, bx3));
+        F.at(i1, 0, 0, ex3) += coeff1 * (EB(i1, 0, 0, bx2) - EB(i1 - 1, 0, 0, bx2));
+      } else if constexpr (D == 2) {
+        F.at(i1, i2, 0, ex1) += coeff1 * (EB(i1, i2, 0, bx3) - EB(i1, i2 - 1, 0, bx3));
+        F.at(i1, i2, 0, ex2) += coeff1 * (EB(i1 - 1, i2, 0, bx3) - EB(i1, i2, 0, bx3));
+        F.at(i1, i2, 0, ex3) += coeff2 * (EB(i1, i2 - 1, 0, bx1) - EB(i1, i2, 0, bx1) +
+                                          EB(i1, i2, 0, bx2) - EB(i1 - 1, i2, 0, bx2));
+      } else {
+        F.at(i1, i2, i3, ex1) += coeff1 * (EB(i1, i2, i3 - 1, bx2) - EB(i1, i2, i3, bx2) +
+                                           EB(i1, i2, i3, bx3) - EB(i1, i2 - 1, i3, bx3));
+        F.at(i1, i2, i3, ex2) += coeff1 * (EB(i1 - 1, i2, i3, bx3) - EB(i1, i2, i3, bx3) +
+                                           EB(i1, i2, i3, bx1) - EB(i1, i2, i3 - 1, bx1));
+        F.at(i1, i2, i3, ex3) += coeff1 * (EB(i1, i2 - 1, i3, bx1) - EB(i1, i2, i3, bx1) +
+                                           EB(i1, i2, i3, bx2) - EB(i1 - 1, i2, i3, bx2));
+      }
+    }
+
+    template <int D>
+    __global__ void __launch_bounds__(256)
+      currents_ampere_kernel(Box box, FieldView<D> E, FieldView<D> J, float coeff, float ppc0) {
+      int i1, i2, i3;
+      if (!cell_of<D>(box, (long)blockIdx.x * blockDim.x + threadIdx.x, i1, i2, i3)) return;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float j = J.at(i1, i2, i3, c);
+        E.at(i1, i2, i3, c) += j * coeff;
+        J.at(i1, i2, i3, c) = j / ppc0;
+      }
+    }
+
+    /* ------------------------------------------------------------ binomial filter */
+    struct FilterBC {
+      bool cmin[3], cmax[3]; // conductor faces
+    };
+
+    template <int D>
+    __global__ void __launch_bounds__(256)
+      filter_kernel(Box box, FieldView<D> A, FieldView<D> B, FilterBC bc) {
+      int i1, i2, i3;
+      if (!cell_of<D>(box, (long)blockIdx.x * blockDim.x + threadIdx.x, i1, i2, i3)) return;
+      auto      buf = [&](int i, int j, int k, int c) -> float { return B.ld(i, j, k, c); };
+      const int G      = box.G;
+      const int i1_max = box.n[0] + G, i2_max = box.n[1] + G, i3_max = box.n[2] + G;
+      if constexpr (D == 1) {
+        if ((bc.cmin[0] && i1 == G) || (bc.cmax[0] && i1 == i1_max - 1)) {
+          const int s          = bc.cmin[0] ? (i1 + 1) : (i1 - 1);
+          A.at(i1, 0, 0, jx1) = (THREE * INV_4) * buf(i1, 0, 0, jx1) + (INV_4)*buf(s, 0, 0, jx1);
+        } else if ((bc.cmin[0] && i1 == G + 1) || (bc.cmax[0] && i1 == i1_max - 2)) {
+          const int s          = bc.cmin[0] ? (i1 + 1) : (i1 - 1);
+          A.at(i1, 0, 0, jx1) = INV_2 * buf(i1, 0, 0, jx1) +
+                                INV_4 * (buf(i1 - 1, 0, 0, jx1) + buf(i1 + 1, 0, 0, jx1));
+          A.at(i1, 0, 0, jx2) = (INV_2)*buf(i1, 0, 0, jx2) + (INV_4)*buf(s, 0, 0, jx2);
+          A.at(i1, 0, 0, jx3) = (INV_2)*buf(i1, 0, 0, jx3) + (INV_4)*buf(s, 0, 0, jx3);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            A.at(i1, 0, 0, c) = INV_2 * buf(i1, 0, 0, c) +
+                                INV_4 * (buf(i1 - 1, 0, 0, c) + buf(i1 + 1, 0, 0, c));
+          }
+        }
+      } else if constexpr (D == 2) {
+        auto F1 = [&](int c, int i, int j) {
+          return INV_2 * buf(i, j, 0, c) + INV_4 * (buf(i - 1, j, 0, c) + buf(i + 1, j, 0, c));
+        };
+        auto F2 = [&](int c, int i, int j) {
+          return INV_2 * buf(i, j, 0, c) + INV_4 * (buf(i, j - 1, 0, c) + buf(i, j + 1, 0, c));
+        };
+        if ((bc.cmin[0] && i1 == G) || (bc.cmax[0] && i1 == i1_max - 1)) {
+          const int s           = bc.cmin[0] ? (i1 + 1) : (i1 - 1);
+          A.at(i1, i2, 0, jx1) = (THREE * INV_4) * (F2(jx1, i1, i2)) + (INV_4) * (F2(jx1, s, i2));
+        } else if ((bc.cmin[0] && i1 == G + 1) || (bc.cmax[0] && i1 == i1_max - 2)) {
+          const int s           = bc.cmin[0] ? (i1 + 1) : (i1 - 1);
+          A.at(i1, i2, 0, jx1) = INV_2 * (F2(jx1, i1, i2)) +
+                                 INV_4 * ((F2(jx1, i1 - 1, i2)) + (F2(jx1, i1 + 1, i2)));
+          A.at(i1, i2, 0, jx2) = INV_2 * (F2(jx2, i1, i2)) + INV_4 * (F2(jx2, s, i2));
+          A.at(i1, i2, 0, jx3) = INV_2 * (F2(jx3, i1, i2)) + INV_4 * (F2(jx3, s, i2));
+        } else if ((bc.cmin[1] && i2 == G) || (bc.cmax[1] && i2 == i2_max - 1)) {
+          const int s           = bc.cmin[1] ? (i2 + 1) : (i2 - 1);
+          A.at(i1, i2, 0, jx2) = (THREE * INV_4) * (F1(jx2, i1, i2)) + (INV_4) * (F1(jx2, i1, s));
+        } else if ((bc.cmin[1] && i2 == G + 1) || (bc.cmax[1] && i2 == i2_max - 2)) {
+          const int s           = bc.cmin[1] ? (i2 + 1) : (i2 - 1);
+          A.at(i1, i2, 0, jx1) = INV_2 * (F1(jx1, i1, i2)) + INV_4 * (F1(jx1, i1, s));
+          A.at(i1, i2, 0, jx2) = INV_2 * (F1(jx2, i1, i2)) +
+                                 INV_4 * ((F1(jx2, i1, i2 - 1)) + (F1(jx2, i1, i2 + 1)));
+          A.at(i1, i2, 0, jx3) = INV_2 * (F1(jx3, i1, i2)) + INV_4 * (F1(jx3, i1, s));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            A.at(i1, i2, 0, c) =
+              INV_4 * buf(i1, i2, 0, c) +
+              INV_8 * (buf(i1 - 1, i2, 0, c) + buf(i1 + 1, i2, 0, c) + buf(i1, i2 - 1, 0, c) +
+                       buf(i1, i2 + 1, 0, c)) +
+              INV_16 * (buf(i1 - 1, i2 - 1, 0, c) + buf(i1 + 1, i2 + 1, 0, c) +
+                        buf(i1 - 1, i2 + 1, 0, c) + buf(i1 + 1, i2 - 1, 0, c));
+          }
+        }
+      } else {
+        auto F12 = [&](int c, int i, int j, int k) {
+          return INV_4 * buf(i, j, k, c) +
+                 INV_8 * (buf(i - 1, j, k, c) + buf(i + 1, j, k, c) + buf(i, j - 1, k, c) +
+                          buf(i, j + 1, k, c)) +
+                 INV_16 * (buf(i - 1, j - 1, k, c) + buf(i + 1, j + 1, k, c) +
+                           buf(i - 1, j + 1, k, c) + buf(i + 1, j - 1, k, c));
+        };
+        auto F23 = [&](int c, int i, int j, int k) {
+          return INV_4 * buf(i, j, k, c) +
+                 INV_8 * (buf(i, j - 1, k, c) + buf(i, j + 1, k, c) + buf(i, j, k - 1, c) +
+                          buf(i, j, k + 1, c)) +
+                 INV_16 * (buf(i, j - 1, k - 1, c) + buf(i, j + 1, k + 1, c) +
+                           buf(i, j - 1, k + 1, c) + buf(i, j + 1, k - 1, c));
+        };
+        auto F13 = [&](int c, int i, int j, int k) {
+          return INV_4 * buf(i, j, k, c) +
+                 INV_8 * (buf(i - 1, j, k, c) + buf(i + 1, j, k, c) + buf(i, j, k - 1, c) +
+                          buf(i, j, k + 1, c)) +
+                 INV_16 * (buf(i - 1, j, k - 1, c) + buf(i + 1, j, k + 1, c) +
+                           buf(i - 1, j, k + 1, c) + buf(i + 1, j, k - 1, c));
+        };
+        if ((bc.cmin[0] && i1 == G) || (bc.cmax[0] && i1 == i1_max - 1)) {
+          const int s            = bc.cmin[0] ? (i1 + 1) : (i1 - 1);
+          A.at(i1, i2, i3, jx1) = (THREE * INV_4) * (F23(jx1, i1, i2, i3)) +
+                                  (INV_4) * (F23(jx1, s, i2, i3));
+        } else if ((bc.cmin[0] && i1 == G + 1) || (bc.cmax[0] && i1 == i1_max - 2)) {
+          const int s            = bc.cmin[0] ? (i1 + 1) : (i1 - 1);
+          A.at(i1, i2, i3, jx1) = INV_2 * (F23(jx1, i1, i2, i3)) +
+                                  INV_4 * ((F23(jx1, i1 - 1, i2, i3)) + (F23(jx1, i1 + 1, i2, i3)));
+          A.at(i1, i2, i3, jx2) = INV_2 * (F23(jx2, i1, i2, i3)) + INV_4 * (F23(jx2, s, i2, i3));
+          A.at(i1, i2, i3, jx3) = INV_2 * (F23(jx3, i1, i2, i3)) + INV_4 * (F23(jx3, s, i2, i3));
+        } else if ((bc.cmin[1] && i2 == G) || (bc.cmax[1] && i2 == i2_max - 1)) {
+          const int s            = bc.cmin[1] ? (i2 + 1) : (i2 - 1);
+          A.at(i1, i2, i3, jx2) = (THREE * INV_4) * (F13(jx2, i1, i2, i3)) +
+                                  (INV_4) * (F13(jx2, i1, s, i3));
+        } else if ((bc.cmin[1] && i2 == G + 1) || (bc.cmax[1] && i2 == i2_max - 2)) {
+          const int s            = bc.cmin[1] ? (i2 + 1) : (i2 - 1);
+          A.at(i1, i2, i3, jx1) = INV_2 * (F13(jx1, i1, i2, i3)) + INV_4 * (F13(jx1, i1, s, i3));
+          A.at(i1, i2, i3, jx2) = INV_2 * (F13(jx2, i1, i2, i3)) +
+                                  INV_4 * ((F13(jx2, i1, i2 - 1, i3)) + (F13(jx2, i1, i2 + 1, i3)));
+          A.at(i1, i2, i3, jx3) = INV_2 * (F13(jx3, i1, i2, i3)) + INV_4 * (F13(jx3, i1, s, i3));
+        } else if ((bc.cmin[2] && i3 == G) || (bc.cmax[2] && i3 == i3_max - 1)) {
+          const int s            = bc.cmin[2] ? (i3 + 1) : (i3 - 1);
+          A.at(i1, i2, i3, jx3) = (THREE * INV_4) * (F12(jx3, i1, i2, i3)) +
+                                  (INV_4) * (F12(jx3, i1, i2, s));
+        } else if ((bc.cmin[2] && i3 == G + 1) || (bc.cmax[2] && i3 == i3_max - 2)) {
+          const int s            = bc.cmin[2] ? (i3 + 1) : (i3 - 1);
+          A.at(i1, i2, i3, jx1) = INV_2 * (F12(jx1, i1, i2, i3)) + INV_4 * (F12(jx1, i1, i2, s));
+          A.at(i1, i2, i3, jx2) = INV_2 * (F12(jx2, i1, i2, i3)) + INV_4 * (F12(jx2, i1, i2, s));
+          A.at(i1, i2, i3, jx3) = INV_2 * (F12(jx3, i1, i2, i3)) +
+                                  INV_4 * ((F12(jx3, i1, i2, i3 - 1)) + (F12(jx3, i1, i2, i3 + 1)));
+        } else {
+          // the 1/32 group repeats (0,0,-+1) where the (0,-+1,+-1) pair would be expected;
+          // that is what the reference computes (digital_filter.hpp:358-369)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            A.at(i1, i2, i3, c) =
+              INV_8 * buf(i1, i2, i3, c) +
+              INV_16 * (buf(i1 - 1, i2, i3, c) + buf(i1 + 1, i2, i3, c) + buf(i1, i2 - 1, i3, c) +
+                        buf(i1, i2 + 1, i3, c) + buf(i1, i2, i3 - 1, c) + buf(i1, i2, i3 + 1, c)) +
+              INV_32 * (buf(i1 - 1, i2 - 1, i3, c) + buf(i1 + 1, i2 + 1, i3, c) +
+                        buf(i1 - 1, i2 + 1, i3, c) + buf(i1 + 1, i2 - 1, i3, c) +
+                        buf(i1, i2 - 1, i3 - 1, c) + buf(i1, i2 + 1, i3 + 1, c) +
+                        buf(i1, i2, i3 - 1, c) + buf(i1, i2, i3 + 1, c) +
+                        buf(i1 - 1, i2, i3 - 1, c) + buf(i1 + 1, i2, i3 + 1, c) +
+                        buf(i1 - 1, i2, i3 + 1, c) + buf(i1 + 1, i2, i3 - 1, c)) +
+              INV_64 * (buf(i1 - 1, i2 - 1, i3 - 1, c) + buf(i1 + 1, i2 + 1, i3 + 1, c) +
+                        buf(i1 - 1, i2 + 1, i3 + 1, c) + buf(i1 + 1, i2 - 1, i3 - 1, c) +
+                        buf(i1 - 1, i2 - 1, i3 + 1, c) + buf(i1 + 1, i2 + 1, i3 - 1, c) +
+                        buf(i1 - 1, i2 + 1, i3 - 1, c) + buf(i1 + 1, i2 - 1, i3 + 1, c));
+          }
+        }
+      }
+    }
+
+    /* ------------------------------------------------- single-domain ghost exchange */
+    struct Periodic {
+      bool per[3];
+    };
+
+    // one thread per cell of the ghost-inclusive box; a ghost cell takes the value of its
+    // periodic image (an active cell) when every face it lies beyond is periodic
+    template <int D>
+    __global__ void __launch_bounds__(256)
+      ghost_fill_kernel(Box box, FieldView<D> F, int c0, int c1, Periodic per) {
+      const long t  = (long)blockIdx.x * blockDim.x + threadIdx.x;
+      const long N1 = F.N1, N2 = F.N2, N3 = F.N3;
+      if (t >= N1 * N2 * N3) return;
+      int x[3] = { (int)(t % N1), (int)((t / N1) % N2), (int)(t / (N1 * N2)) };
+      int s[3] = { x[0], x[1], x[2] };
+      bool ghost = false;
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        const int G = box.G, n = box.n[a];
+        if (x[a] < G) {
+          if (!per.per[a]) return;
+          s[a]  = x[a] + n;
+          ghost = true;
+        } else if (x[a] >= n + G) {
+          if (!per.per[a]) return;
+          s[a]  = x[a] - n;
+          ghost = true;
+        }
+      }
+      if (!ghost) return;
+      for (int c = c0; c < c1; ++c) {
+        F.at(x[0], x[1], x[2], c) = F.at(s[0], s[1], s[2], c);
+      }
+    }
+
+    // additive synchronisation of deposited currents: every active cell within G of a
+    // periodic face receives what was deposited into the image ghost/edge cells. The
+    // contributions are summed from zero in the reference's direction order (lexicographic
+    // over {-1,0,1}^D) and then added to the cell, reproducing buff-then-add exactly.
+    // All sources have at least one ghost coordinate, so the update is safe in place.
+    template <int D>
+    __global__ void __launch_bounds__(256)
+      sync_currents_kernel(Box box, FieldView<D> J, Periodic per) {
+      int x[3];
+      if (!cell_of<D>(box, (long)blockIdx.x * blockDim.x + threadIdx.x, x[0], x[1], x[2])) return;
+      const int G = box.G;
+      bool      lo[3] = { false, false, false }, hi[3] = { false, false, false };
+      bool      any   = false;
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        lo[a] = per.per[a] && (x[a] < 2 * G);
+        hi[a] = per.per[a] && (x[a] >= box.n[a]);
+        any   = any || lo[a] || hi[a];
+      }
+      if (!any) return;
+      float acc[3] = { ZERO, ZERO, ZERO };
+      constexpr int ND = (D == 1) ? 3 : ((D == 2) ? 9 : 27);
+      for (int lin = 0; lin < ND; ++lin) {
+        int  d[3] = { 0, 0, 0 };
+        int  r    = lin;
+        bool ok   = true, zero = true;
+#pragma unroll
+        for (int a = D - 1; a >= 0; --a) {
+          d[a] = (r % 3) - 1;
+          r   /= 3;
+        }
+        int s[3] = { x[0], x[1], x[2] };
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          if (d[a] == 1) {
+            ok   = ok && lo[a];
+            s[a] = x[a] + box.n[a];
+            zero = false;
+          } else if (d[a] == -1) {
+            ok   = ok && hi[a];
+            s[a] = x[a] - box.n[a];
+            zero = false;
+          }
+        }
+        if (zero || !ok) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          acc[c] += J.at(s[0], s[1], s[2], c);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        J.at(x[0], x[1], x[2], c) += acc[c];
+      }
+    }
+
+    /* ----------------------------------------------------------------- launchers */
+    static Box make_box(const eb200_grid_t& g) {
+      Box b;
+      b.n[0] = g.n[0];
+      b.n[1] = g.dim > 1 ? g.n[1] : 1;
+      b.n[2] = g.dim > 2 ? g.n[2] : 1;
+      b.G    = g.ng;
+      return b;
+    }
+
+    static unsigned blocks_for(long n) { return (unsigned)((n + 255) / 256); }
+
+    static long n_active(const eb200_grid_t& g) {
+      return (long)g.n[0] * (g.dim > 1 ? g.n[1] : 1) * (g.dim > 2 ? g.n[2] : 1);
+    }
+
+    static long n_total(const eb200_grid_t& g) {
+      long t = 1;
+      for (int a = 0; a < g.dim; ++a) t *= g.n[a] + 2 * g.ng;
+      return t;
+    }
+
+#define BY_DIM(g, CALL)                                                                        \
+  switch ((g).dim) {                                                                           \
+    case 1: CALL(1); break;                                                                    \
+    case 2: CALL(2); break;                                                                    \
+    case 3: CALL(3); break;                                                                    \
+    default: return cudaErrorInvalidValue;                                                     \
+  }
+
+    cudaError_t faraday(const eb200_grid_t& g, float* em, float c1, float c2,
+                        const float* st9, cudaStream_t st) {
+      Stencil s { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+      bool    ext = false;
+      if (st9) {
+        s = Stencil { st9[0], st9[1], st9[2], st9[3], st9[4], st9[5], st9[6], st9[7], st9[8] };
+        for (int q = 0; q < 9; ++q) ext = ext || (st9[q] != 0.0f);
+      }
+#if EB200_STRICT
+      ext = true; // keep the reference's full expression (signed zeros included)
+#endif
+      const Box  box = make_box(g);
+      const long n   = n_active(g);
+#define CALL(D)                                                                                \
+  if (ext)                                                                                     \
+    faraday_kernel<D, true><<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, em), c1, c2, s); \
+  else                                                                                         \
+    faraday_kernel<D, false><<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, em), c1, c2, s);
+      BY_DIM(g, CALL)
+#undef CALL
+      count_launch();
+      return cudaGetLastError();
+    }
+
+    cudaError_t ampere(const eb200_grid_t& g, float* em, float c1, float c2, cudaStream_t st) {
+      const Box  box = make_box(g);
+      const long n   = n_active(g);
+#define CALL(D) ampere_kernel<D><<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, em), c1, c2);
+      BY_DIM(g, CALL)
+#undef CALL
+      count_launch();
+      return cudaGetLastError();
+    }
+
+    cudaError_t currents_ampere(const eb200_grid_t& g, float* em, float* cur, float coeff,
+                                float ppc0, cudaStream_t st) {
+      const Box  box = make_box(g);
+      const long n   = n_active(g);
+#define CALL(D)                                                                                \
+  currents_ampere_kernel<D>                                                                    \
+    <<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, em), FieldView<D>(g, cur), coeff, ppc0);
+      BY_DIM(g, CALL)
+#undef CALL
+      count_launch();
+      return cudaGetLastError();
+    }
+
+    cudaError_t filter_pass(const eb200_grid_t& g, float* cur, const float* buff, const int* fbc,
+                            cudaStream_t st) {
+      const Box box = make_box(g);
+      FilterBC  bc;
+      for (int a = 0; a < 3; ++a) {
+        bc.cmin[a] = (a < g.dim) && fbc[2 * a] == EB200_FBC_CONDUCTOR;
+        bc.cmax[a] = (a < g.dim) && fbc[2 * a + 1] == EB200_FBC_CONDUCTOR;
+      }
+      const long n = n_active(g);
+#define CALL(D)                                                                                \
+  filter_kernel<D><<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, cur),                   \
+                                                  FieldView<D>(g, const_cast<float*>(buff)), bc);
+      BY_DIM(g, CALL)
+#undef CALL
+      count_launch();
+      return cudaGetLastError();
+    }
+
+    static Periodic periodic_of(const eb200_grid_t& g, const int* fbc) {
+      Periodic p;
+      for (int a = 0; a < 3; ++a) {
+        p.per[a] = (a < g.dim) && fbc[2 * a] == EB200_FBC_PERIODIC &&
+                   fbc[2 * a + 1] == EB200_FBC_PERIODIC;
+      }
+      return p;
+    }
+
+    cudaError_t comm_fields_self(const eb200_grid_t& g, float* fld, int c0, int c1,
+                                 const int* fbc, cudaStream_t st) {
+      const Box      box = make_box(g);
+      const Periodic per = periodic_of(g, fbc);
+      if (!(per.per[0] || per.per[1] || per.per[2])) return cudaSuccess;
+      const long n = n_total(g);
+#define CALL(D)                                                                                \
+  ghost_fill_kernel<D><<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, fld), c0, c1, per);
+      BY_DIM(g, CALL)
+#undef CALL
+      count_launch();
+      return cudaGetLastError();
+    }
+
+    cudaError_t sync_currents_self(const eb200_grid_t& g, float* cur, float* buff,
+                                   const int* fbc, cudaStream_t st) {
+      (void)buff; // the in-place kernel needs no staging buffer
+      const Box      box = make_box(g);
+      const Periodic per = periodic_of(g, fbc);
+      if (!(per.per[0] || per.per[1] || per.per[2])) return cudaSuccess;
+      const long n = n_active(g);
+#define CALL(D) sync_currents_kernel<D><<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, cur), per);
+      BY_DIM(g, CALL)
+#undef CALL
+      count_launch();
+      return cudaGetLastError();
+    }
+
+  } // namespace EB200_VARIANT
+} // namespace eb200

@@ -1,0 +1,69 @@
+// entity_b200 -- host-side declarations shared by the kernel translation units and capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/entity_b200.h"
+
+namespace eb200 {
+
+  // number of kernel launches issued by this library (eb200_launch_count)
+  void     count_launch();
+  uint64_t launches();
+
+  // grow-only device scratch owned by a context
+  struct Scratch {
+    void*  ptr   = nullptr;
+    size_t bytes = 0;
+
+    cudaError_t reserve(size_t n) {
+      if (n <= bytes) return cudaSuccess;
+      if (ptr) cudaFree(ptr);
+      ptr   = nullptr;
+      bytes = 0;
+      cudaError_t e = cudaMalloc(&ptr, n);
+      if (e == cudaSuccess) bytes = n;
+      return e;
+    }
+
+    void release() {
+      if (ptr) cudaFree(ptr);
+      ptr   = nullptr;
+      bytes = 0;
+    }
+  };
+
+#define EB200_DECLARE_VARIANT(NS)                                                              \
+  namespace NS {                                                                               \
+    cudaError_t push_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,            \
+                        const eb200_prtls_t& S, uint32_t npart, const float* em,               \
+                        cudaStream_t st);                                                      \
+    cudaError_t deposit(const eb200_grid_t& g, int order, const eb200_prtls_t& S,             \
+                        uint32_t npart, float charge, float dt, float dxc, float* cur,         \
+                        int mode, Scratch& scratch, cudaStream_t st);                          \
+    cudaError_t push_deposit_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,    \
+                                const eb200_prtls_t& S, uint32_t npart, const float* em,       \
+                                float* cur, cudaStream_t st);                                  \
+    cudaError_t faraday(const eb200_grid_t& g, float* em, float c1, float c2,                 \
+                        const float* stencil9, cudaStream_t st);                               \
+    cudaError_t ampere(const eb200_grid_t& g, float* em, float c1, float c2, cudaStream_t st); \
+    cudaError_t currents_ampere(const eb200_grid_t& g, float* em, float* cur, float coeff,    \
+                                float ppc0, cudaStream_t st);                                  \
+    cudaError_t filter_pass(const eb200_grid_t& g, float* cur, const float* buff,             \
+                            const int* fbc, cudaStream_t st);                                  \
+    cudaError_t comm_fields_self(const eb200_grid_t& g, float* fld, int c0, int c1,           \
+                                 const int* fbc, cudaStream_t st);                             \
+    cudaError_t sync_currents_self(const eb200_grid_t& g, float* cur, float* buff,            \
+                                   const int* fbc, cudaStream_t st);                           \
+  }
+
+  EB200_DECLARE_VARIANT(strict_fp)
+  EB200_DECLARE_VARIANT(fast_fp)
+
+  // variant-independent (integer / copy work): sort.cu
+  cudaError_t sort_particles(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
+                             uint32_t maxnpart, int remove_dead, uint32_t* n_alive_out,
+                             Scratch& scratch, cudaStream_t st);
+
+} // namespace eb200

@@ -1,0 +1,737 @@
+// entity_b200 -- per-particle device arithmetic of the SR pusher and the current deposit.
+//
+// Register-resident formulation: a particle is loaded once into a `Prtl` struct, pushed,
+// deposited and stored once. The arithmetic (operand order included) follows
+//   src/kernels/pushers/sr.hpp          (gather :851-1370, Boris :337-368, Vay :370-437,
+//                                        GCA :439-521, drag :1372-1424/:1487-1499,
+//                                        position push :526-572, boundaries :659-814)
+//   src/kernels/currents_deposit.hpp    (zig-zag :171-405, Esirkepov :406-754)
+//   src/kernels/particle_shapes.hpp     (order<> :544-613, for_deposit<> :934-1024)
+// so that the EB200_STRICT build reproduces the reference bit for bit.
+#pragma once
+#include "common.cuh"
+
+namespace eb200 {
+
+  template <int D>
+  struct Prtl {
+    int   i[3], ip[3];
+    float d[3], dp[3];
+    float u[3];
+    float w;
+    short tag;
+  };
+
+  /* ------------------------------------------------------------------ shapes */
+  __device__ __forceinline__ float S3(float x) {
+    if (x < ONE) {
+      return static_cast<float>(2.0 / 3.0) - SQR(x) + HALF * CUBE(x);
+    } else if (x < TWO) {
+      return static_cast<float>(4.0 / 3.0) - TWO * x + SQR(x) -
+             static_cast<float>(1.0 / 6.0) * CUBE(x);
+    }
+    return ZERO;
+  }
+
+  template <bool STAG, int O>
+  __device__ __forceinline__ void shape_w(int i, float di, int& i_min, float (&S)[O + 1]) {
+    static_assert(O >= 1 && O <= 3, "shape orders 1..3");
+    if constexpr (O == 1) {
+      if constexpr (!STAG) {
+        i_min = i;
+        S[0]  = ONE - di;
+        S[1]  = di;
+      } else {
+        const bool lo = di < HALF;
+        i_min         = lo ? i - 1 : i;
+        S[0]          = (lo ? HALF : THREE_HALFS) - di;
+        S[1]          = ONE - S[0];
+      }
+    } else if constexpr (O == 2) {
+      if constexpr (!STAG) {
+        if (di < HALF) {
+          i_min = i - 1;
+          S[0]  = HALF * SQR(HALF - di);
+          S[1]  = THREE_FOURTHS - SQR(di);
+        } else {
+          i_min = i;
+          S[0]  = HALF * SQR(THREE_HALFS - di);
+          S[1]  = THREE_FOURTHS - SQR(ONE - di);
+        }
+        S[2] = ONE - S[0] - S[1];
+      } else {
+        i_min = i - 1;
+        S[0]  = HALF * SQR(ONE - di);
+        S[2]  = HALF * SQR(di);
+        S[1]  = ONE - S[0] - S[2];
+      }
+    } else {
+      float base;
+      if constexpr (!STAG) {
+        i_min = i - 1;
+        base  = ONE + di;
+      } else {
+        const bool lo = di < HALF;
+        i_min         = lo ? i - 2 : i - 1;
+        base          = (lo ? 1.5f : HALF) + di;
+      }
+#pragma unroll
+      for (int n = 0; n < 4; n++) {
+        S[n] = S3(fabsf(base - static_cast<float>(n)));
+      }
+    }
+  }
+
+  // initial/final shape arrays aligned on a common (O+2)-wide window
+  template <int O>
+  __device__ __forceinline__ void deposit_shapes(int i_init, float di_init, int i_fin,
+                                                 float di_fin, int& i_min, int& i_max,
+                                                 float (&iS)[O + 2], float (&fS)[O + 2]) {
+    int   a_min, b_min;
+    float a[O + 1], b[O + 1];
+    shape_w<false, O>(i_init, di_init, a_min, a);
+    shape_w<false, O>(i_fin, di_fin, b_min, b);
+    const int sa = (a_min > b_min) ? 1 : 0; // shift of the initial shape inside the window
+    const int sb = (a_min < b_min) ? 1 : 0; // shift of the final shape
+    i_min        = (a_min < b_min) ? a_min : b_min;
+    i_max        = i_min + O + ((a_min != b_min) ? 1 : 0);
+#pragma unroll
+    for (int j = 0; j < O + 2; ++j) {
+      iS[j] = ZERO;
+      fS[j] = ZERO;
+    }
+#pragma unroll
+    for (int j = 0; j < O + 1; ++j) {
+      // static indexing in both branches keeps the arrays in registers
+      if (sa) {
+        iS[j + 1] = a[j];
+      } else {
+        iS[j] = a[j];
+      }
+      if (sb) {
+        fS[j + 1] = b[j];
+      } else {
+        fS[j] = b[j];
+      }
+    }
+  }
+
+  /* ---------------------------------------------------------------- vector ops */
+  __device__ __forceinline__ float dot3(const float* a, const float* b) {
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+  }
+
+  __device__ __forceinline__ float nsq(const float* a) { return dot3(a, a); }
+
+  __device__ __forceinline__ void cross3(const float* a, const float* b, float* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+  }
+
+  /* ------------------------------------------------------------------- gather */
+  // EM: callable (i, j, k, comp) -> float in ghost-inclusive indices.
+  template <int D, int O, class EM>
+  __device__ __forceinline__ void gather_fields(const EM& F, int ng, const Prtl<D>& P, float* e0,
+                                                float* b0) {
+    if constexpr (O == 0) {
+      // staggered multilinear interpolation; per axis a primal pair {1-d, d} at nodes
+      // (i, i+1) and a dual pair at nodes (i-1+ind, i+ind), ind = int(d + 1/2)
+      int   base[3] = { 0, 0, 0 }, dbase[3] = { 0, 0, 0 };
+      float wp[3][2], wd[3][2];
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        const int ind = static_cast<int>(P.d[a] + HALF);
+        base[a]       = P.i[a] + ng;
+        dbase[a]      = base[a] - 1 + ind;
+        wp[a][0]      = ONE - P.d[a];
+        wp[a][1]      = P.d[a];
+        wd[a][0]      = static_cast<float>(ind + 1) - (P.d[a] + HALF);
+        wd[a][1]      = ONE - wd[a][0];
+      }
+      // sx/sy/sz: which axes read the dual nodes; wy_dual: which x2 weights are applied.
+      // The reference weights Bx3 in 3D with the primal x2 pair (sr.hpp:1102-1116).
+      auto lerp = [&](int c, bool sx, bool sy, bool sz, bool wy_dual) -> float {
+        const int    i0 = sx ? dbase[0] : base[0];
+        const float* wx = sx ? wd[0] : wp[0];
+        if constexpr (D == 1) {
+          return F(i0, 0, 0, c) * wx[0] + F(i0 + 1, 0, 0, c) * wx[1];
+        } else if constexpr (D == 2) {
+          const int    j0  = sy ? dbase[1] : base[1];
+          const float* wy  = wy_dual ? wd[1] : wp[1];
+          const float  c00 = F(i0, j0, 0, c) * wx[0] + F(i0 + 1, j0, 0, c) * wx[1];
+          const float  c10 = F(i0, j0 + 1, 0, c) * wx[0] + F(i0 + 1, j0 + 1, 0, c) * wx[1];
+          return c00 * wy[0] + c10 * wy[1];
+        } else {
+          const int    j0  = sy ? dbase[1] : base[1];
+          const int    k0  = sz ? dbase[2] : base[2];
+          const float* wy  = wy_dual ? wd[1] : wp[1];
+          const float* wz  = sz ? wd[2] : wp[2];
+          const float  c00 = F(i0, j0, k0, c) * wx[0] + F(i0 + 1, j0, k0, c) * wx[1];
+          const float  c10 = F(i0, j0 + 1, k0, c) * wx[0] + F(i0 + 1, j0 + 1, k0, c) * wx[1];
+          const float  c0  = c00 * wy[0] + c10 * wy[1];
+          const float  c01 = F(i0, j0, k0 + 1, c) * wx[0] + F(i0 + 1, j0, k0 + 1, c) * wx[1];
+          const float  c11 = F(i0, j0 + 1, k0 + 1, c) * wx[0] +
+                            F(i0 + 1, j0 + 1, k0 + 1, c) * wx[1];
+          const float c1 = c01 * wy[0] + c11 * wy[1];
+          return c0 * wz[0] + c1 * wz[1];
+        }
+      };
+      e0[0] = lerp(ex1, true, false, false, false);
+      e0[1] = lerp(ex2, false, true, false, true);
+      e0[2] = lerp(ex3, false, false, true, false);
+      b0[0] = lerp(bx1, false, true, true, true);
+      b0[1] = lerp(bx2, true, false, true, false);
+      b0[2] = lerp(bx3, true, true, false, D != 3);
+    } else {
+      int   pmin[3] = { 0, 0, 0 }, dmin[3] = { 0, 0, 0 };
+      float Sp[3][O + 1], Sd[3][O + 1];
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        shape_w<false, O>(P.i[a] + ng, P.d[a], pmin[a], Sp[a]);
+        shape_w<true, O>(P.i[a] + ng, P.d[a], dmin[a], Sd[a]);
+      }
+      auto spline = [&](int c, bool sx, bool sy, bool sz) -> float {
+        const float* S1 = sx ? Sd[0] : Sp[0];
+        const int    m1 = sx ? dmin[0] : pmin[0];
+        if constexpr (D == 1) {
+          float r = ZERO;
+#pragma unroll
+          for (int a = 0; a < O + 1; a++) r += S1[a] * F(m1 + a, 0, 0, c);
+          return r;
+        } else if constexpr (D == 2) {
+          const float* S2 = sy ? Sd[1] : Sp[1];
+          const int    m2 = sy ? dmin[1] : pmin[1];
+          float        r  = ZERO;
+#pragma unroll
+          for (int b = 0; b < O + 1; b++) {
+            float c0 = ZERO;
+#pragma unroll
+            for (int a = 0; a < O + 1; a++) c0 += S1[a] * F(m1 + a, m2 + b, 0, c);
+            r += c0 * S2[b];
+          }
+          return r;
+        } else {
+          const float* S2 = sy ? Sd[1] : Sp[1];
+          const int    m2 = sy ? dmin[1] : pmin[1];
+          const float* S3w = sz ? Sd[2] : Sp[2];
+          const int    m3 = sz ? dmin[2] : pmin[2];
+          float        r  = ZERO;
+#pragma unroll
+          for (int q = 0; q < O + 1; q++) {
+            float c0 = ZERO;
+#pragma unroll
+            for (int b = 0; b < O + 1; b++) {
+              float c00 = ZERO;
+#pragma unroll
+              for (int a = 0; a < O + 1; a++) c00 += S1[a] * F(m1 + a, m2 + b, m3 + q, c);
+              c0 += c00 * S2[b];
+            }
+            r += c0 * S3w[q];
+          }
+          return r;
+        }
+      };
+      e0[0] = spline(ex1, true, false, false);
+      e0[1] = spline(ex2, false, true, false);
+      e0[2] = spline(ex3, false, false, true);
+      b0[0] = spline(bx1, false, true, true);
+      b0[1] = spline(bx2, true, false, true);
+      b0[2] = spline(bx3, true, true, false);
+    }
+  }
+
+  /* ---------------------------------------------------------- velocity updates */
+  __device__ __forceinline__ void boris(float ndh, float* u, float* e0, float* b0) {
+    float c = ndh;
+    e0[0] *= c;
+    e0[1] *= c;
+    e0[2] *= c;
+    float u0[3] = { u[0] + e0[0], u[1] + e0[1], u[2] + e0[2] };
+    c *= ONE / sqrtf(ONE + nsq(u0));
+    b0[0] *= c;
+    b0[1] *= c;
+    b0[2] *= c;
+    c = TWO / (ONE + nsq(b0));
+    float x[3], u1[3];
+    cross3(u0, b0, x);
+    u1[0] = (u0[0] + x[0]) * c;
+    u1[1] = (u0[1] + x[1]) * c;
+    u1[2] = (u0[2] + x[2]) * c;
+    cross3(u1, b0, x);
+    u[0] = u0[0] + (x[0] + e0[0]);
+    u[1] = u0[1] + (x[1] + e0[1]);
+    u[2] = u0[2] + (x[2] + e0[2]);
+  }
+
+  __device__ __forceinline__ void vay(float ndh, float* u, float* e0, float* b0) {
+    float c = ndh;
+    e0[0] *= c;
+    e0[1] *= c;
+    e0[2] *= c;
+    b0[0] *= c;
+    b0[1] *= c;
+    b0[2] *= c;
+    c = ONE / sqrtf(ONE + nsq(u));
+    float x[3];
+    cross3(u, b0, x);
+    const float u1[3] = { (u[0] + TWO * e0[0] + x[0] * c), (u[1] + TWO * e0[1] + x[1] * c),
+                          (u[2] + TWO * e0[2] + x[2] * c) };
+    c        = dot3(u1, b0);
+    float c2 = ONE + nsq(u1) - nsq(b0);
+    c        = ONE / sqrtf(INV_2 * (c2 + sqrtf(SQR(c2) + FOUR * (SQR(b0[0]) + SQR(b0[1]) +
+                                                              SQR(b0[2]) + SQR(c)))));
+    c2 = ONE / (ONE + SQR(b0[0] * c) + SQR(b0[1] * c) + SQR(b0[2] * c));
+    const float udb = dot3(u1, b0);
+    u[0] = c2 * (u1[0] + c * udb * (b0[0] * c) + u1[1] * b0[2] * c - u1[2] * b0[1] * c);
+    u[1] = c2 * (u1[1] + c * udb * (b0[1] * c) + u1[2] * b0[0] * c - u1[0] * b0[2] * c);
+    u[2] = c2 * (u1[2] + c * udb * (b0[2] * c) + u1[0] * b0[1] * c - u1[1] * b0[0] * c);
+  }
+
+  // guiding-centre update; `f0` may be null (no external force term)
+  __device__ __forceinline__ void gca(float ndh, float dt, float* u, const float* f0, float* e0,
+                                      float* b0) {
+    const float eb_sqr = nsq(e0) + nsq(b0);
+    float       wE[3];
+    cross3(e0, b0, wE);
+    wE[0] /= eb_sqr;
+    wE[1] /= eb_sqr;
+    wE[2] /= eb_sqr;
+    const float b_norm_inv = ONE / sqrtf(nsq(b0));
+    b0[0] *= b_norm_inv;
+    b0[1] *= b_norm_inv;
+    b0[2] *= b_norm_inv;
+    float upar = dot3(u, b0) + ndh * TWO * dot3(e0, b0);
+    if (f0 != nullptr) {
+      upar = upar + dt * dot3(f0, b0);
+    }
+    const float w2 = nsq(wE);
+    float       factor;
+    if (w2 < 0.01f) {
+      factor = ONE + w2 + TWO * SQR(w2) + FIVE * SQR(w2) * w2;
+    } else {
+      factor = (ONE - sqrtf(ONE - FOUR * w2)) / (TWO * w2);
+    }
+    const float vE[3] = { wE[0] * factor, wE[1] * factor, wE[2] * factor };
+    const float Gamma = sqrtf(ONE + SQR(upar)) / sqrtf(ONE - nsq(vE));
+    u[0]              = upar * b0[0] + vE[0] * Gamma;
+    u[1]              = upar * b0[1] + vE[1] * Gamma;
+    u[2]              = upar * b0[2] + vE[2] * Gamma;
+  }
+
+  __device__ __forceinline__ void synchrotron_drag(float coeff, float* u, float* up,
+                                                   const float* e0, const float* b0) {
+    float g = ONE / sqrtf(ONE + nsq(up));
+    up[0] *= g;
+    up[1] *= g;
+    up[2] *= g;
+    g                = SQR(ONE / g);
+    const float bde  = dot3(up, e0);
+    float       x[3], kap[3];
+    cross3(up, b0, x);
+    const float epb[3] = { e0[0] + x[0], e0[1] + x[1], e0[2] + x[2] };
+    cross3(epb, b0, kap);
+    kap[0] += bde * e0[0];
+    kap[1] += bde * e0[1];
+    kap[2] += bde * e0[2];
+    const float chi = nsq(epb) - SQR(bde);
+    u[0] += coeff * (kap[0] - g * up[0] * chi);
+    u[1] += coeff * (kap[1] - g * up[1] * chi);
+    u[2] += coeff * (kap[2] - g * up[2] * chi);
+  }
+
+  __device__ __forceinline__ void compton_drag(float coeff, float* u, float* up) {
+    float g = ONE / sqrtf(ONE + nsq(up));
+    up[0] *= g;
+    up[1] *= g;
+    up[2] *= g;
+    g = SQR(ONE / g);
+    u[0] -= coeff * g * up[0];
+    u[1] -= coeff * g * up[1];
+    u[2] -= coeff * g * up[2];
+  }
+
+  /* ------------------------------------------------------------- one full push */
+  struct PushArgs {
+    eb200_pusher_t c;
+    float          ndh; // 1/2 (q/m) omegaB0 dt  (sr.hpp:111)
+    int            ni[3];
+    int            ng;
+  };
+
+  template <int D, int O, class EM>
+  __device__ __forceinline__ void push_particle(const PushArgs& A, const EM& F, Prtl<D>& P) {
+    const eb200_pusher_t& c  = A.c;
+    const float           dt = c.dt;
+    bool                  massive = true;
+    if (c.pusher_flags == EB200_PUSHER_PHOTON) {
+      massive = false;
+    } else {
+      float ec[3], bc[3];
+      gather_fields<D, O>(F, A.ng, P, ec, bc);
+      // contravariant -> Cartesian: in-plane components scale with the cell size
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        ec[a] = ec[a] * c.dx;
+        bc[a] = bc[a] * c.dx;
+      }
+      float       fext[3] = { ZERO, ZERO, ZERO };
+      float       up[3] = { ZERO, ZERO, ZERO }, er[3] = { ZERO, ZERO, ZERO },
+            br[3]       = { ZERO, ZERO, ZERO };
+      const bool drag   = c.drag_flags != EB200_DRAG_NONE;
+      if (drag) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          er[a] = ec[a];
+          br[a] = bc[a];
+          up[a] = P.u[a];
+        }
+      }
+      if (c.has_atmosphere) {
+        const float gg[3] = { c.atm_gx1, c.atm_gx2, c.atm_gx3 };
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          const float xph = (static_cast<float>(P.i[a]) + P.d[a]) * c.dx + c.xmin[a];
+          const bool  on  = !(fabsf(gg[a]) <= 1.1920929e-07f) &&
+                          ((c.atm_ds < ZERO || xph <= c.atm_x_surf + c.atm_ds) &&
+                           (c.atm_ds > ZERO || xph >= c.atm_x_surf + c.atm_ds));
+          if (on) {
+            fext[a] += gg[a];
+          }
+        }
+      }
+      bool is_gca = false;
+      if (c.pusher_flags & EB200_PUSHER_GCA) {
+        const float E2 = nsq(ec), B2 = nsq(bc);
+        const float rL = sqrtf(ONE + nsq(P.u)) * dt / (TWO * fabsf(A.ndh) * sqrtf(B2));
+        is_gca = (B2 > ZERO) && (rL < c.gca_larmor_max) && ((E2 / B2) < c.gca_e_ovr_b_sqr_max);
+      }
+      if (is_gca) {
+        gca(A.ndh, dt, P.u, c.has_atmosphere ? fext : nullptr, ec, bc);
+      } else {
+        if (c.has_atmosphere) {
+          P.u[0] += HALF * dt * fext[0];
+          P.u[1] += HALF * dt * fext[1];
+          P.u[2] += HALF * dt * fext[2];
+        }
+        if (c.pusher_flags & EB200_PUSHER_BORIS) {
+          boris(A.ndh, P.u, ec, bc);
+        } else if (c.pusher_flags & EB200_PUSHER_VAY) {
+          vay(A.ndh, P.u, ec, bc);
+        }
+        if (c.has_atmosphere) {
+          P.u[0] += HALF * dt * fext[0];
+          P.u[1] += HALF * dt * fext[1];
+          P.u[2] += HALF * dt * fext[2];
+        }
+        if (drag) {
+          up[0] = HALF * (up[0] + P.u[0]);
+          up[1] = HALF * (up[1] + P.u[1]);
+          up[2] = HALF * (up[2] + P.u[2]);
+          if (c.drag_flags & EB200_DRAG_SYNCHROTRON) {
+            synchrotron_drag(c.sync_coeff, P.u, up, er, br);
+          }
+          if (c.drag_flags & EB200_DRAG_COMPTON) {
+            compton_drag(c.compton_coeff, P.u, up);
+          }
+        }
+      }
+    }
+    // Cartesian i+dx position update
+    const float g2 = massive ? (ONE + SQR(P.u[0]) + SQR(P.u[1]) + SQR(P.u[2]))
+                             : (SQR(P.u[0]) + SQR(P.u[1]) + SQR(P.u[2]));
+    const float dt_inv_energy = dt / sqrtf(g2);
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      P.ip[a]  = P.i[a];
+      P.dp[a]  = P.d[a];
+      float dx = P.d[a] + (P.u[a] / c.dx) * dt_inv_energy;
+      P.i[a]  += static_cast<int>(dx >= ONE) - static_cast<int>(dx < ZERO);
+      dx      -= static_cast<float>(dx >= ONE);
+      dx      += static_cast<float>(dx < ZERO);
+      P.d[a]   = dx;
+    }
+    // particle boundaries, then the migration tag
+    int lin = 0, centre = 0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const int ni  = A.ni[a];
+      bool      inv = false;
+      if (P.i[a] < 0) {
+        const int b = c.pbc[2 * a];
+        if (b == EB200_PBC_PERIODIC) {
+          P.i[a]  += ni;
+          P.ip[a] += ni;
+        } else if (b == EB200_PBC_ABSORB) {
+          P.tag = 0;
+        } else if (b == EB200_PBC_REFLECT || b == EB200_PBC_AXIS) {
+          P.i[a] = 0;
+          P.d[a] = ONE - P.d[a];
+          inv    = (b == EB200_PBC_REFLECT);
+        }
+      } else if (P.i[a] >= ni) {
+        const int b = c.pbc[2 * a + 1];
+        if (b == EB200_PBC_PERIODIC) {
+          P.i[a]  -= ni;
+          P.ip[a] -= ni;
+        } else if (b == EB200_PBC_ABSORB) {
+          P.tag = 0;
+        } else if (b == EB200_PBC_REFLECT || b == EB200_PBC_AXIS) {
+          P.i[a] = ni - 1;
+          P.d[a] = ONE - P.d[a];
+          inv    = (b == EB200_PBC_REFLECT);
+        }
+      }
+      if (inv) {
+        P.u[a] = -P.u[a];
+      }
+      const int dir = (P.i[a] < 0) ? 0 : ((P.i[a] >= ni) ? 2 : 1);
+      lin           = lin * 3 + dir;
+      centre        = centre * 3 + 1;
+    }
+    if (c.tag_outgoing && lin != centre) {
+      // mpi::SendTag: 2 + lexicographic index of the direction, null direction skipped
+      P.tag = static_cast<short>((2 + lin - (lin > centre ? 1 : 0)) * P.tag);
+    }
+  }
+
+  /* ------------------------------------------------------------------ deposit */
+  // SINK: callable (i, j, k, comp, value) in ghost-inclusive indices. Calls are issued in the
+  // reference's program order so that an order-preserving sink reproduces its sums exactly.
+  template <int D, int O, class SINK>
+  __device__ __forceinline__ void deposit_particle(const Prtl<D>& P, float charge, float inv_dt,
+                                                   float dxc, int G, SINK&& J) {
+    float vp[3];
+    {
+      vp[0] = (0 < D) ? P.u[0] / dxc : P.u[0];
+      vp[1] = (1 < D) ? P.u[1] / dxc : P.u[1];
+      vp[2] = (2 < D) ? P.u[2] / dxc : P.u[2];
+      const float inv_energy = ONE / sqrtf(ONE + nsq(P.u));
+      if (isnan(vp[2]) || isinf(vp[2])) {
+        vp[2] = ZERO;
+      }
+      vp[0] *= inv_energy;
+      vp[1] *= inv_energy;
+      vp[2] *= inv_energy;
+    }
+    const float coeff = P.w * charge;
+
+    if constexpr (O == 0) {
+      // zig-zag: the move is split at a relay point into one segment in the old cell
+      // (index 0) and one in the new cell (index 1)
+      float W[3][2], Fl[3][2];
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        const int   up = static_cast<int>(P.i[a] > P.ip[a]);
+        const float r  = static_cast<float>(P.i[a] == P.ip[a]) * (P.d[a] + P.dp[a]) * INV_2;
+        W[a][0]        = INV_2 * (r + P.dp[a] + static_cast<float>(up));
+        W[a][1]        = INV_2 * (P.d[a] + r + static_cast<float>(up + P.ip[a] - P.i[a]));
+        Fl[a][0]       = (static_cast<float>(up) + r - P.dp[a]) * coeff * inv_dt;
+        Fl[a][1] = (static_cast<float>(P.i[a] - P.ip[a] - up) + P.d[a] - r) * coeff * inv_dt;
+      }
+      if constexpr (D == 1) {
+        const int   a0 = P.ip[0] + G, a1 = P.i[0] + G;
+        const float F2 = HALF * vp[1] * coeff, F3 = HALF * vp[2] * coeff;
+        J(a0, 0, 0, jx1, Fl[0][0]);
+        J(a1, 0, 0, jx1, Fl[0][1]);
+        J(a0, 0, 0, jx2, F2 * (ONE - W[0][0]));
+        J(a0 + 1, 0, 0, jx2, F2 * W[0][0]);
+        J(a1, 0, 0, jx2, F2 * (ONE - W[0][1]));
+        J(a1 + 1, 0, 0, jx2, F2 * W[0][1]);
+        J(a0, 0, 0, jx3, F3 * (ONE - W[0][0]));
+        J(a0 + 1, 0, 0, jx3, F3 * W[0][0]);
+        J(a1, 0, 0, jx3, F3 * (ONE - W[0][1]));
+        J(a1 + 1, 0, 0, jx3, F3 * W[0][1]);
+      } else if constexpr (D == 2) {
+        const float F3 = HALF * vp[2] * coeff;
+        const int   ci[2] = { P.ip[0] + G, P.i[0] + G }, cj[2] = { P.ip[1] + G, P.i[1] + G };
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          J(ci[s], cj[s], 0, jx1, Fl[0][s] * (ONE - W[1][s]));
+          J(ci[s], cj[s] + 1, 0, jx1, Fl[0][s] * W[1][s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          J(ci[s], cj[s], 0, jx2, Fl[1][s] * (ONE - W[0][s]));
+          J(ci[s] + 1, cj[s], 0, jx2, Fl[1][s] * W[0][s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          J(ci[s], cj[s], 0, jx3, F3 * (ONE - W[0][s]) * (ONE - W[1][s]));
+          J(ci[s] + 1, cj[s], 0, jx3, F3 * W[0][s] * (ONE - W[1][s]));
+          J(ci[s], cj[s] + 1, 0, jx3, F3 * (ONE - W[0][s]) * W[1][s]);
+          J(ci[s] + 1, cj[s] + 1, 0, jx3, F3 * W[0][s] * W[1][s]);
+        }
+      } else {
+        const int ci[2] = { P.ip[0] + G, P.i[0] + G }, cj[2] = { P.ip[1] + G, P.i[1] + G },
+                  ck[2] = { P.ip[2] + G, P.i[2] + G };
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          J(ci[s], cj[s], ck[s], jx1, Fl[0][s] * (ONE - W[1][s]) * (ONE - W[2][s]));
+          J(ci[s], cj[s] + 1, ck[s], jx1, Fl[0][s] * W[1][s] * (ONE - W[2][s]));
+          J(ci[s], cj[s], ck[s] + 1, jx1, Fl[0][s] * (ONE - W[1][s]) * W[2][s]);
+          J(ci[s], cj[s] + 1, ck[s] + 1, jx1, Fl[0][s] * W[1][s] * W[2][s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          J(ci[s], cj[s], ck[s], jx2, Fl[1][s] * (ONE - W[0][s]) * (ONE - W[2][s]));
+          J(ci[s] + 1, cj[s], ck[s], jx2, Fl[1][s] * W[0][s] * (ONE - W[2][s]));
+          J(ci[s], cj[s], ck[s] + 1, jx2, Fl[1][s] * (ONE - W[0][s]) * W[2][s]);
+          J(ci[s] + 1, cj[s], ck[s] + 1, jx2, Fl[1][s] * W[0][s] * W[2][s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          J(ci[s], cj[s], ck[s], jx3, Fl[2][s] * (ONE - W[0][s]) * (ONE - W[1][s]));
+          J(ci[s] + 1, cj[s], ck[s], jx3, Fl[2][s] * W[0][s] * (ONE - W[1][s]));
+          J(ci[s], cj[s] + 1, ck[s], jx3, Fl[2][s] * (ONE - W[0][s]) * W[1][s]);
+          J(ci[s] + 1, cj[s] + 1, ck[s], jx3, Fl[2][s] * W[0][s] * W[1][s]);
+        }
+      }
+    } else {
+      // Esirkepov density decomposition on an (O+2)^D window
+      constexpr int N = O + 2;
+      float         iS1[N], fS1[N];
+      int           min1, max1;
+      deposit_shapes<O>(P.ip[0], P.dp[0], P.i[0], P.d[0], min1, max1, iS1, fS1);
+      const float Q = coeff * inv_dt;
+      if constexpr (D == 1) {
+        const float QV2 = coeff * vp[1], QV3 = coeff * vp[2];
+        min1 += G;
+        max1 += G;
+        const int d1 = max1 - min1;
+        float     acc = ZERO;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          acc = (i == 0) ? (-Q * (fS1[0] - iS1[0])) : (acc - Q * (fS1[i] - iS1[i]));
+          if (i < d1) J(min1 + i, 0, 0, jx1, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if (i <= d1) J(min1 + i, 0, 0, jx2, QV2 * (HALF * (fS1[i] + iS1[i])));
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if (i <= d1) J(min1 + i, 0, 0, jx3, QV3 * (HALF * (fS1[i] + iS1[i])));
+        }
+      } else if constexpr (D == 2) {
+        float iS2[N], fS2[N];
+        int   min2, max2;
+        deposit_shapes<O>(P.ip[1], P.dp[1], P.i[1], P.d[1], min2, max2, iS2, fS2);
+        const float QV3 = coeff * vp[2];
+        min1 += G;
+        min2 += G;
+        max1 += G;
+        max2 += G;
+        const int d1 = max1 - min1, d2 = max2 - min2;
+        // jx1: prefix sums along x1 for every x2 row of the window
+        {
+          float acc[N];
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              const float w = HALF * (fS1[i] - iS1[i]) * (fS2[j] + iS2[j]);
+              acc[j]        = (i == 0) ? (-Q * w) : (acc[j] - Q * w);
+              if (i < d1 && j <= d2) J(min1 + i, min2 + j, 0, jx1, acc[j]);
+            }
+          }
+        }
+        // jx2: prefix sums along x2
+        {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            float acc = ZERO;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              const float w = HALF * (fS1[i] + iS1[i]) * (fS2[j] - iS2[j]);
+              acc           = (j == 0) ? (-Q * w) : (acc - Q * w);
+              if (i <= d1 && j < d2) J(min1 + i, min2 + j, 0, jx2, acc);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            const float w = THIRD * (fS2[j] * (HALF * iS1[i] + fS1[i]) +
+                                     iS2[j] * (HALF * fS1[i] + iS1[i]));
+            if (i <= d1 && j <= d2) J(min1 + i, min2 + j, 0, jx3, QV3 * w);
+          }
+        }
+      } else {
+        float iS2[N], fS2[N], iS3[N], fS3[N];
+        int   min2, max2, min3, max3;
+        deposit_shapes<O>(P.ip[1], P.dp[1], P.i[1], P.d[1], min2, max2, iS2, fS2);
+        deposit_shapes<O>(P.ip[2], P.dp[2], P.i[2], P.d[2], min3, max3, iS3, fS3);
+        min1 += G;
+        min2 += G;
+        min3 += G;
+        max1 += G;
+        max2 += G;
+        max3 += G;
+        const int d1 = max1 - min1, d2 = max2 - min2, d3 = max3 - min3;
+        // jx1: running sum over i for each (j,k)
+        {
+          float acc[N][N];
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+#pragma unroll
+              for (int k = 0; k < N; ++k) {
+                const float w = THIRD * (fS1[i] - iS1[i]) *
+                                ((iS2[j] * iS3[k] + fS2[j] * fS3[k]) +
+                                 HALF * (iS3[k] * fS2[j] + iS2[j] * fS3[k]));
+                acc[j][k] = (i == 0) ? (-Q * w) : (acc[j][k] - Q * w);
+                if (i < d1 && j <= d2 && k <= d3) {
+                  J(min1 + i, min2 + j, min3 + k, jx1, acc[j][k]);
+                }
+              }
+            }
+          }
+        }
+        // jx2: running sum over j for each (i,k)
+        {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            float acc[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+#pragma unroll
+              for (int k = 0; k < N; ++k) {
+                const float w = THIRD * (fS2[j] - iS2[j]) *
+                                (iS1[i] * iS3[k] + fS1[i] * fS3[k] +
+                                 HALF * (iS3[k] * fS1[i] + iS1[i] * fS3[k]));
+                acc[k] = (j == 0) ? (-Q * w) : (acc[k] - Q * w);
+                if (i <= d1 && j < d2 && k <= d3) {
+                  J(min1 + i, min2 + j, min3 + k, jx2, acc[k]);
+                }
+              }
+            }
+          }
+        }
+        // jx3: running sum over k for each (i,j)
+        {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              float acc = ZERO;
+#pragma unroll
+              for (int k = 0; k < N; ++k) {
+                const float w = THIRD * (fS3[k] - iS3[k]) *
+                                (iS1[i] * iS2[j] + fS1[i] * fS2[j] +
+                                 HALF * (iS1[i] * fS2[j] + iS2[j] * fS1[i]));
+                acc = (k == 0) ? (-Q * w) : (acc - Q * w);
+                if (i <= d1 && j <= d2 && k < d3) {
+                  J(min1 + i, min2 + j, min3 + k, jx3, acc);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+} // namespace eb200

@@ -1,0 +1,151 @@
+// entity_b200 -- particle sorting / compaction (integer + copy work, one variant).
+//
+// Replaces Particles::SortSpatially and Particles::RemoveDead
+// (src/framework/containers/particles_sort.cpp:104-253, key: src/global/utils/sorting.h:120-133)
+// with one stable key-index radix sort followed by a gather of every SoA array through the
+// permutation. Differences by design: the key runs i1-fastest (the field layout, so that a warp
+// of consecutive particles touches consecutive field nodes), and the sort is stable, i.e.
+// deterministic, where the reference's atomic compaction is not.
+#include "common.cuh"
+#include "launch.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace eb200 {
+
+  template <int D>
+  __global__ void __launch_bounds__(256)
+    sort_keys_kernel(eb200_prtls_t S, uint32_t npart, int n1, int n2, int n3, uint32_t ncells,
+                     uint32_t* keys, uint32_t* idx, uint32_t* n_alive) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t       alive = 0;
+    if (p < npart) {
+      uint32_t key = ncells; // dead (or any non-alive tag) goes last
+      if (S.tag[p] == 1) {
+        alive = 1;
+        int i = min(max(S.i1[p], 0), n1 - 1);
+        key   = (uint32_t)i;
+        if constexpr (D > 1) {
+          int j = min(max(S.i2[p], 0), n2 - 1);
+          key  += (uint32_t)n1 * (uint32_t)j;
+          if constexpr (D > 2) {
+            int k = min(max(S.i3[p], 0), n3 - 1);
+            key  += (uint32_t)n1 * (uint32_t)n2 * (uint32_t)k;
+          }
+        }
+      }
+      keys[p] = key;
+      idx[p]  = p;
+    }
+    // block-aggregated count of alive particles
+    const uint32_t w = __reduce_add_sync(0xffffffffu, alive);
+    if ((threadIdx.x & 31) == 0 && w) {
+      atomicAdd(n_alive, w);
+    }
+  }
+
+  template <class T>
+  __global__ void __launch_bounds__(256)
+    gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t n,
+                  T* __restrict__ dst) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) {
+      dst[q] = src[perm[q]];
+    }
+  }
+
+  template <class T>
+  static void permute(T* arr, const uint32_t* perm, uint32_t n, void* tmp, cudaStream_t st) {
+    if (arr == nullptr || n == 0) return;
+    gather_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(arr, perm, n, (T*)tmp);
+    count_launch();
+    cudaMemcpyAsync(arr, tmp, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st);
+  }
+
+  cudaError_t sort_particles(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
+                             uint32_t maxnpart, int remove_dead, uint32_t* n_alive_out,
+                             Scratch& scratch, cudaStream_t st) {
+    (void)maxnpart;
+    if (n_alive_out) *n_alive_out = npart;
+    if (npart == 0) return cudaSuccess;
+    const int      n1 = g.n[0], n2 = g.dim > 1 ? g.n[1] : 1, n3 = g.dim > 2 ? g.n[2] : 1;
+    const uint64_t nc64 = (uint64_t)n1 * n2 * n3;
+    if (nc64 >= 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    const uint32_t ncells = (uint32_t)nc64;
+    int            bits   = 1;
+    while ((1ull << bits) <= ncells) ++bits;
+
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (uint32_t*)nullptr, (size_t)npart, 0,
+                                    bits, st);
+    const size_t n4  = ((size_t)npart * 4 + 255) / 256 * 256;
+    cudaError_t  err = scratch.reserve(5 * n4 + tmp_bytes + 512);
+    if (err != cudaSuccess) return err;
+    char*     base  = (char*)scratch.ptr;
+    uint32_t* k0    = (uint32_t*)(base);
+    uint32_t* k1    = (uint32_t*)(base + n4);
+    uint32_t* i0    = (uint32_t*)(base + 2 * n4);
+    uint32_t* perm  = (uint32_t*)(base + 3 * n4);
+    void*     tmp   = (void*)(base + 4 * n4);
+    uint32_t* count = (uint32_t*)(base + 5 * n4);
+    void*     cubws = (void*)(base + 5 * n4 + 256);
+
+    cudaMemsetAsync(count, 0, sizeof(uint32_t), st);
+    const unsigned nb = (npart + 255) / 256;
+    switch (g.dim) {
+      case 1:
+        sort_keys_kernel<1><<<nb, 256, 0, st>>>(S, npart, n1, n2, n3, ncells, k0, i0, count);
+        break;
+      case 2:
+        sort_keys_kernel<2><<<nb, 256, 0, st>>>(S, npart, n1, n2, n3, ncells, k0, i0, count);
+        break;
+      case 3:
+        sort_keys_kernel<3><<<nb, 256, 0, st>>>(S, npart, n1, n2, n3, ncells, k0, i0, count);
+        break;
+      default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    err = cub::DeviceRadixSort::SortPairs(cubws, tmp_bytes, k0, k1, i0, perm, (size_t)npart, 0,
+                                          bits, st);
+    if (err != cudaSuccess) return err;
+    count_launch();
+
+    permute(S.i1, perm, npart, tmp, st);
+    permute(S.dx1, perm, npart, tmp, st);
+    permute(S.i1_prev, perm, npart, tmp, st);
+    permute(S.dx1_prev, perm, npart, tmp, st);
+    if (g.dim > 1) {
+      permute(S.i2, perm, npart, tmp, st);
+      permute(S.dx2, perm, npart, tmp, st);
+      permute(S.i2_prev, perm, npart, tmp, st);
+      permute(S.dx2_prev, perm, npart, tmp, st);
+    }
+    if (g.dim > 2) {
+      permute(S.i3, perm, npart, tmp, st);
+      permute(S.dx3, perm, npart, tmp, st);
+      permute(S.i3_prev, perm, npart, tmp, st);
+      permute(S.dx3_prev, perm, npart, tmp, st);
+    }
+    permute(S.ux1, perm, npart, tmp, st);
+    permute(S.ux2, perm, npart, tmp, st);
+    permute(S.ux3, perm, npart, tmp, st);
+    permute(S.weight, perm, npart, tmp, st);
+    permute(S.tag, perm, npart, tmp, st);
+    if (S.phi) permute(S.phi, perm, npart, tmp, st);
+
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    if (remove_dead && n_alive_out) {
+      // the one host-visible result of this call: the new particle count
+      uint32_t h = 0;
+      err = cudaMemcpyAsync(&h, count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+      if (err != cudaSuccess) return err;
+      err = cudaStreamSynchronize(st);
+      if (err != cudaSuccess) return err;
+      *n_alive_out = h;
+    }
+    return cudaSuccess;
+  }
+
+} // namespace eb200

@@ -1,0 +1,264 @@
+"""ctypes binding of include/entity_b200.h. Device memory comes from torch tensors."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libentity_b200.so")
+
+PUSHER_NONE, PUSHER_PHOTON, PUSHER_BORIS, PUSHER_VAY, PUSHER_GCA = 0, 1, 2, 4, 8
+DRAG_NONE, DRAG_SYNCHROTRON, DRAG_COMPTON = 0, 1, 2
+PBC_NONE, PBC_PERIODIC, PBC_ABSORB, PBC_REFLECT, PBC_AXIS = 0, 1, 2, 3, 4
+FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC = 0, 1, 2, 3, 4
+DEPOSIT_ATOMIC, DEPOSIT_ORDERED = 0, 1
+
+PRTL_FIELDS = ["i1", "i2", "i3", "dx1", "dx2", "dx3", "ux1", "ux2", "ux3", "weight",
+               "i1_prev", "i2_prev", "i3_prev", "dx1_prev", "dx2_prev", "dx3_prev",
+               "tag", "pld_r", "pld_i", "phi"]
+
+
+class EB200Error(RuntimeError):
+    pass
+
+
+def nghosts_for(order: int) -> int:
+    """N_GHOSTS of the reference build (src/global/global.h:130-136)."""
+    return 2 if order == 0 else (order + 1) // 2 + 1
+
+
+class Grid(C.Structure):
+    _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("ng", C.c_int)]
+
+    @staticmethod
+    def make(n, ng):
+        g = Grid()
+        g.dim = len(n)
+        g.n = (C.c_int * 3)(*(list(n) + [1] * (3 - len(n))))
+        g.ng = ng
+        return g
+
+    def shape(self, ncomp):
+        ext = [self.n[a] + 2 * self.ng for a in range(self.dim)]
+        return (ncomp, *ext[::-1])
+
+
+class Prtls(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in PRTL_FIELDS]
+
+
+class Pusher(C.Structure):
+    _fields_ = [
+        ("pusher_flags", C.c_int), ("drag_flags", C.c_int),
+        ("mass", C.c_float), ("charge", C.c_float),
+        ("time", C.c_double),
+        ("dt", C.c_float), ("omegaB0", C.c_float),
+        ("gca_larmor_max", C.c_float), ("gca_e_ovr_b_sqr_max", C.c_float),
+        ("sync_coeff", C.c_float), ("compton_coeff", C.c_float),
+        ("has_atmosphere", C.c_int),
+        ("atm_gx1", C.c_float), ("atm_gx2", C.c_float), ("atm_gx3", C.c_float),
+        ("atm_x_surf", C.c_float), ("atm_ds", C.c_float),
+        ("pbc", C.c_int * 6),
+        ("tag_outgoing", C.c_int),
+        ("dx", C.c_float),
+        ("xmin", C.c_float * 3),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int), ("strict_fp", C.c_int),
+        ("grid", Grid), ("shape_order", C.c_int),
+        ("metric", C.c_int), ("metric_params", C.c_float * 8),
+        ("maxnpart", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load libentity_b200.so; there is no fallback when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m entity_b200.build` "
+            "(entity_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p = C.c_void_p, C.POINTER(C.c_int)
+    ctxp = C.c_void_p
+    lib.eb200_version.restype = C.c_int
+    lib.eb200_device_count.restype = C.c_int
+    lib.eb200_last_error.restype = C.c_char_p
+    lib.eb200_last_error.argtypes = [ctxp]
+    lib.eb200_launch_count.restype = C.c_uint64
+    lib.eb200_launch_count.argtypes = [ctxp]
+    lib.eb200_init.argtypes = [C.POINTER(Config), C.POINTER(ctxp)]
+    lib.eb200_finalize.argtypes = [ctxp]
+    lib.eb200_finalize.restype = None
+    lib.eb200_faraday.argtypes = [ctxp, vp, C.c_float, C.c_float, vp, vp]
+    lib.eb200_ampere.argtypes = [ctxp, vp, C.c_float, C.c_float, vp]
+    lib.eb200_currents_ampere.argtypes = [ctxp, vp, vp, C.c_float, C.c_float, vp]
+    lib.eb200_filter.argtypes = [ctxp, vp, vp, C.c_int, i32p, vp]
+    lib.eb200_push_sr.argtypes = [ctxp, C.POINTER(Pusher), C.POINTER(Prtls), C.c_uint32, vp, vp]
+    lib.eb200_deposit.argtypes = [ctxp, C.POINTER(Prtls), C.c_uint32, C.c_float, C.c_float, vp,
+                                  C.c_int, vp]
+    lib.eb200_push_deposit_sr.argtypes = [ctxp, C.POINTER(Pusher), C.POINTER(Prtls), C.c_uint32,
+                                          vp, vp, vp]
+    lib.eb200_zero_currents.argtypes = [ctxp, vp, vp]
+    lib.eb200_comm_fields.argtypes = [ctxp, vp, C.c_int, C.c_int, C.c_int, i32p, vp]
+    lib.eb200_sync_currents.argtypes = [ctxp, vp, vp, i32p, vp]
+    lib.eb200_sort_particles.argtypes = [ctxp, C.POINTER(Prtls), C.POINTER(C.c_uint32), C.c_int, vp]
+    for name in ("init", "faraday", "ampere", "currents_ampere", "filter", "push_sr", "deposit",
+                 "push_deposit_sr", "zero_currents", "comm_fields", "sync_currents",
+                 "sort_particles"):
+        getattr(lib, "eb200_" + name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    """Names the header declares (used by the CPU-side ABI test)."""
+    import re
+    hdr = os.path.join(os.path.dirname(HERE), "include", "entity_b200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(eb200_[a-z_0-9]+)\s*\(", txt)))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Context:
+    """One eb200 context (one local domain on one device)."""
+
+    def __init__(self, n, order=0, strict=False, device=0, dx=1.0, xmin=(0.0, 0.0, 0.0),
+                 ng=None, maxnpart=0):
+        self.lib = load()
+        self.order = order
+        self.grid = Grid.make(n, nghosts_for(order) if ng is None else ng)
+        cfg = Config()
+        cfg.device = device
+        cfg.strict_fp = int(strict)
+        cfg.grid = self.grid
+        cfg.shape_order = order
+        cfg.metric = 0
+        cfg.metric_params = (C.c_float * 8)(dx, *xmin, 0, 0, 0, 0)
+        cfg.maxnpart = maxnpart
+        self.dx = dx
+        self.xmin = tuple(xmin)
+        self.handle = C.c_void_p()
+        rc = self.lib.eb200_init(C.byref(cfg), C.byref(self.handle))
+        if rc != 0:
+            raise EB200Error(self.lib.eb200_last_error(None).decode())
+
+    def close(self):
+        if self.handle:
+            self.lib.eb200_finalize(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EB200Error(self.lib.eb200_last_error(self.handle).decode())
+
+    @property
+    def launch_count(self):
+        return int(self.lib.eb200_launch_count(self.handle))
+
+    @staticmethod
+    def _stream(stream):
+        if stream is None:
+            import torch
+            return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return C.c_void_p(stream)
+
+    def make_pusher(self, **kw) -> Pusher:
+        p = Pusher()
+        p.pusher_flags = kw.get("pusher_flags", PUSHER_BORIS)
+        p.drag_flags = kw.get("drag_flags", DRAG_NONE)
+        p.mass = kw.get("mass", 1.0)
+        p.charge = kw.get("charge", -1.0)
+        p.time = kw.get("time", 0.0)
+        p.dt = kw["dt"]
+        p.omegaB0 = kw.get("omegaB0", 1.0)
+        for k in ("gca_larmor_max", "gca_e_ovr_b_sqr_max", "sync_coeff", "compton_coeff",
+                  "atm_gx1", "atm_gx2", "atm_gx3", "atm_x_surf", "atm_ds"):
+            setattr(p, k, kw.get(k, 0.0))
+        p.has_atmosphere = kw.get("has_atmosphere", 0)
+        p.pbc = (C.c_int * 6)(*kw.get("pbc", [PBC_PERIODIC] * 6))
+        p.tag_outgoing = kw.get("tag_outgoing", 0)
+        p.dx = kw.get("dx", self.dx)
+        p.xmin = (C.c_float * 3)(*kw.get("xmin", self.xmin))
+        return p
+
+    @staticmethod
+    def prtls_struct(arrays: dict) -> Prtls:
+        s = Prtls()
+        for name in PRTL_FIELDS:
+            t = arrays.get(name)
+            setattr(s, name, _ptr(t) if t is not None and t.numel() else None)
+        return s
+
+    # -- field solvers
+    def faraday(self, em, coeff1, coeff2, stencil=None, stream=None):
+        st = None
+        if stencil is not None:
+            st = (C.c_float * 9)(*stencil)
+        self._check(self.lib.eb200_faraday(self.handle, _ptr(em), coeff1, coeff2,
+                                           C.cast(st, C.c_void_p) if st is not None else None,
+                                           self._stream(stream)))
+
+    def ampere(self, em, coeff1, coeff2, stream=None):
+        self._check(self.lib.eb200_ampere(self.handle, _ptr(em), coeff1, coeff2,
+                                          self._stream(stream)))
+
+    def currents_ampere(self, em, cur, coeff, ppc0, stream=None):
+        self._check(self.lib.eb200_currents_ampere(self.handle, _ptr(em), _ptr(cur), coeff, ppc0,
+                                                   self._stream(stream)))
+
+    def filter(self, cur, buff, nfilter, fbc, stream=None):
+        self._check(self.lib.eb200_filter(self.handle, _ptr(cur), _ptr(buff), nfilter,
+                                          (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    # -- particles
+    def push(self, pusher, arrays, npart, em, stream=None):
+        s = self.prtls_struct(arrays)
+        self._check(self.lib.eb200_push_sr(self.handle, C.byref(pusher), C.byref(s), npart,
+                                           _ptr(em), self._stream(stream)))
+
+    def deposit(self, arrays, npart, charge, dt, cur, mode=DEPOSIT_ATOMIC, stream=None):
+        s = self.prtls_struct(arrays)
+        self._check(self.lib.eb200_deposit(self.handle, C.byref(s), npart, charge, dt, _ptr(cur),
+                                           mode, self._stream(stream)))
+
+    def push_deposit(self, pusher, arrays, npart, em, cur, stream=None):
+        s = self.prtls_struct(arrays)
+        self._check(self.lib.eb200_push_deposit_sr(self.handle, C.byref(pusher), C.byref(s),
+                                                   npart, _ptr(em), _ptr(cur),
+                                                   self._stream(stream)))
+
+    def zero_currents(self, cur, stream=None):
+        self._check(self.lib.eb200_zero_currents(self.handle, _ptr(cur), self._stream(stream)))
+
+    def comm_fields(self, fld, c0, c1, fbc, stream=None):
+        self._check(self.lib.eb200_comm_fields(self.handle, _ptr(fld), fld.shape[0], c0, c1,
+                                               (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    def sync_currents(self, cur, buff, fbc, stream=None):
+        self._check(self.lib.eb200_sync_currents(self.handle, _ptr(cur), _ptr(buff),
+                                                 (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    def sort_particles(self, arrays, npart, remove_dead=False, stream=None):
+        s = self.prtls_struct(arrays)
+        n = C.c_uint32(npart)
+        self._check(self.lib.eb200_sort_particles(self.handle, C.byref(s), C.byref(n),
+                                                  int(remove_dead), self._stream(stream)))
+        return int(n.value)

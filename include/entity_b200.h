@@ -1,0 +1,190 @@
+/*
+ * entity_b200 -- C ABI of the B200-native PIC timestep hot path.
+ *
+ * One entry point per dispatcher of the reference's engine layer, i.e. what a
+ * maintainer binds in place of the Kokkos functors of src/kernels (see
+ * INTEGRATION.md for the shim that replaces the bodies of ntt::srpic::* with
+ * these calls). Plain pointers and sizes only; no torch / Kokkos types.
+ *
+ * Conventions
+ *  - All array arguments are DEVICE pointers unless the name ends in `_host`.
+ *  - Fields: fp32, extents (n_d + 2*ng) per simulated dimension, i1 fastest,
+ *    then i2, i3; the component index is slowest ("component planes"). This is
+ *    Kokkos LayoutLeft, the layout of the reference's CUDA build for
+ *    ndfield_t<D,N> (src/global/arch/kokkos_aliases.h:83-105,
+ *    src/framework/containers/fields.h:38-108).
+ *  - Particles: SoA; eb200_prtls_t lists the arrays in the member order of
+ *    ntt::ParticleArrays (src/framework/containers/particles.h:47-71).
+ *  - `stream` is a cudaStream_t passed as void*; every call only enqueues work
+ *    on it and never synchronises the device, except where a host-visible value
+ *    is returned (particle counts after sort / migration), mirroring
+ *    SURVEY.md section 8b "Threading".
+ *  - Return value: 0 on success, non-zero on error; eb200_last_error() gives
+ *    the message (reference: raise::Error / Kokkos::abort, src/global/utils/error.h).
+ *  - There is no CPU fallback: every call fails with EB200_ERR_NO_DEVICE when
+ *    no CUDA device is usable.
+ */
+#ifndef ENTITY_B200_H
+#define ENTITY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EB200_VERSION 100
+
+enum {
+  EB200_OK            = 0,
+  EB200_ERR_ARG       = 1,
+  EB200_ERR_CUDA      = 2,
+  EB200_ERR_NO_DEVICE = 3,
+  EB200_ERR_CAPACITY  = 4, /* npart + nrecv >= maxnpart: particles_comm.cpp:219-221 */
+  EB200_ERR_UNSUPPORTED = 5,
+  EB200_ERR_NCCL      = 6
+};
+
+/* ntt::ParticlePusher flags, src/global/enums.h:317-324 */
+enum { EB200_PUSHER_NONE = 0, EB200_PUSHER_PHOTON = 1, EB200_PUSHER_BORIS = 2, EB200_PUSHER_VAY = 4, EB200_PUSHER_GCA = 8 };
+/* ntt::RadiativeDrag flags, src/global/enums.h:351-356 */
+enum { EB200_DRAG_NONE = 0, EB200_DRAG_SYNCHROTRON = 1, EB200_DRAG_COMPTON = 2 };
+/* particle boundary per face; what kernel::sr::PusherBoundaries distinguishes
+ * (src/kernels/pushers/context.h:124-178). NONE = SYNC/other: particle leaves, gets a send tag. */
+enum { EB200_PBC_NONE = 0, EB200_PBC_PERIODIC = 1, EB200_PBC_ABSORB = 2, EB200_PBC_REFLECT = 3, EB200_PBC_AXIS = 4 };
+/* field boundary per face, as far as filter and ghost exchange need it (ntt::FldsBC) */
+enum { EB200_FBC_NONE = 0, EB200_FBC_PERIODIC = 1, EB200_FBC_CONDUCTOR = 2, EB200_FBC_AXIS = 3, EB200_FBC_SYNC = 4 };
+enum { EB200_METRIC_MINKOWSKI = 0 };
+/* deposit modes */
+enum { EB200_DEPOSIT_ATOMIC = 0, EB200_DEPOSIT_ORDERED = 1 };
+
+typedef struct eb200_ctx eb200_ctx_t;
+typedef void*            eb200_stream_t;
+
+/* local (per-domain) mesh: Mesh::n_active + N_GHOSTS (src/global/global.h:130-136) */
+typedef struct {
+  int dim;  /* 1, 2, 3 */
+  int n[3]; /* active cells per dimension; unused dimensions = 1 */
+  int ng;   /* ghost cells per side */
+} eb200_grid_t;
+
+/* raw device pointers in the order of ntt::ParticleArrays (particles.h:53-70) */
+typedef struct {
+  int*      i1;
+  int*      i2;
+  int*      i3;
+  float*    dx1;
+  float*    dx2;
+  float*    dx3;
+  float*    ux1;
+  float*    ux2;
+  float*    ux3;
+  float*    weight;
+  int*      i1_prev;
+  int*      i2_prev;
+  int*      i3_prev;
+  float*    dx1_prev;
+  float*    dx2_prev;
+  float*    dx3_prev;
+  short*    tag;
+  float*    pld_r; /* [npart][npld_r], may be NULL */
+  uint32_t* pld_i; /* [npart][npld_i], may be NULL */
+  float*    phi;   /* 2D non-Cartesian only, may be NULL */
+} eb200_prtls_t;
+
+/* scalar arguments of kernel::sr::Pusher_kernel: PusherContext + PusherBoundaries
+ * (src/kernels/pushers/context.h:74-178), filled by the host exactly like
+ * srpic::ParticlePush does (src/engines/srpic/particle_pusher.h:36-150). */
+typedef struct {
+  int    pusher_flags;
+  int    drag_flags;
+  float  mass, charge;
+  double time;
+  float  dt, omegaB0;
+  float  gca_larmor_max, gca_e_ovr_b_sqr_max;
+  float  sync_coeff, compton_coeff;
+  int    has_atmosphere;
+  float  atm_gx1, atm_gx2, atm_gx3, atm_x_surf, atm_ds;
+  int    pbc[6];       /* EB200_PBC_* for i1min,i1max,i2min,i2max,i3min,i3max */
+  int    tag_outgoing; /* 1: tag leaving particles with mpi::SendTag (mpi_tags.h:175-233) */
+  float  dx;           /* Minkowski cell size (metric::Minkowski::dx) */
+  float  xmin[3];      /* Minkowski x*_min */
+} eb200_pusher_t;
+
+typedef struct {
+  int          device;      /* CUDA device ordinal */
+  int          strict_fp;   /* 1: kernels built without FMA contraction (bit-exact with the
+                               reference's baseline CPU build); 0: contraction allowed */
+  eb200_grid_t grid;        /* local mesh */
+  int          shape_order; /* SHAPE_ORDER of the reference build: 0 (zig-zag), 1..3 (Esirkepov) */
+  int          metric;      /* EB200_METRIC_* */
+  float        metric_params[8]; /* Minkowski: dx, x1min, x2min, x3min */
+  uint32_t     maxnpart;    /* capacity of each particle array handed to this context */
+} eb200_config_t;
+
+/* ------------------------------------------------------------------ lifetime */
+int         eb200_version(void);
+int         eb200_device_count(void);
+int         eb200_init(const eb200_config_t* cfg, eb200_ctx_t** out);
+void        eb200_finalize(eb200_ctx_t* ctx);
+const char* eb200_last_error(const eb200_ctx_t* ctx); /* ctx may be NULL: last global error */
+/* number of kernels this library has launched since eb200_init (bench.py's gpu_launches) */
+uint64_t    eb200_launch_count(const eb200_ctx_t* ctx);
+
+/* ------------------------------------------------------------- field solvers */
+/* replaces kernel::mink::Faraday_kernel as launched by srpic::Faraday
+ * (src/engines/srpic/fieldsolvers.h:36-98, src/kernels/faraday_mink.hpp:71-166).
+ * stencil9 = {delta_x, delta_y, beta_xy, beta_yx, delta_z, beta_xz, beta_zx, beta_yz, beta_zy}
+ * (host pointer, may be NULL = all zero). */
+int eb200_faraday(eb200_ctx_t* ctx, float* em, float coeff1, float coeff2,
+                  const float* stencil9_host, eb200_stream_t stream);
+/* kernel::mink::Ampere_kernel / srpic::Ampere (fieldsolvers.h:101-139, ampere_mink.hpp:48-89) */
+int eb200_ampere(eb200_ctx_t* ctx, float* em, float coeff1, float coeff2, eb200_stream_t stream);
+/* kernel::mink::CurrentsAmpere_kernel without ext. current / srpic::CurrentsAmpere
+ * (fieldsolvers.h:142-199, ampere_mink.hpp:134-215): E += J*coeff; J /= ppc0 */
+int eb200_currents_ampere(eb200_ctx_t* ctx, float* em, float* cur, float coeff, float ppc0,
+                          eb200_stream_t stream);
+/* srpic::CurrentsFilter (src/engines/srpic/currents.h:89-119): nfilter x { buff = cur;
+ * DigitalFilter_kernel (digital_filter.hpp:99-388, Cartesian); ghost exchange of J }.
+ * fbc_host[6] = EB200_FBC_* per face. */
+int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const int* fbc_host,
+                 eb200_stream_t stream);
+
+/* ------------------------------------------------------------------ particles */
+/* srpic::ParticlePush for one species (particle_pusher.h:36-185, sr.hpp:117-332) */
+int eb200_push_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher, const eb200_prtls_t* prtls,
+                  uint32_t npart, const float* em, eb200_stream_t stream);
+/* one species of srpic::CurrentsDeposit (currents.h:32-62, currents_deposit.hpp:108-761):
+ * accumulates into cur (the caller zeroes it once per step with eb200_zero_currents, as
+ * currents.h:67 does). mode = EB200_DEPOSIT_ATOMIC | EB200_DEPOSIT_ORDERED; ORDERED sums every
+ * J element in particle order (the reference's Serial-backend order) and is bit-reproducible. */
+int eb200_deposit(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, float charge,
+                  float dt, float* cur, int mode, eb200_stream_t stream);
+/* fused ParticlePush + CurrentsDeposit of one species in a single pass over the particles */
+int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
+                          const eb200_prtls_t* prtls, uint32_t npart, const float* em, float* cur,
+                          eb200_stream_t stream);
+int eb200_zero_currents(eb200_ctx_t* ctx, float* cur, eb200_stream_t stream);
+
+/* ------------------------------------------------- single-domain ghost exchange */
+/* Metadomain::CommunicateFields for a domain that is its own periodic neighbour
+ * (metadomain_comm.cpp:205-367 + comm_nompi.hpp:29-119): ghost fill of components [c0,c1). */
+int eb200_comm_fields(eb200_ctx_t* ctx, float* fld, int ncomp, int c0, int c1,
+                      const int* fbc_host, eb200_stream_t stream);
+/* Metadomain::SynchronizeFields(Comm::J) (metadomain_comm.cpp:409-562): additive sync of the
+ * 2*ng wide boundary strips through buff, then cur += buff on active cells. */
+int eb200_sync_currents(eb200_ctx_t* ctx, float* cur, float* buff, const int* fbc_host,
+                        eb200_stream_t stream);
+
+/* ------------------------------------------------------------- sort / compaction */
+/* Particles::SortSpatially (particles_sort.cpp:197-253): stable sort by cell index
+ * (i1 fastest, matching the field layout), dead particles moved to the end.
+ * Particles::RemoveDead (particles_sort.cpp:104-194) is the same call with
+ * remove_dead = 1: *npart_inout_host becomes the number of alive particles. */
+int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls,
+                         uint32_t* npart_inout_host, int remove_dead, eb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENTITY_B200_H */

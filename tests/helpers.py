@@ -75,3 +75,45 @@ def assert_bits_equal(x, y, what=""):
         raise AssertionError(
             f"{what}: {bad.shape[0]} of {x.size} entries differ; first at {bad[:3].tolist()} "
             f"max abs diff {np.max(np.abs(x.astype(np.float64) - y.astype(np.float64))):.3e}")
+
+
+# ------------------------------------------------------------------ torch <-> numpy bridges
+def to_device(p, device="cuda"):
+    """ParticleSet (numpy) -> dict of torch tensors on the device."""
+    import torch
+    out = {}
+    for nm in p.names():
+        out[nm] = torch.from_numpy(getattr(p, nm).copy()).to(device)
+    return out
+
+
+def to_host(arrays, n):
+    """dict of torch tensors -> ParticleSet (numpy)."""
+    p = orc.ParticleSet(n)
+    for nm in p.names():
+        getattr(p, nm)[:] = arrays[nm][:n].cpu().numpy()
+    return p
+
+
+def values_equal(x, y):
+    """Exact value equality (NaN == NaN; +0 == -0)."""
+    return np.array_equal(x, y, equal_nan=True)
+
+
+def assert_values_equal(x, y, what=""):
+    if not values_equal(x, y):
+        bad = np.argwhere(~((x == y) | (np.isnan(x) & np.isnan(y))))
+        d = np.abs(x.astype(np.float64) - y.astype(np.float64))
+        raise AssertionError(
+            f"{what}: {bad.shape[0]} of {x.size} entries differ; first at {bad[:3].tolist()}, "
+            f"max abs diff {np.nanmax(d):.3e}")
+
+
+def assert_prtls_values_equal(a, b, what=""):
+    for nm in a.names():
+        x, y = getattr(a, nm), getattr(b, nm)
+        if not values_equal(x, y):
+            bad = np.nonzero(x != y)[0]
+            raise AssertionError(
+                f"{what}: particle array {nm} differs at {bad.size} entries, "
+                f"first {bad[:5]}: {x[bad[:5]]} vs {y[bad[:5]]}")

@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA library (through its C ABI) against the CPU oracle on the same
+seeded inputs. Strict-fp contexts must match exactly (bit-exact up to the sign of zero);
+fast-fp contexts (FMA contraction, atomic deposit) within the tolerances written below."""
+import numpy as np
+import pytest
+
+from helpers import (assert_prtls_values_equal, assert_values_equal, random_fields,
+                     random_particles, smooth_fields, to_device, to_host)
+
+pytestmark = pytest.mark.gpu
+
+DIMS = {1: (37,), 2: (23, 17), 3: (11, 9, 13)}
+
+# fp32 tolerances of the fast (FMA-contracted) build against the oracle
+RTOL_FAST = 2e-5
+ATOL_FAST = 2e-6
+
+
+@pytest.fixture(scope="module")
+def eb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import entity_b200
+    return entity_b200
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(a.copy()).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("stencil", [None, "ext"])
+def test_field_solvers(eb, orc_mod, dim, stencil, strict):
+    orc = orc_mod.oracle()
+    g = orc_mod.Grid.make(DIMS[dim], 2)
+    ctx = eb.Context(DIMS[dim], order=0, strict=strict)
+    st = None
+    if stencil:
+        st = [0.01, 0.02, 0.03, 0.015, 0.012, 0.022, 0.011, 0.017, 0.019]
+    em = random_fields(g, 6, 1)
+    cur = random_fields(g, 3, 2)
+    d_em, d_cur = dev(em), dev(cur)
+    orc.faraday(g, em, 0.21, 0.37, st)
+    ctx.faraday(d_em, 0.21, 0.37, st)
+    orc.ampere(g, em, 0.45, 0.4)
+    ctx.ampere(d_em, 0.45, 0.4)
+    orc.currents_ampere(g, em, cur, -0.013, 16.0)
+    ctx.currents_ampere(d_em, d_cur, -0.013, 16.0)
+    if strict:
+        assert_values_equal(host(d_em), em, "em")
+        assert_values_equal(host(d_cur), cur, "cur")
+    else:
+        np.testing.assert_allclose(host(d_em), em, rtol=RTOL_FAST, atol=ATOL_FAST)
+        np.testing.assert_allclose(host(d_cur), cur, rtol=RTOL_FAST, atol=ATOL_FAST)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("fbc", ["periodic", "conductor", "mixed"])
+def test_filter_and_ghosts(eb, orc_mod, dim, fbc):
+    """CurrentsFilter loop = nfilter x (copy, filter, ghost exchange); strict build, exact."""
+    orc = orc_mod.oracle()
+    g = orc_mod.Grid.make(DIMS[dim], 2)
+    ctx = eb.Context(DIMS[dim], order=0, strict=True)
+    P, Cn = orc_mod.FBC_PERIODIC, orc_mod.FBC_CONDUCTOR
+    bc = dict(periodic=[P] * 6, conductor=[Cn] * 6, mixed=[P, P, Cn, Cn, P, P])[fbc]
+    cur = random_fields(g, 3, 5)
+    buff = np.zeros_like(cur)
+    d_cur, d_buff = dev(cur), dev(buff)
+    # additive sync + ghost fill first, like the engine does after the deposit
+    orc.sync_currents(g, cur, buff, bc)
+    orc.comm_fields(g, cur, 0, 3, bc)
+    ctx.sync_currents(d_cur, d_buff, bc)
+    ctx.comm_fields(d_cur, 0, 3, bc)
+    assert_values_equal(host(d_cur), cur, "sync+comm")
+    nfilter = 3
+    for _ in range(nfilter):
+        buff[...] = cur
+        orc.filter_pass(g, cur, buff, bc)
+        orc.comm_fields(g, cur, 0, 3, bc)
+    ctx.filter(d_cur, d_buff, nfilter, bc)
+    assert_values_equal(host(d_cur), cur, "filter")
+
+
+PUSH_CASES = [
+    dict(pusher_flags=2),
+    dict(pusher_flags=4),
+    dict(pusher_flags=2 | 8, gca_larmor_max=5.0, gca_e_ovr_b_sqr_max=0.81),
+    dict(pusher_flags=1),
+    dict(pusher_flags=2, drag_flags=3, sync_coeff=0.01, compton_coeff=0.02),
+    dict(pusher_flags=2, pbc="absorb"),
+    dict(pusher_flags=4, pbc="reflect"),
+    dict(pusher_flags=2, pbc="none", tag_outgoing=1),
+    dict(pusher_flags=2, has_atmosphere=1, atm_gx1=-0.3, atm_x_surf=0.4, atm_ds=0.7),
+]
+
+
+def _setup_push(eb, orc_mod, dim, order, case, strict, n=4000):
+    ng = orc_mod.nghosts_for(order)
+    g = orc_mod.Grid.make(DIMS[dim], ng)
+    kw = dict(PUSH_CASES[case])
+    pbc = kw.pop("pbc", "periodic")
+    code = dict(periodic=orc_mod.PBC_PERIODIC, absorb=orc_mod.PBC_ABSORB,
+                reflect=orc_mod.PBC_REFLECT, none=orc_mod.PBC_NONE)[pbc]
+    dx = 0.5
+    common = dict(dt=0.45 * dx, omegaB0=0.7, mass=1.0, charge=-1.0, dx=dx, xmin=[0.1, 0.2, 0.3],
+                  pbc=[code] * 6, **kw)
+    octx = orc_mod.make_pusher(**common)
+    ctx = eb.Context(DIMS[dim], order=order, strict=strict, dx=dx, xmin=(0.1, 0.2, 0.3))
+    gctx = ctx.make_pusher(**common)
+    em = smooth_fields(g, 10 + dim, amp=0.6)
+    p = random_particles(g, n, 100 + case, umag=2.0, dead_frac=0.05)
+    return g, ctx, octx, gctx, em, p, pbc, dx
+
+
+def _kill_outside(p, g, dim):
+    out = np.zeros(p.n, bool)
+    for a, nm in enumerate(["i1", "i2", "i3"][:dim]):
+        out |= (getattr(p, nm) < 0) | (getattr(p, nm) >= g.n[a])
+    p.tag[out] = 0
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+@pytest.mark.parametrize("case", range(len(PUSH_CASES)))
+def test_push_deposit_strict(eb, orc_mod, dim, order, case):
+    """Strict build: pusher bit-exact, ordered deposit bit-exact (serial particle order)."""
+    orc = orc_mod.oracle()
+    g, ctx, octx, gctx, em, p, pbc, dx = _setup_push(eb, orc_mod, dim, order, case, True)
+    n = p.n
+    d_em = dev(em)
+    arr = to_device(p)
+    j_ref = np.zeros(g.shape(3), np.float32)
+    d_j = dev(j_ref)
+    for step in range(3):
+        orc.push(g, order, octx, p, n, em)
+        ctx.push(gctx, arr, n, d_em)
+        q = to_host(arr, n)
+        assert_prtls_values_equal(q, p, what=f"push step {step}")
+        if pbc == "none":
+            _kill_outside(p, g, dim)
+            arr = to_device(p)
+        orc.deposit(g, order, p, n, -1.0, octx.dt, dx, j_ref)
+        ctx.deposit(arr, n, -1.0, octx.dt, d_j, mode=eb.DEPOSIT_ORDERED)
+        assert_values_equal(host(d_j), j_ref, f"ordered deposit step {step}")
+    assert np.abs(j_ref).max() > 0
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+@pytest.mark.parametrize("fused", [False, True])
+def test_push_deposit_fast(eb, orc_mod, dim, order, fused):
+    """Fast build (FMA contraction, atomic deposit, optional fusion): fp32 tolerance."""
+    orc = orc_mod.oracle()
+    g, ctx, octx, gctx, em, p, pbc, dx = _setup_push(eb, orc_mod, dim, order, 0, False, n=20000)
+    n = p.n
+    d_em = dev(em)
+    arr = to_device(p)
+    j_ref = np.zeros(g.shape(3), np.float32)
+    d_j = dev(j_ref)
+    orc.push(g, order, octx, p, n, em)
+    orc.deposit(g, order, p, n, -1.0, octx.dt, dx, j_ref)
+    if fused:
+        ctx.push_deposit(gctx, arr, n, d_em, d_j)
+    else:
+        ctx.push(gctx, arr, n, d_em)
+        ctx.deposit(arr, n, -1.0, octx.dt, d_j)
+    q = to_host(arr, n)
+    for nm in ("i1", "i2", "i3", "i1_prev", "i2_prev", "i3_prev", "tag"):
+        # a particle within rounding of a cell face may land on the other side: allow a handful
+        assert (getattr(q, nm) != getattr(p, nm)).sum() <= 2, nm
+    same = np.ones(n, bool)
+    for nm in ("i1", "i2", "i3"):
+        same &= getattr(q, nm) == getattr(p, nm)
+    for nm in ("ux1", "ux2", "ux3", "dx1", "dx2", "dx3"):
+        np.testing.assert_allclose(getattr(q, nm)[same], getattr(p, nm)[same], rtol=1e-4,
+                                   atol=2e-5, err_msg=nm)
+    scale = np.abs(j_ref).max()
+    assert np.abs(host(d_j) - j_ref).max() <= 2e-4 * scale
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_sort_particles(eb, orc_mod, dim):
+    g = orc_mod.Grid.make(DIMS[dim], 2)
+    ctx = eb.Context(DIMS[dim], order=0)
+    n = 5000
+    p = random_particles(g, n, 7, dead_frac=0.2)
+    arr = to_device(p)
+    n_alive = ctx.sort_particles(arr, n, remove_dead=True)
+    assert n_alive == int((p.tag == 1).sum())
+    q = to_host(arr, n)
+    assert (q.tag[:n_alive] == 1).all() and (q.tag[n_alive:] == 0).all()
+    key = q.i1.astype(np.int64)
+    if dim > 1:
+        key = key + g.n[0] * q.i2.astype(np.int64)
+    if dim > 2:
+        key = key + g.n[0] * g.n[1] * q.i3.astype(np.int64)
+    assert (np.diff(key[:n_alive]) >= 0).all(), "not sorted by cell"
+    # stable: expected result = numpy stable argsort of the same key
+    key0 = p.i1.astype(np.int64)
+    if dim > 1:
+        key0 = key0 + g.n[0] * p.i2.astype(np.int64)
+    if dim > 2:
+        key0 = key0 + g.n[0] * g.n[1] * p.i3.astype(np.int64)
+    key0[p.tag != 1] = np.iinfo(np.int64).max
+    perm = np.argsort(key0, kind="stable")
+    for nm in p.names():
+        assert np.array_equal(getattr(q, nm), getattr(p, nm)[perm]), nm
+
+
+def test_errors(eb):
+    with pytest.raises(eb.EB200Error):
+        eb.Context((8, 8), order=7)
+    ctx = eb.Context((8, 8), order=0)
+    with pytest.raises(eb.EB200Error, match="No particle pusher"):
+        ctx.push(ctx.make_pusher(dt=0.1, pusher_flags=0), {}, 0, None)
