@@ -30,6 +30,7 @@ UNITS = [
     ("fields.cu", "fast", ["-DEB200_STRICT=0"]),
     ("sort.cu", "one", []),
     ("comm.cu", "one", []),
+    ("engine.cu", "one", []),
     ("capi.cu", "one", []),
 ]
 

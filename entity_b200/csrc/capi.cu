@@ -118,6 +118,15 @@ void eb200_finalize(eb200_ctx_t* ctx) {
   delete ctx;
 }
 
+// internal accessor used by engine.cu
+int eb200_ctx_grid(const eb200_ctx_t* ctx, eb200_grid_t* grid, float* dx, float* xmin3) {
+  if (!ctx || !grid || !dx || !xmin3) return EB200_ERR_ARG;
+  *grid = ctx->cfg.grid;
+  *dx   = ctx->cfg.metric_params[0];
+  for (int a = 0; a < 3; ++a) xmin3[a] = ctx->cfg.metric_params[1 + a];
+  return EB200_OK;
+}
+
 int eb200_faraday(eb200_ctx_t* ctx, float* em, float coeff1, float coeff2,
                   const float* stencil9_host, eb200_stream_t stream) {
   ENTER(ctx);

@@ -74,6 +74,26 @@ class Config(C.Structure):
     ]
 
 
+class SpeciesC(C.Structure):
+    _fields_ = [("mass", C.c_float), ("charge", C.c_float), ("pusher_flags", C.c_int),
+                ("drag_flags", C.c_int), ("npart", C.c_uint32), ("maxnpart", C.c_uint32),
+                ("arrays", Prtls)]
+
+
+class ParamsC(C.Structure):
+    _fields_ = [
+        ("dt", C.c_float), ("correction", C.c_float), ("omegaB0", C.c_float),
+        ("q0", C.c_float), ("B0", C.c_float), ("V0", C.c_float), ("ppc0", C.c_float),
+        ("nfilter", C.c_int), ("fieldsolver_enabled", C.c_int), ("deposit_enabled", C.c_int),
+        ("stencil", C.c_float * 9), ("fbc", C.c_int * 6), ("pbc", C.c_int * 6),
+        ("gca_larmor_max", C.c_float), ("gca_e_ovr_b_max", C.c_float),
+        ("sync_gamma_rad", C.c_float), ("compton_gamma_rad", C.c_float),
+        ("fuse_push_deposit", C.c_int), ("deposit_mode", C.c_int),
+        ("sort_interval", C.c_int), ("clear_interval", C.c_int),
+    ]
+
+
+
 _lib = None
 
 
@@ -111,6 +131,9 @@ def load():
     lib.eb200_comm_fields.argtypes = [ctxp, vp, C.c_int, C.c_int, C.c_int, i32p, vp]
     lib.eb200_sync_currents.argtypes = [ctxp, vp, vp, i32p, vp]
     lib.eb200_sort_particles.argtypes = [ctxp, C.POINTER(Prtls), C.POINTER(C.c_uint32), C.c_int, vp]
+    lib.eb200_srpic_step.argtypes = [ctxp, C.POINTER(ParamsC), vp, vp, vp, C.POINTER(SpeciesC),
+                                     C.c_int, C.c_uint32, C.c_double, vp]
+    lib.eb200_srpic_step.restype = C.c_int
     for name in ("init", "faraday", "ampere", "currents_ampere", "filter", "push_sr", "deposit",
                  "push_deposit_sr", "zero_currents", "comm_fields", "sync_currents",
                  "sort_particles"):

@@ -1,0 +1,161 @@
+"""Python driver of the SRPIC step (``eb200_srpic_step``): owns the device tensors of one
+Minkowski domain and calls the C++ engine mirror in ``csrc/engine.cu``. Plumbing only --
+all arithmetic on fields and particles happens in the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+from . import lib as L
+from .lib import ParamsC, SpeciesC
+
+PRTL_DTYPES = {
+    "i1": "int32", "i2": "int32", "i3": "int32",
+    "dx1": "float32", "dx2": "float32", "dx3": "float32",
+    "ux1": "float32", "ux2": "float32", "ux3": "float32", "weight": "float32",
+    "i1_prev": "int32", "i2_prev": "int32", "i3_prev": "int32",
+    "dx1_prev": "float32", "dx2_prev": "float32", "dx3_prev": "float32",
+    "tag": "int16",
+}
+
+
+@dataclass
+class Scales:
+    """Derived scales exactly as SimulationParams computes them (parameters.cpp:47-78,
+    grid.cpp:39-50, algorithms.cpp:21-22), in fp32."""
+    dim: int
+    dx: float
+    larmor0: float
+    skindepth0: float
+    ppc0: float
+    cfl: float = 0.5
+    correction: float = 1.0
+
+    def derive(self):
+        import numpy as np
+        f = np.float32
+        dx = f(self.dx)
+        dx0 = dx / np.sqrt(f(self.dim))
+        V0 = dx if self.dim == 1 else (dx * dx if self.dim == 2 else dx * dx * dx)
+        out = dict(
+            dt=f(self.cfl) * dx0,
+            omegaB0=f(1.0) / f(self.larmor0),
+            B0=f(1.0) / f(self.larmor0),
+            V0=f(V0),
+            q0=f(V0) / (f(self.ppc0) * (f(self.skindepth0) * f(self.skindepth0))),
+            n0=f(self.ppc0) / f(V0),
+            ppc0=f(self.ppc0),
+            correction=f(self.correction),
+        )
+        return {k: float(v) for k, v in out.items()}
+
+
+@dataclass
+class Species:
+    mass: float
+    charge: float
+    pusher: int = L.PUSHER_BORIS
+    drag: int = L.DRAG_NONE
+    npart: int = 0
+    maxnpart: int = 0
+    arrays: dict = field(default_factory=dict)
+
+
+class Simulation:
+    """One Minkowski domain: em/cur/buff fields + species on one GPU."""
+
+    def __init__(self, n, order, scales: Scales, nfilter=0, strict=False, fused=False,
+                 deposit_mode=L.DEPOSIT_ATOMIC, fbc=None, pbc=None, sort_interval=0,
+                 clear_interval=0, device=0, xmin=(0.0, 0.0, 0.0), stencil=None,
+                 fieldsolver=True, deposit=True):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.dim = len(n)
+        self.ctx = L.Context(n, order=order, strict=strict, device=device, dx=scales.dx, xmin=xmin)
+        self.grid = self.ctx.grid
+        self.scales = scales.derive()
+        self.order = order
+        shape6, shape3 = self.grid.shape(6), self.grid.shape(3)
+        self.em = torch.zeros(shape6, dtype=torch.float32, device=self.device)
+        self.cur = torch.zeros(shape3, dtype=torch.float32, device=self.device)
+        self.buff = torch.zeros(shape3, dtype=torch.float32, device=self.device)
+        self.species: list[Species] = []
+        self.step_index = 0
+        self.time = 0.0
+        p = ParamsC()
+        s = self.scales
+        p.dt, p.correction, p.omegaB0 = s["dt"], s["correction"], s["omegaB0"]
+        p.q0, p.B0, p.V0, p.ppc0 = s["q0"], s["B0"], s["V0"], s["ppc0"]
+        p.nfilter = nfilter
+        p.fieldsolver_enabled, p.deposit_enabled = int(fieldsolver), int(deposit)
+        p.stencil = (C.c_float * 9)(*(stencil or [0.0] * 9))
+        p.fbc = (C.c_int * 6)(*(fbc or [L.FBC_PERIODIC] * 6))
+        p.pbc = (C.c_int * 6)(*(pbc or [L.PBC_PERIODIC] * 6))
+        p.fuse_push_deposit = int(fused)
+        p.deposit_mode = deposit_mode
+        p.sort_interval, p.clear_interval = sort_interval, clear_interval
+        self.params = p
+        self._species_c = None
+
+    @property
+    def dt(self):
+        return self.scales["dt"]
+
+    def add_species(self, mass, charge, arrays: dict, npart: int, pusher=L.PUSHER_BORIS,
+                    maxnpart=None):
+        """arrays: name -> torch tensor on this device (capacity = maxnpart)."""
+        cap = maxnpart or next(iter(arrays.values())).numel()
+        sp = Species(mass, charge, pusher, L.DRAG_NONE, npart, cap, arrays)
+        self.species.append(sp)
+        self._species_c = None
+        return sp
+
+    def alloc_species(self, mass, charge, maxnpart, pusher=L.PUSHER_BORIS):
+        torch = self.torch
+        arrays = {}
+        for k in PRTL_DTYPES:
+            axis = [c for c in k if c in "123"]
+            if k.startswith(("i", "dx")) and axis and int(axis[0]) > self.dim:
+                continue
+            arrays[k] = torch.zeros(maxnpart, dtype=getattr(torch, PRTL_DTYPES[k]),
+                                    device=self.device)
+        return self.add_species(mass, charge, arrays, 0, pusher, maxnpart)
+
+    def _pack_species(self):
+        arr = (SpeciesC * max(1, len(self.species)))()
+        for k, sp in enumerate(self.species):
+            arr[k].mass, arr[k].charge = sp.mass, sp.charge
+            arr[k].pusher_flags, arr[k].drag_flags = sp.pusher, sp.drag
+            arr[k].npart, arr[k].maxnpart = sp.npart, sp.maxnpart
+            arr[k].arrays = L.Context.prtls_struct(sp.arrays)
+        return arr
+
+    def step(self, nsteps=1, stream=None):
+        lib = self.ctx.lib
+        if self._species_c is None:
+            self._species_c = self._pack_species()
+        arr = self._species_c
+        st = L.Context._stream(stream)
+        for _ in range(nsteps):
+            rc = lib.eb200_srpic_step(self.ctx.handle, C.byref(self.params), self.em.data_ptr(),
+                                      self.cur.data_ptr(), self.buff.data_ptr(), arr,
+                                      len(self.species), self.step_index, self.time, st)
+            if rc != 0:
+                raise L.EB200Error(lib.eb200_last_error(self.ctx.handle).decode() or f"rc={rc}")
+            self.step_index += 1
+            self.time += self.dt
+        for k, sp in enumerate(self.species):
+            sp.npart = int(arr[k].npart)
+
+    # ------------------------------------------------------------ diagnostics (torch)
+    def n_pushed(self):
+        return sum(sp.npart for sp in self.species if sp.pusher != L.PUSHER_NONE)
+
+    def field_energy(self):
+        """Sum of E^2 and B^2 over active cells (plumbing-side diagnostic, not hot path)."""
+        g = self.grid
+        sl = (slice(None),) + tuple(slice(g.ng, g.ng + g.n[a]) for a in range(g.dim))[::-1]
+        act = self.em[sl].double()
+        return float((act[:3] ** 2).sum()), float((act[3:] ** 2).sum())

@@ -184,6 +184,47 @@ int eb200_sync_currents(eb200_ctx_t* ctx, float* cur, float* buff, const int* fb
 int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls,
                          uint32_t* npart_inout_host, int remove_dead, eb200_stream_t stream);
 
+/* ------------------------------------------------------------- whole SRPIC step */
+/* One species as the engine sees it: ntt::ParticleSpecies (src/framework/containers/species.h)
+ * + the SoA arrays + the live particle count. */
+typedef struct {
+  float         mass, charge;
+  int           pusher_flags; /* EB200_PUSHER_NONE: species is neither pushed nor deposited */
+  int           drag_flags;
+  uint32_t      npart;        /* in/out */
+  uint32_t      maxnpart;
+  eb200_prtls_t arrays;
+} eb200_species_t;
+
+/* The SimulationParams entries the SRPIC dispatchers read (src/engines/srpic/*.h), by value. */
+typedef struct {
+  float dt;           /* algorithms.timestep.dt = CFL * dx0 (algorithms.cpp:21-22) */
+  float correction;   /* algorithms.timestep.correction */
+  float omegaB0;      /* scales.omegaB0 = 1 / larmor0 */
+  float q0, B0, V0;   /* scales.* (parameters.cpp:47-78) */
+  float ppc0;         /* particles.ppc0 */
+  int   nfilter;      /* algorithms.current_filters */
+  int   fieldsolver_enabled, deposit_enabled;
+  float stencil[9];   /* algorithms.fieldsolver.{delta_x,delta_y,beta_xy,beta_yx,delta_z,beta_xz,beta_zx,beta_yz,beta_zy} */
+  int   fbc[6];       /* EB200_FBC_* per face */
+  int   pbc[6];       /* EB200_PBC_* per face */
+  float gca_larmor_max, gca_e_ovr_b_max;         /* algorithms.gca.* */
+  float sync_gamma_rad, compton_gamma_rad;       /* radiation.drag.*.gamma_rad */
+  int   fuse_push_deposit; /* 1: one pass over the particles for push + deposit */
+  int   deposit_mode;      /* EB200_DEPOSIT_* */
+  int   sort_interval;     /* particles.spatial_sorting_interval (0: never) */
+  int   clear_interval;    /* particles.clear_interval (0: never) */
+} eb200_srpic_params_t;
+
+/* SRPICEngine::step_forward (src/engines/srpic/srpic.hpp:65-188) for one Minkowski domain:
+ * Faraday(1/2) -> comm B -> ParticlePush -> CurrentsDeposit -> sync J, comm J -> CurrentsFilter ->
+ * [particle migration] -> Faraday(1/2) -> comm B -> Ampere -> CurrentsAmpere -> comm E|J ->
+ * SortParticles. Field/particle boundary kernels other than periodic wrap, absorb and reflect
+ * are outside this library. species[s].npart is updated in place. */
+int eb200_srpic_step(eb200_ctx_t* ctx, const eb200_srpic_params_t* prm, float* em, float* cur,
+                     float* buff, eb200_species_t* species, int nspecies, uint32_t step,
+                     double time, eb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

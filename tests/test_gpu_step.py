@@ -1,0 +1,93 @@
+"""Whole-step parity of eb200_srpic_step against the oracle stepping the same imported state
+(never regenerate, always import the initial state)."""
+import numpy as np
+import pytest
+
+from helpers import assert_values_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import entity_b200
+    from entity_b200 import workloads
+    from oracle import orc, pic
+    orc.build()
+    return entity_b200, workloads, orc, pic
+
+
+def _compare_particles(sim, osim, exact):
+    for sp, osp in zip(sim.species, osim.species):
+        assert sp.npart == osp["npart"]
+        n = sp.npart
+        for nm in osp["prtls"].names():
+            if nm not in sp.arrays:
+                continue
+            a = sp.arrays[nm][:n].cpu().numpy()
+            b = getattr(osp["prtls"], nm)[:n]
+            if exact:
+                assert np.array_equal(a, b), f"{nm}: {(a != b).sum()} of {n} differ"
+            elif a.dtype.kind == "f":
+                np.testing.assert_allclose(a, b, rtol=2e-3, atol=2e-4, err_msg=nm)
+
+
+@pytest.mark.parametrize("case", ["two_stream_2d", "two_stream_1d", "turbulence_3d_o3",
+                                  "reconnection_2d", "two_stream_2d_o2"])
+def test_step_strict_exact(mods, case):
+    """strict-fp + ordered deposit: particles, J and E/B bit-identical to the serial oracle
+    over a window of steps."""
+    eb, wl, orc, pic = mods
+    kw = dict(strict=True, deposit_mode=eb.DEPOSIT_ORDERED)
+    if case == "two_stream_2d":
+        sim = wl.two_stream((48, 32), ppc0=16, **kw)
+    elif case == "two_stream_1d":
+        sim = wl.two_stream((96,), ppc0=16, **kw)
+    elif case == "two_stream_2d_o2":
+        sim = wl.two_stream((32, 32), ppc0=8, **kw)
+        # same plasma, different shape order: rebuild with order 2
+        from entity_b200.srpic import Scales, Simulation
+        s2 = Simulation((32, 32), 2, Scales(2, sim.ctx.dx, 100.0, 10.0, 8), nfilter=2, **kw)
+        for sp in sim.species:
+            s2.add_species(sp.mass, sp.charge, sp.arrays, sp.npart, sp.pusher)
+        sim = s2
+    elif case == "turbulence_3d_o3":
+        sim = wl.turbulence((12, 10, 8), ppc0=4, order=3, **kw)
+    else:
+        sim = wl.reconnection((64, 64), ppc0=8, nfilter=3, **kw)
+    osim = pic.from_device_sim(sim)
+    nsteps = 6
+    for step in range(nsteps):
+        sim.step()
+        osim.step()
+        assert_values_equal(sim.cur.cpu().numpy(), osim.cur, f"{case}: J at step {step}")
+        assert_values_equal(sim.em.cpu().numpy(), osim.em, f"{case}: EM at step {step}")
+    _compare_particles(sim, osim, exact=True)
+    assert np.abs(osim.cur).max() > 0
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_step_fast_tolerance(mods, fused):
+    """fast-fp (FMA contraction, atomic deposit, optionally fused push+deposit, sorting on):
+    particle counts identical, fields/currents/energy within fp32 tolerance over the window."""
+    eb, wl, orc, pic = mods
+    sim = wl.two_stream((64, 48), ppc0=16, fused=fused, sort_interval=2)
+    osim = pic.from_device_sim(sim)
+    for step in range(8):
+        sim.step()
+        osim.step()
+    assert sim.n_pushed() == osim.n_pushed()
+    j, jo = sim.cur.cpu().numpy(), osim.cur
+    e, eo = sim.em.cpu().numpy(), osim.em
+    # stated tolerances: 5e-4 of the field maximum (fp32 sums of ~1e2 contributions per node,
+    # reordered by atomics, accumulated over 8 steps)
+    assert np.abs(j - jo).max() <= 5e-4 * np.abs(jo).max()
+    assert np.abs(e - eo).max() <= 5e-4 * max(np.abs(eo).max(), 1e-30)
+    g = osim.grid
+    sl = (slice(None),) + tuple(slice(g.ng, g.ng + g.n[a]) for a in range(g.dim))[::-1]
+    en = float((e[sl].astype(np.float64) ** 2).sum())
+    eno = float((eo[sl].astype(np.float64) ** 2).sum())
+    assert abs(en - eno) <= 1e-3 * eno
