@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the PIC timestep hot path (push + deposit + fields) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU kernels
+
+One "step" is one full SRPIC step (SRPICEngine::step_forward order) over the synthetic
+reconnection plasma of BASELINE.json configs[1]: 2D Cartesian pair plasma, Harris sheets,
+4096x2048 cells, 32 ppc, zig-zag deposit, 8 filter passes, periodic-core variant. The metric
+is particle-steps/s = (pushed, alive particles) x steps / time, whole job over all GPUs.
+
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for how each key is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec (push+deposit+fields)"
+UNIT = "particle-steps/s"
+B_P_2D = 78.0  # algorithmic bytes per particle-step, fused push+deposit, 2D
+WORKLOAD = "reconnection 2D Cartesian SR pair-plasma Harris sheet (periodic core), 4096x2048 cells, 32 ppc"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_sample(nsteps, warmup, size=(512, 256), ppc0=32, nfilter=8, threads=None):
+    """The reference's CPU kernels (oracle/_ref, else the oracle port) on a bounded cut of the
+    workload; returns (particle-steps/s, info dict). Needs a CUDA device only to generate the
+    synthetic state when one exists -- otherwise numpy."""
+    import numpy as np
+    from oracle import orc, pic
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liborc.so")):
+        orc.build()
+    impl = orc.reference(0)
+    kind = "reference"
+    if impl is None:
+        impl, kind = orc.oracle(), "port"
+    threads = threads or host_threads()
+    used = impl.set_threads(threads)
+    osim = cpu_reconnection(impl, size, ppc0, nfilter)
+    for _ in range(warmup):
+        osim.step()
+    n0 = osim.n_pushed()
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        osim.step()
+    dt = time.perf_counter() - t0
+    val = n0 * nsteps / dt
+    info = {"value": val, "unit": UNIT, "cores": used, "kind": kind,
+            "sample": f"{size[0]}x{size[1]} cut of the workload, {ppc0} ppc, {n0} particles, "
+                      f"{nsteps} full steps ({dt:.2f} s), oracle/_ref kernels"
+                      if kind == "reference" else
+                      f"{size[0]}x{size[1]} cut, {ppc0} ppc, {n0} particles, {nsteps} steps, serial port"}
+    return val, info, dt / nsteps
+
+
+def cpu_reconnection(impl, size, ppc0, nfilter, seed=0x5678):
+    """Numpy twin of workloads.reconnection (same shape; own RNG) for the CPU arms."""
+    import numpy as np
+    from oracle import orc, pic
+    from entity_b200.srpic import Scales
+    n1, n2 = size
+    Lx = 1000.0 * (n1 / 4096.0)
+    dx = Lx / n1
+    Ly = dx * n2
+    scales = Scales(2, dx, larmor0=0.1, skindepth0=1.0, ppc0=ppc0).derive()
+    o = pic.OracleSim(impl, size, 0, scales, dx, nfilter, xmin=(-0.5 * Lx, -0.5 * Ly, 0.0))
+    g = o.grid
+    w = 10.0 * (n1 / 4096.0)
+    y1, y2 = -0.25 * Ly, 0.25 * Ly
+    jj = np.arange(n2 + 2 * g.ng, dtype=np.float32) - g.ng
+    y = (jj + 0.5) * dx - 0.5 * Ly
+    bx = np.tanh((y - y1) / w) - np.tanh((y - y2) / w) - 1.0
+    o.em[3] = (bx / dx)[:, None].astype(np.float32)
+    rng = np.random.default_rng(seed)
+    ncell = n1 * n2
+    n_bg = ncell * (ppc0 // 2)
+    n_cs = int(3.0 * 2.0 * (w / dx) * n1 * (ppc0 // 2)) * 2
+    for charge in (-1.0, 1.0):
+        n = n_bg + n_cs
+        ps = orc.ParticleSet(n)
+        cell = np.arange(n_bg) // (ppc0 // 2)
+        ps.i1[:n_bg] = cell % n1
+        ps.i2[:n_bg] = cell // n1
+        ps.dx1[:n_bg] = rng.random(n_bg, dtype=np.float32)
+        ps.dx2[:n_bg] = rng.random(n_bg, dtype=np.float32)
+        for nm in ("ux1", "ux2", "ux3"):
+            getattr(ps, nm)[:n_bg] = (1e-2 * rng.standard_normal(n_bg)).astype(np.float32)
+        half = n_cs // 2
+        for s, yc in enumerate((y1, y2)):
+            lo = n_bg + s * half
+            r = np.clip(rng.random(half), 1e-6, 1 - 1e-6)
+            yy = np.mod(yc + 0.5 * w * np.log(r / (1 - r)) + 0.5 * Ly, Ly) / dx
+            xx = rng.random(half) * n1
+            for nm_i, nm_d, c, nn in (("i1", "dx1", xx, n1), ("i2", "dx2", yy, n2)):
+                ci = np.clip(np.floor(c), 0, nn - 1)
+                getattr(ps, nm_i)[lo:lo + half] = ci.astype(np.int32)
+                getattr(ps, nm_d)[lo:lo + half] = np.clip(c - ci, 0, 0.99999994).astype(np.float32)
+            T = 0.5 * 100.0 / 3.0
+            mag = -T * np.log(np.clip(rng.random((3, half)), 1e-12, None).prod(axis=0))
+            mu = 2 * rng.random(half) - 1
+            ph = 2 * np.pi * rng.random(half)
+            st = np.sqrt(1 - mu * mu)
+            ps.ux1[lo:lo + half] = mag * st * np.cos(ph)
+            ps.ux2[lo:lo + half] = mag * st * np.sin(ph)
+            ps.ux3[lo:lo + half] = mag * mu
+        np.minimum(ps.dx1, np.float32(0.99999994), out=ps.dx1)
+        np.minimum(ps.dx2, np.float32(0.99999994), out=ps.dx2)
+        ps.i1_prev[:], ps.i2_prev[:] = ps.i1, ps.i2
+        ps.dx1_prev[:], ps.dx2_prev[:] = ps.dx1, ps.dx2
+        ps.weight[:] = 1.0
+        ps.tag[:] = 1
+        o.add_species(1.0, charge, ps, n)
+    return o
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    val, info, sec_per_step = reference_sample(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": info["sample"], "shape_order": 0,
+                   "current_filters": 8, "host_threads": info["cores"]},
+        "cpu_baseline": info,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; entity_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from entity_b200 import workloads
+
+    size = tuple(args.size)
+    sim = workloads.reconnection(size, ppc0=args.ppc, nfilter=args.filters, fused=not args.unfused,
+                                 sort_interval=args.sort_interval, device=local,
+                                 seed=0x5678 + rank)
+    n_pushed0 = sim.n_pushed()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sim.step()
+    barrier()
+    sim.profile(True)
+    launches0 = sim.ctx.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    sim.step(args.steps)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.ctx.launch_count - launches0
+    prof = sim.read_profile()
+    sim.profile(False)
+    n_pushed = sim.n_pushed()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(n_pushed)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max, total = float(t.item()), float(cnt.item())
+    value = total * args.steps / (ms_max * 1e-3)
+
+    # roofline of the dominant kernel (fused push+deposit), from the in-step CUDA events
+    peak, peak_src = measured_peaks()
+    pd_ms, pd_calls = prof["PushDeposit"]
+    per_launch_s = 1e-3 * pd_ms / max(args.steps, 1)  # one push+deposit phase per step
+    achieved = n_pushed * B_P_2D / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": "push_deposit (all species of one step)", "peak_source": peak_src,
+                "phase_ms_per_step": {k: v[0] / max(args.steps, 1) for k, v in prof.items()}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        with open(tr) as f:
+            roofline["traffic"] = json.load(f).get("push_deposit_bytes_per_launch")
+
+    # end to end through the host-buffer C-ABI entry (pinned host state, H2D + D2H per step)
+    e2e = None
+    if not args.no_e2e:
+        hs = sim.host_state()
+        sim.step_host(hs)  # warm-up (allocates the device mirrors)
+        barrier()
+        t0 = time.perf_counter()
+        up = down = 0
+        for _ in range(args.e2e_steps):
+            u, d = sim.step_host(hs)
+            up, down = u, d
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total * args.e2e_steps / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": up, "d2h_bytes_per_step": down, "steps": args.e2e_steps}
+        del hs
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        _, cpu, _ = reference_sample(args.cpu_steps, 1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if size == (4096, 2048) and args.ppc == 32 else
+                       f"reconnection 2D {size[0]}x{size[1]} cells, {args.ppc} ppc (reduced)",
+                       "cells_per_gpu": list(size), "ppc0": args.ppc, "shape_order": 0,
+                       "current_filters": args.filters, "particles_per_gpu": n_pushed0,
+                       "fused_push_deposit": not args.unfused, "sort_interval": args.sort_interval,
+                       "parallelism": f"dd{world}" if world > 1 else "single domain",
+                       "l2": "inputs larger than L2 (particle state >> 126 MB), no flush"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, nargs=2, default=[4096, 2048])
+    ap.add_argument("--ppc", type=int, default=32)
+    ap.add_argument("--filters", type=int, default=8)
+    ap.add_argument("--sort-interval", type=int, default=0)
+    ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -17,8 +17,15 @@ namespace eb200 {
   uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 } // namespace eb200
 
+namespace eb200 {
+  struct EngineState;
+  EngineState* engine_state_new();
+  void         engine_state_delete(EngineState*);
+} // namespace eb200
+
 struct eb200_ctx {
   eb200_config_t cfg;
+  eb200::EngineState* engine = nullptr;
   eb200::Scratch scratch;
   std::string    err;
   uint64_t       launches_at_init;
@@ -106,6 +113,7 @@ int eb200_init(const eb200_config_t* cfg, eb200_ctx_t** out) {
   eb200_ctx* ctx        = new eb200_ctx();
   ctx->cfg              = *cfg;
   ctx->launches_at_init = eb200::launches();
+  ctx->engine           = eb200::engine_state_new();
   for (int a = cfg->grid.dim; a < 3; ++a) ctx->cfg.grid.n[a] = 1;
   *out = ctx;
   return EB200_OK;
@@ -115,8 +123,11 @@ void eb200_finalize(eb200_ctx_t* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   ctx->scratch.release();
+  eb200::engine_state_delete(ctx->engine);
   delete ctx;
 }
+
+eb200::EngineState* eb200_ctx_engine_state(eb200_ctx_t* ctx) { return ctx->engine; }
 
 // internal accessor used by engine.cu
 int eb200_ctx_grid(const eb200_ctx_t* ctx, eb200_grid_t* grid, float* dx, float* xmin3) {

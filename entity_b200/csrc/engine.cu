@@ -8,6 +8,64 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <vector>
+
+// ---- phase profiler: event pairs on the caller's stream, owned by the engine state -------
+namespace eb200 {
+  struct Profiler {
+    bool on = false;
+    struct Rec {
+      int         phase;
+      cudaEvent_t a, b;
+    };
+    std::vector<Rec>         recs;
+    std::vector<cudaEvent_t> pool;
+
+    cudaEvent_t get() {
+      if (!pool.empty()) {
+        cudaEvent_t e = pool.back();
+        pool.pop_back();
+        return e;
+      }
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      return e;
+    }
+  };
+
+  struct HostMirror {
+    std::vector<void*>  ptrs;
+    std::vector<size_t> sizes;
+  };
+
+  struct EngineState {
+    Profiler   prof;
+    HostMirror mirror;
+  };
+
+  struct PhaseScope {
+    Profiler*    p;
+    cudaStream_t st;
+    size_t       idx;
+    bool         live;
+
+    PhaseScope(Profiler* prof, int phase, cudaStream_t s) : p { prof }, st { s }, idx { 0 }, live { false } {
+      if (p && p->on) {
+        Profiler::Rec r { phase, p->get(), p->get() };
+        cudaEventRecord(r.a, st);
+        p->recs.push_back(r);
+        idx  = p->recs.size() - 1;
+        live = true;
+      }
+    }
+
+    ~PhaseScope() {
+      if (live) cudaEventRecord(p->recs[idx].b, st);
+    }
+  };
+} // namespace eb200
+
+extern "C" eb200::EngineState* eb200_ctx_engine_state(eb200_ctx_t* ctx);
 
 namespace eb200 {
   namespace srpic {
@@ -22,7 +80,10 @@ namespace eb200 {
       eb200_species_t*            species;
       int                         nspecies;
       eb200_stream_t              stream;
+      Profiler*                   prof;
     };
+
+#define PHASE(dom, which) PhaseScope phase_scope_((dom).prof, (which), (cudaStream_t)(dom).stream)
 
 #define TRY(expr)                                                                              \
   do {                                                                                         \
@@ -171,37 +232,62 @@ namespace eb200 {
     int step_forward(Domain& dom, uint32_t step, double time) {
       const eb200_srpic_params_t& p = *dom.prm;
       if (step == 0) {
+        PHASE(dom, EB200_PHASE_COMM);
         TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 0, 6, p.fbc, dom.stream));
       }
       if (p.fieldsolver_enabled) {
-        TRY(Faraday(dom, 0.5f));
+        {
+          PHASE(dom, EB200_PHASE_FIELDSOLVER);
+          TRY(Faraday(dom, 0.5f));
+        }
+        PHASE(dom, EB200_PHASE_COMM);
         TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 3, 6, p.fbc, dom.stream));
       }
-      if (p.deposit_enabled && p.fuse_push_deposit) {
-        TRY(ParticlePushAndDeposit(dom, time));
-      } else {
-        TRY(ParticlePush(dom, time));
-        if (p.deposit_enabled) {
-          TRY(CurrentsDeposit(dom));
+      {
+        PHASE(dom, EB200_PHASE_PUSH_DEPOSIT);
+        if (p.deposit_enabled && p.fuse_push_deposit) {
+          TRY(ParticlePushAndDeposit(dom, time));
+        } else {
+          TRY(ParticlePush(dom, time));
+          if (p.deposit_enabled) {
+            TRY(CurrentsDeposit(dom));
+          }
         }
       }
       if (p.deposit_enabled) {
-        TRY(eb200_sync_currents(dom.ctx, dom.cur, dom.buff, p.fbc, dom.stream));
-        TRY(eb200_comm_fields(dom.ctx, dom.cur, 3, 0, 3, p.fbc, dom.stream));
+        {
+          PHASE(dom, EB200_PHASE_COMM);
+          TRY(eb200_sync_currents(dom.ctx, dom.cur, dom.buff, p.fbc, dom.stream));
+          TRY(eb200_comm_fields(dom.ctx, dom.cur, 3, 0, 3, p.fbc, dom.stream));
+        }
+        PHASE(dom, EB200_PHASE_FILTER);
         TRY(CurrentsFilter(dom));
       }
       // CommunicateParticles: a single periodic domain has no neighbour to migrate to
       if (p.fieldsolver_enabled) {
-        TRY(Faraday(dom, 0.5f));
-        TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 3, 6, p.fbc, dom.stream));
-        TRY(Ampere(dom, 1.0f));
-        if (p.deposit_enabled) {
-          TRY(CurrentsAmpere(dom));
+        {
+          PHASE(dom, EB200_PHASE_FIELDSOLVER);
+          TRY(Faraday(dom, 0.5f));
         }
+        {
+          PHASE(dom, EB200_PHASE_COMM);
+          TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 3, 6, p.fbc, dom.stream));
+        }
+        {
+          PHASE(dom, EB200_PHASE_FIELDSOLVER);
+          TRY(Ampere(dom, 1.0f));
+          if (p.deposit_enabled) {
+            TRY(CurrentsAmpere(dom));
+          }
+        }
+        PHASE(dom, EB200_PHASE_COMM);
         TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 0, 3, p.fbc, dom.stream));
         TRY(eb200_comm_fields(dom.ctx, dom.cur, 3, 0, 3, p.fbc, dom.stream));
       }
-      TRY(SortParticles(dom, step));
+      {
+        PHASE(dom, EB200_PHASE_SORT);
+        TRY(SortParticles(dom, step));
+      }
       return EB200_OK;
     }
 
@@ -225,5 +311,137 @@ extern "C" int eb200_srpic_step(eb200_ctx_t* ctx, const eb200_srpic_params_t* pr
   dom.species  = species;
   dom.nspecies = nspecies;
   dom.stream   = stream;
+  dom.prof     = &eb200_ctx_engine_state(ctx)->prof;
   return eb200::srpic::step_forward(dom, step, time);
+}
+
+namespace eb200 {
+  EngineState* engine_state_new() { return new EngineState(); }
+
+  void engine_state_delete(EngineState* e) {
+    if (!e) return;
+    for (auto& r : e->prof.recs) {
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    for (auto ev : e->prof.pool) cudaEventDestroy(ev);
+    for (auto p : e->mirror.ptrs)
+      if (p) cudaFree(p);
+    delete e;
+  }
+} // namespace eb200
+
+extern "C" int eb200_profile_enable(eb200_ctx_t* ctx, int on) {
+  if (!ctx) return EB200_ERR_ARG;
+  eb200::Profiler& p = eb200_ctx_engine_state(ctx)->prof;
+  p.on               = on != 0;
+  for (auto& r : p.recs) {
+    p.pool.push_back(r.a);
+    p.pool.push_back(r.b);
+  }
+  p.recs.clear();
+  return EB200_OK;
+}
+
+extern "C" int eb200_profile_read(eb200_ctx_t* ctx, float* ms, int* calls) {
+  if (!ctx || !ms || !calls) return EB200_ERR_ARG;
+  eb200::Profiler& p = eb200_ctx_engine_state(ctx)->prof;
+  for (int k = 0; k < EB200_NPHASES; ++k) {
+    ms[k]    = 0.0f;
+    calls[k] = 0;
+  }
+  for (auto& r : p.recs) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return EB200_ERR_CUDA;
+    float t = 0.0f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return EB200_ERR_CUDA;
+    ms[r.phase]    += t;
+    calls[r.phase] += 1;
+    p.pool.push_back(r.a);
+    p.pool.push_back(r.b);
+  }
+  p.recs.clear();
+  return EB200_OK;
+}
+
+// ---- host-buffer step: device mirrors owned by the context ---------------------------------
+namespace {
+  struct Slot {
+    void** host_field; // address of the pointer inside the struct
+    size_t elem;
+  };
+
+  void* mirror_get(eb200::HostMirror& m, size_t slot, size_t bytes) {
+    if (m.ptrs.size() <= slot) {
+      m.ptrs.resize(slot + 1, nullptr);
+      m.sizes.resize(slot + 1, 0);
+    }
+    if (m.sizes[slot] < bytes) {
+      if (m.ptrs[slot]) cudaFree(m.ptrs[slot]);
+      m.ptrs[slot]  = nullptr;
+      m.sizes[slot] = 0;
+      if (cudaMalloc(&m.ptrs[slot], bytes) != cudaSuccess) return nullptr;
+      m.sizes[slot] = bytes;
+    }
+    return m.ptrs[slot];
+  }
+} // namespace
+
+extern "C" int eb200_srpic_step_host(eb200_ctx_t* ctx, const eb200_srpic_params_t* prm,
+                                     float* em_host, float* cur_host,
+                                     eb200_species_t* species_host, int nspecies, uint32_t step,
+                                     double time, uint64_t* bytes_h2d, uint64_t* bytes_d2h) {
+  if (!ctx || !prm || !em_host || !cur_host || (nspecies > 0 && !species_host)) return EB200_ERR_ARG;
+  eb200_grid_t g;
+  float        dx, xmin[3];
+  if (eb200_ctx_grid(ctx, &g, &dx, xmin) != EB200_OK) return EB200_ERR_ARG;
+  eb200::HostMirror& m = eb200_ctx_engine_state(ctx)->mirror;
+  size_t cells = 1;
+  for (int a = 0; a < g.dim; ++a) cells *= (size_t)(g.n[a] + 2 * g.ng);
+  const size_t b6 = cells * 6 * sizeof(float), b3 = cells * 3 * sizeof(float);
+  cudaStream_t st = 0;
+  uint64_t     up = 0, down = 0;
+  float*       d_em   = (float*)mirror_get(m, 0, b6);
+  float*       d_cur  = (float*)mirror_get(m, 1, b3);
+  float*       d_buff = (float*)mirror_get(m, 2, b3);
+  if (!d_em || !d_cur || !d_buff) return EB200_ERR_CUDA;
+  cudaMemcpyAsync(d_em, em_host, b6, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_cur, cur_host, b3, cudaMemcpyHostToDevice, st);
+  up += b6 + b3;
+  std::vector<eb200_species_t> dev(species_host, species_host + nspecies);
+  // per species 17 candidate arrays; element sizes in ParticleArrays order
+  static const size_t esz[17] = { 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 2 };
+  for (int s = 0; s < nspecies; ++s) {
+    void** hp = (void**)&species_host[s].arrays;
+    void** dp = (void**)&dev[s].arrays;
+    for (int k = 0; k < 20; ++k) dp[k] = nullptr;
+    const size_t n = species_host[s].npart, cap = species_host[s].maxnpart;
+    for (int k = 0; k < 17; ++k) {
+      if (!hp[k]) continue;
+      void* d = mirror_get(m, 3 + (size_t)s * 17 + k, cap * esz[k]);
+      if (!d) return EB200_ERR_CUDA;
+      dp[k] = d;
+      cudaMemcpyAsync(d, hp[k], n * esz[k], cudaMemcpyHostToDevice, st);
+      up += n * esz[k];
+    }
+  }
+  int rc = eb200_srpic_step(ctx, prm, d_em, d_cur, d_buff, dev.data(), nspecies, step, time, st);
+  if (rc != EB200_OK) return rc;
+  cudaMemcpyAsync(em_host, d_em, b6, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(cur_host, d_cur, b3, cudaMemcpyDeviceToHost, st);
+  down += b6 + b3;
+  for (int s = 0; s < nspecies; ++s) {
+    species_host[s].npart = dev[s].npart;
+    void** hp = (void**)&species_host[s].arrays;
+    void** dp = (void**)&dev[s].arrays;
+    const size_t n = dev[s].npart;
+    for (int k = 0; k < 17; ++k) {
+      if (!hp[k]) continue;
+      cudaMemcpyAsync(hp[k], dp[k], n * esz[k], cudaMemcpyDeviceToHost, st);
+      down += n * esz[k];
+    }
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess) return EB200_ERR_CUDA;
+  if (bytes_h2d) *bytes_h2d = up;
+  if (bytes_d2h) *bytes_d2h = down;
+  return EB200_OK;
 }

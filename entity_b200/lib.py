@@ -13,6 +13,8 @@ PBC_NONE, PBC_PERIODIC, PBC_ABSORB, PBC_REFLECT, PBC_AXIS = 0, 1, 2, 3, 4
 FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC = 0, 1, 2, 3, 4
 DEPOSIT_ATOMIC, DEPOSIT_ORDERED = 0, 1
 
+PHASES = ["FieldSolver", "PushDeposit", "CurrentFiltering", "Communications", "ParticleSort"]
+
 PRTL_FIELDS = ["i1", "i2", "i3", "dx1", "dx2", "dx3", "ux1", "ux2", "ux3", "weight",
                "i1_prev", "i2_prev", "i3_prev", "dx1_prev", "dx2_prev", "dx3_prev",
                "tag", "pld_r", "pld_i", "phi"]
@@ -134,6 +136,14 @@ def load():
     lib.eb200_srpic_step.argtypes = [ctxp, C.POINTER(ParamsC), vp, vp, vp, C.POINTER(SpeciesC),
                                      C.c_int, C.c_uint32, C.c_double, vp]
     lib.eb200_srpic_step.restype = C.c_int
+    lib.eb200_profile_enable.argtypes = [ctxp, C.c_int]
+    lib.eb200_profile_enable.restype = C.c_int
+    lib.eb200_profile_read.argtypes = [ctxp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    lib.eb200_profile_read.restype = C.c_int
+    lib.eb200_srpic_step_host.argtypes = [ctxp, C.POINTER(ParamsC), vp, vp, C.POINTER(SpeciesC),
+                                          C.c_int, C.c_uint32, C.c_double,
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.eb200_srpic_step_host.restype = C.c_int
     for name in ("init", "faraday", "ampere", "currents_ampere", "filter", "push_sr", "deposit",
                  "push_deposit_sr", "zero_currents", "comm_fields", "sync_currents",
                  "sort_particles"):

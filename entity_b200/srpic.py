@@ -149,6 +149,47 @@ class Simulation:
         for k, sp in enumerate(self.species):
             sp.npart = int(arr[k].npart)
 
+    # ------------------------------------------------------------------ profiling
+    def profile(self, on=True):
+        self.ctx._check(self.ctx.lib.eb200_profile_enable(self.ctx.handle, int(on)))
+
+    def read_profile(self):
+        """{phase: (milliseconds, calls)} accumulated since the last read."""
+        ms = (C.c_float * len(L.PHASES))()
+        calls = (C.c_int * len(L.PHASES))()
+        self.ctx._check(self.ctx.lib.eb200_profile_read(self.ctx.handle, ms, calls))
+        return {nm: (float(ms[k]), int(calls[k])) for k, nm in enumerate(L.PHASES)}
+
+    # ------------------------------------------------------- host-resident state (e2e)
+    def host_state(self):
+        """Pinned host copies of em, cur and all species arrays (for eb200_srpic_step_host)."""
+        torch = self.torch
+        pin = lambda t: t.detach().cpu().pin_memory()
+        hs = dict(em=pin(self.em), cur=pin(self.cur), species=[])
+        for sp in self.species:
+            hs["species"].append({k: pin(v) for k, v in sp.arrays.items()})
+        arr = (SpeciesC * max(1, len(self.species)))()
+        for k, sp in enumerate(self.species):
+            arr[k].mass, arr[k].charge = sp.mass, sp.charge
+            arr[k].pusher_flags, arr[k].drag_flags = sp.pusher, sp.drag
+            arr[k].npart, arr[k].maxnpart = sp.npart, sp.maxnpart
+            arr[k].arrays = L.Context.prtls_struct(hs["species"][k])
+        hs["c"] = arr
+        hs["step"], hs["time"] = self.step_index, self.time
+        return hs
+
+    def step_host(self, hs):
+        """One step through the host-buffer entry point; returns (h2d_bytes, d2h_bytes)."""
+        up, down = C.c_uint64(0), C.c_uint64(0)
+        rc = self.ctx.lib.eb200_srpic_step_host(
+            self.ctx.handle, C.byref(self.params), hs["em"].data_ptr(), hs["cur"].data_ptr(),
+            hs["c"], len(self.species), hs["step"], hs["time"], C.byref(up), C.byref(down))
+        if rc != 0:
+            raise L.EB200Error(self.ctx.lib.eb200_last_error(self.ctx.handle).decode() or f"rc={rc}")
+        hs["step"] += 1
+        hs["time"] += self.dt
+        return int(up.value), int(down.value)
+
     # ------------------------------------------------------------ diagnostics (torch)
     def n_pushed(self):
         return sum(sp.npart for sp in self.species if sp.pusher != L.PUSHER_NONE)

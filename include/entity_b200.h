@@ -225,6 +225,32 @@ int eb200_srpic_step(eb200_ctx_t* ctx, const eb200_srpic_params_t* prm, float* e
                      float* buff, eb200_species_t* species, int nspecies, uint32_t step,
                      double time, eb200_stream_t stream);
 
+/* ------------------------------------------------------------------- profiling */
+/* Phases of eb200_srpic_step, bracketed by CUDA events on the caller's stream when profiling
+ * is enabled (names follow the reference's timers, src/engines/engine.hpp:245-257). */
+enum {
+  EB200_PHASE_FIELDSOLVER = 0, /* Faraday x2 + Ampere + CurrentsAmpere */
+  EB200_PHASE_PUSH_DEPOSIT = 1, /* ParticlePusher + CurrentDeposit (incl. zeroing J) */
+  EB200_PHASE_FILTER = 2,       /* CurrentFiltering */
+  EB200_PHASE_COMM = 3,         /* Communications (ghost fill, J sync, migration) */
+  EB200_PHASE_SORT = 4,         /* ParticleSort */
+  EB200_NPHASES = 5
+};
+int eb200_profile_enable(eb200_ctx_t* ctx, int on);
+/* synchronises the recorded events; ms_host[EB200_NPHASES], calls_host[EB200_NPHASES]
+ * (accumulated since enable; reading resets the accumulators) */
+int eb200_profile_read(eb200_ctx_t* ctx, float* ms_host, int* calls_host);
+
+/* ---------------------------------------------------------- host-buffer entry */
+/* The same step for a caller whose state lives in HOST memory (pinned or pageable): copies
+ * em, cur and every species array to context-owned device mirrors, runs eb200_srpic_step,
+ * copies everything back, and returns after the stream has drained. Pointers inside
+ * species_host[s].arrays are host pointers. bytes_h2d/bytes_d2h (may be NULL) receive the
+ * bytes moved. */
+int eb200_srpic_step_host(eb200_ctx_t* ctx, const eb200_srpic_params_t* prm, float* em_host,
+                          float* cur_host, eb200_species_t* species_host, int nspecies,
+                          uint32_t step, double time, uint64_t* bytes_h2d, uint64_t* bytes_d2h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,17 +170,35 @@ def _declare(lib, prefix):
 class Impl:
     """One implementation (oracle port or compiled reference) behind numpy arguments."""
 
-    def __init__(self, lib, prefix, kind):
+    def __init__(self, lib, prefix, kind, fallback=None):
         self.lib, self.prefix, self.kind = lib, prefix, kind
+        self.fallback = fallback
         _declare(lib, prefix)
 
     def _f(self, name):
-        return getattr(self.lib, self.prefix + name)
+        try:
+            return getattr(self.lib, self.prefix + name)
+        except AttributeError:
+            # the compiled reference covers the kernels (src/kernels, src/metrics); the
+            # framework-level ghost exchange (src/framework/domain) exists only as the port
+            if self.fallback is None:
+                raise
+            return self.fallback._f(name)
 
     @staticmethod
     def _p(a):
         assert a.flags["C_CONTIGUOUS"]
         return a.ctypes.data
+
+    def set_threads(self, n):
+        """Worker threads of the compiled reference (1 = serial program order). The port is
+        always serial."""
+        fn = getattr(self.lib, self.prefix + "set_threads", None)
+        if fn is not None:
+            fn.argtypes = [C.c_int]
+            fn(int(n))
+            return int(n)
+        return 1
 
     def faraday(self, g, em, coeff1, coeff2, stencil=None):
         st = None
@@ -231,5 +249,6 @@ def reference(order: int) -> Impl | None:
     key = f"ref{order}"
     if key not in _cache:
         path = os.path.join(HERE, "_ref", f"libref_o{order}.so")
-        _cache[key] = Impl(C.CDLL(path), "ref_", "reference") if os.path.exists(path) else None
+        _cache[key] = (Impl(C.CDLL(path), "ref_", "reference", fallback=oracle())
+                       if os.path.exists(path) else None)
     return _cache[key]

@@ -20,9 +20,12 @@
 #include "kernels/faraday_mink.hpp"
 #include "kernels/pushers/sr.hpp"
 
+#include <algorithm>
+#include <cstring>
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace ntt;
@@ -59,18 +62,44 @@ namespace {
     }
   }
 
+  // number of worker threads for the *_mt entry points (1 = the serial reference order)
+  int g_threads = 1;
+
+  template <class F>
+  void parallel_chunks(std::size_t n, const F& fn) {
+    const int nt = std::max(1, std::min<int>(g_threads, (int)std::max<std::size_t>(n, 1)));
+    if (nt == 1) {
+      fn(0, n, 0);
+      return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+      const std::size_t lo = n * t / nt, hi = n * (t + 1) / nt;
+      th.emplace_back([=, &fn]() { fn(lo, hi, t); });
+    }
+    for (auto& x : th) x.join();
+  }
+
+  // active cells; the slowest active dimension is split across the worker threads (cells are
+  // independent in every field kernel, like a Kokkos MDRangePolicy)
   template <class K, Dimension D>
   void loop_active(const orc_grid_t* g, const K& k) {
     const ncells_t G = N_GHOSTS;
     if constexpr (D == Dim::_1D) {
-      for (ncells_t i = G; i < g->n[0] + G; ++i) k(i);
+      parallel_chunks(g->n[0], [&](std::size_t lo, std::size_t hi, int) {
+        for (ncells_t i = G + lo; i < G + hi; ++i) k(i);
+      });
     } else if constexpr (D == Dim::_2D) {
-      for (ncells_t j = G; j < g->n[1] + G; ++j)
-        for (ncells_t i = G; i < g->n[0] + G; ++i) k(i, j);
+      parallel_chunks(g->n[1], [&](std::size_t lo, std::size_t hi, int) {
+        for (ncells_t j = G + lo; j < G + hi; ++j)
+          for (ncells_t i = G; i < g->n[0] + G; ++i) k(i, j);
+      });
     } else {
-      for (ncells_t l = G; l < g->n[2] + G; ++l)
-        for (ncells_t j = G; j < g->n[1] + G; ++j)
-          for (ncells_t i = G; i < g->n[0] + G; ++i) k(i, j, l);
+      parallel_chunks(g->n[2], [&](std::size_t lo, std::size_t hi, int) {
+        for (ncells_t l = G + lo; l < G + hi; ++l)
+          for (ncells_t j = G; j < g->n[1] + G; ++j)
+            for (ncells_t i = G; i < g->n[0] + G; ++i) k(i, j, l);
+      });
     }
   }
 
@@ -192,10 +221,14 @@ namespace {
                                          ::traits::custom_prtl_update::NoPolicy_t,
                                          ::traits::extfields::NoPolicy_t, true>;
       kernel::sr::Pusher_kernel<M, P> k(ctx, pb, arr, EB, metric, P {});
-      for (uint32_t q = 0; q < n; ++q) k(q);
+      parallel_chunks(n, [&](std::size_t lo, std::size_t hi, int) {
+        for (uint32_t q = lo; q < hi; ++q) k(q);
+      });
     } else {
       kernel::sr::Pusher_kernel<M> k(ctx, pb, arr, EB, metric);
-      for (uint32_t q = 0; q < n; ++q) k(q);
+      parallel_chunks(n, [&](std::size_t lo, std::size_t hi, int) {
+        for (uint32_t q = lo; q < hi; ++q) k(q);
+      });
     }
   }
 
@@ -208,10 +241,30 @@ namespace {
     auto Js     = Kokkos::Experimental::create_scatter_view(J);
     ParticleArrays a { 1u };
     fill_arrays(a, p, n);
-    kernel::DepositCurrents_kernel<SimEngine::SRPIC, M, SHAPE_ORDER> k(
-      Js, a.i1, a.i2, a.i3, a.i1_prev, a.i2_prev, a.i3_prev, a.dx1, a.dx2, a.dx3, a.dx1_prev,
-      a.dx2_prev, a.dx3_prev, a.ux1, a.ux2, a.ux3, a.phi, a.weight, a.tag, metric, charge, dt);
-    for (uint32_t q = 0; q < n; ++q) k(q);
+    if (g_threads <= 1) {
+      kernel::DepositCurrents_kernel<SimEngine::SRPIC, M, SHAPE_ORDER> k(
+        Js, a.i1, a.i2, a.i3, a.i1_prev, a.i2_prev, a.i3_prev, a.dx1, a.dx2, a.dx3, a.dx1_prev,
+        a.dx2_prev, a.dx3_prev, a.ux1, a.ux2, a.ux3, a.phi, a.weight, a.tag, metric, charge, dt);
+      for (uint32_t q = 0; q < n; ++q) k(q);
+      return;
+    }
+    // threaded: one private copy of J per worker, reduced afterwards -- the duplication
+    // strategy Kokkos' ScatterView uses on the OpenMP backend
+    const std::size_t tot = J.size();
+    const int         nt  = g_threads;
+    std::vector<std::vector<float>> priv(nt, std::vector<float>(tot, 0.0f));
+    parallel_chunks(n, [&](std::size_t lo, std::size_t hi, int t) {
+      auto Jt  = wrap<D, 3>(g, priv[t].data());
+      auto Jts = Kokkos::Experimental::create_scatter_view(Jt);
+      kernel::DepositCurrents_kernel<SimEngine::SRPIC, M, SHAPE_ORDER> k(
+        Jts, a.i1, a.i2, a.i3, a.i1_prev, a.i2_prev, a.i3_prev, a.dx1, a.dx2, a.dx3, a.dx1_prev,
+        a.dx2_prev, a.dx3_prev, a.ux1, a.ux2, a.ux3, a.phi, a.weight, a.tag, metric, charge, dt);
+      for (uint32_t q = lo; q < hi; ++q) k(q);
+    });
+    parallel_chunks(tot, [&](std::size_t lo, std::size_t hi, int) {
+      for (int t = 0; t < nt; ++t)
+        for (std::size_t x = lo; x < hi; ++x) cur[x] += priv[t][x];
+    });
   }
 
 } // namespace
@@ -226,6 +279,7 @@ namespace {
 
 extern "C" {
 int  ref_shape_order() { return SHAPE_ORDER; }
+void ref_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 int  ref_nghosts() { return (int)N_GHOSTS; }
 void ref_faraday_mink(const orc_grid_t* g, float* em, float c1, float c2, const float* st) {
   BY_DIM(faraday, g, em, c1, c2, st);

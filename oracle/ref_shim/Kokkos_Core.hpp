@@ -120,12 +120,9 @@ namespace Kokkos {
 
     template <class... I>
     inline value_type& operator()(I... idx) const {
-      const std::size_t id[] = { static_cast<std::size_t>(idx)... };
-      std::size_t       off = 0, stride = 1;
-      for (int r = 0; r < static_cast<int>(sizeof...(I)); ++r) {
-        off    += id[r] * stride;
-        stride *= ext[r];
-      }
+      std::size_t off = 0, stride = 1;
+      int         r   = 0;
+      ((off += static_cast<std::size_t>(idx) * stride, stride *= ext[r++]), ...);
       return ptr[off];
     }
 
