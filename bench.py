@@ -227,9 +227,12 @@ def run_ours(args):
     from entity_b200 import workloads
 
     size = tuple(args.size)
+    import entity_b200 as eb
+    dmode = {"atomic": eb.DEPOSIT_ATOMIC, "aggregated": eb.DEPOSIT_AGGREGATED,
+             "ordered": eb.DEPOSIT_ORDERED}[args.deposit]
     sim = workloads.reconnection(size, ppc0=args.ppc, nfilter=args.filters, fused=not args.unfused,
                                  sort_interval=args.sort_interval, device=local,
-                                 seed=0x5678 + rank)
+                                 deposit_mode=dmode, seed=0x5678 + rank)
     n_pushed0 = sim.n_pushed()
 
     def barrier():
@@ -313,6 +316,7 @@ def run_ours(args):
                        "cells_per_gpu": list(size), "ppc0": args.ppc, "shape_order": 0,
                        "current_filters": args.filters, "particles_per_gpu": n_pushed0,
                        "fused_push_deposit": not args.unfused, "sort_interval": args.sort_interval,
+                       "deposit": args.deposit,
                        "parallelism": f"dd{world}" if world > 1 else "single domain",
                        "l2": "inputs larger than L2 (particle state >> 126 MB), no flush"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
@@ -333,7 +337,8 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=[4096, 2048])
     ap.add_argument("--ppc", type=int, default=32)
     ap.add_argument("--filters", type=int, default=8)
-    ap.add_argument("--sort-interval", type=int, default=0)
+    ap.add_argument("--sort-interval", type=int, default=20)
+    ap.add_argument("--deposit", default="aggregated", choices=["atomic", "aggregated", "ordered"])
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)

@@ -11,5 +11,5 @@ from .lib import (  # noqa: F401
     DRAG_NONE, DRAG_SYNCHROTRON, DRAG_COMPTON,
     PBC_NONE, PBC_PERIODIC, PBC_ABSORB, PBC_REFLECT, PBC_AXIS,
     FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC,
-    DEPOSIT_ATOMIC, DEPOSIT_ORDERED, EB200Error,
+    DEPOSIT_ATOMIC, DEPOSIT_ORDERED, DEPOSIT_AGGREGATED, EB200Error,
 )

@@ -243,7 +243,8 @@ int eb200_deposit(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, 
   if (rc) return rc;
   REQUIRE(ctx, cur != nullptr, "cur is null");
   REQUIRE(ctx, dt > 0.0f, "dt must be positive");
-  REQUIRE(ctx, mode == EB200_DEPOSIT_ATOMIC || mode == EB200_DEPOSIT_ORDERED, "bad deposit mode");
+  REQUIRE(ctx, mode == EB200_DEPOSIT_ATOMIC || mode == EB200_DEPOSIT_ORDERED ||
+                 mode == EB200_DEPOSIT_AGGREGATED, "bad deposit mode");
   const float dx = ctx->cfg.metric_params[0];
   REQUIRE(ctx, dx > 0.0f, "metric_params[0] (dx) must be positive");
   return check_cuda(ctx,
@@ -255,8 +256,10 @@ int eb200_deposit(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, 
 
 int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
                           const eb200_prtls_t* prtls, uint32_t npart, const float* em, float* cur,
-                          eb200_stream_t stream) {
+                          int mode, eb200_stream_t stream) {
   ENTER(ctx);
+  REQUIRE(ctx, mode == EB200_DEPOSIT_ATOMIC || mode == EB200_DEPOSIT_AGGREGATED,
+          "fused push+deposit supports the ATOMIC and AGGREGATED modes");
   int rc = check_pusher(ctx, pusher);
   if (rc) return rc;
   rc = check_prtls(ctx, prtls, npart);
@@ -264,7 +267,7 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
   REQUIRE(ctx, em != nullptr && cur != nullptr, "null field");
   return check_cuda(ctx,
                     VARIANT_CALL(ctx, push_deposit_sr(ctx->cfg.grid, ctx->cfg.shape_order,
-                                                      *pusher, *prtls, npart, em, cur,
+                                                      *pusher, *prtls, npart, em, cur, mode,
                                                       (cudaStream_t)stream)),
                     "push_deposit_sr");
 }

@@ -201,6 +201,9 @@ namespace eb200 {
           TRY(eb200_push_sr(dom.ctx, &c, &sp.arrays, sp.npart, dom.em, dom.stream));
         } else {
           TRY(eb200_push_deposit_sr(dom.ctx, &c, &sp.arrays, sp.npart, dom.em, dom.cur,
+                                    dom.prm->deposit_mode == EB200_DEPOSIT_AGGREGATED
+                                      ? EB200_DEPOSIT_AGGREGATED
+                                      : EB200_DEPOSIT_ATOMIC,
                                     dom.stream));
         }
       }

@@ -603,15 +603,15 @@ namespace eb200 {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           acc = (i == 0) ? (-Q * (fS1[0] - iS1[0])) : (acc - Q * (fS1[i] - iS1[i]));
-          if (i < d1) J(min1 + i, 0, 0, jx1, acc);
+          J(min1 + i, 0, 0, jx1, acc, i < d1);
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          if (i <= d1) J(min1 + i, 0, 0, jx2, QV2 * (HALF * (fS1[i] + iS1[i])));
+          J(min1 + i, 0, 0, jx2, QV2 * (HALF * (fS1[i] + iS1[i])), i <= d1);
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          if (i <= d1) J(min1 + i, 0, 0, jx3, QV3 * (HALF * (fS1[i] + iS1[i])));
+          J(min1 + i, 0, 0, jx3, QV3 * (HALF * (fS1[i] + iS1[i])), i <= d1);
         }
       } else if constexpr (D == 2) {
         float iS2[N], fS2[N];
@@ -632,7 +632,7 @@ namespace eb200 {
             for (int j = 0; j < N; ++j) {
               const float w = HALF * (fS1[i] - iS1[i]) * (fS2[j] + iS2[j]);
               acc[j]        = (i == 0) ? (-Q * w) : (acc[j] - Q * w);
-              if (i < d1 && j <= d2) J(min1 + i, min2 + j, 0, jx1, acc[j]);
+              J(min1 + i, min2 + j, 0, jx1, acc[j], i < d1 && j <= d2);
             }
           }
         }
@@ -645,7 +645,7 @@ namespace eb200 {
             for (int j = 0; j < N; ++j) {
               const float w = HALF * (fS1[i] + iS1[i]) * (fS2[j] - iS2[j]);
               acc           = (j == 0) ? (-Q * w) : (acc - Q * w);
-              if (i <= d1 && j < d2) J(min1 + i, min2 + j, 0, jx2, acc);
+              J(min1 + i, min2 + j, 0, jx2, acc, i <= d1 && j < d2);
             }
           }
         }
@@ -655,7 +655,7 @@ namespace eb200 {
           for (int j = 0; j < N; ++j) {
             const float w = THIRD * (fS2[j] * (HALF * iS1[i] + fS1[i]) +
                                      iS2[j] * (HALF * fS1[i] + iS1[i]));
-            if (i <= d1 && j <= d2) J(min1 + i, min2 + j, 0, jx3, QV3 * w);
+            J(min1 + i, min2 + j, 0, jx3, QV3 * w, i <= d1 && j <= d2);
           }
         }
       } else {
@@ -683,9 +683,7 @@ namespace eb200 {
                                 ((iS2[j] * iS3[k] + fS2[j] * fS3[k]) +
                                  HALF * (iS3[k] * fS2[j] + iS2[j] * fS3[k]));
                 acc[j][k] = (i == 0) ? (-Q * w) : (acc[j][k] - Q * w);
-                if (i < d1 && j <= d2 && k <= d3) {
-                  J(min1 + i, min2 + j, min3 + k, jx1, acc[j][k]);
-                }
+                J(min1 + i, min2 + j, min3 + k, jx1, acc[j][k], i < d1 && j <= d2 && k <= d3);
               }
             }
           }
@@ -703,9 +701,7 @@ namespace eb200 {
                                 (iS1[i] * iS3[k] + fS1[i] * fS3[k] +
                                  HALF * (iS3[k] * fS1[i] + iS1[i] * fS3[k]));
                 acc[k] = (j == 0) ? (-Q * w) : (acc[k] - Q * w);
-                if (i <= d1 && j < d2 && k <= d3) {
-                  J(min1 + i, min2 + j, min3 + k, jx2, acc[k]);
-                }
+                J(min1 + i, min2 + j, min3 + k, jx2, acc[k], i <= d1 && j < d2 && k <= d3);
               }
             }
           }
@@ -723,14 +719,205 @@ namespace eb200 {
                                 (iS1[i] * iS2[j] + fS1[i] * fS2[j] +
                                  HALF * (iS1[i] * fS2[j] + iS2[j] * fS1[i]));
                 acc = (k == 0) ? (-Q * w) : (acc - Q * w);
-                if (i <= d1 && j <= d2 && k < d3) {
-                  J(min1 + i, min2 + j, min3 + k, jx3, acc);
-                }
+                J(min1 + i, min2 + j, min3 + k, jx3, acc, i <= d1 && j <= d2 && k < d3);
               }
             }
           }
         }
       }
+    }
+  }
+
+  /* ------------------------------------------------- warp-aggregated deposit */
+  // Particles arrive (nearly) cell-sorted, so consecutive lanes of a warp mostly deposit
+  // onto the same nodes. Instead of one atomic per lane and node, runs of lanes with the
+  // same key (cell / window origin) are summed with a segmented shuffle reduction and only
+  // the head lane of each run issues the atomic. Correct for any order of the particles:
+  // an unsorted warp just degrades to one run per lane.
+  struct WarpRun {
+    bool head;
+    int  end; // last lane of the run this lane belongs to
+  };
+
+  __device__ __forceinline__ WarpRun warp_runs(int key) {
+    const unsigned lane  = threadIdx.x & 31u;
+    const int      prev  = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool     head  = (lane == 0u) || (prev != key);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned above = (lane == 31u) ? 0u : (heads & ~((2u << lane) - 1u));
+    WarpRun        r;
+    r.head = head;
+    r.end  = above ? (__ffs(above) - 2) : 31;
+    return r;
+  }
+
+  // sum of v over the run; valid on the head lane
+  __device__ __forceinline__ float run_sum(float v, const WarpRun& r) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_down_sync(0xffffffffu, v, d);
+      if (lane + d <= r.end) {
+        v += o;
+      }
+    }
+    return v;
+  }
+
+  template <int D>
+  struct ZigZag {
+    static constexpr int NV = (D == 1) ? 5 : ((D == 2) ? 8 : 12);
+  };
+
+  // Contributions of the two zig-zag segments (0: in the old cell, 1: in the new cell) to
+  // the NV nodes around the respective cell, in the node order of zigzag_offsets().
+  template <int D>
+  __device__ __forceinline__ void zigzag_values(const Prtl<D>& P, float charge, float inv_dt,
+                                                float dxc, float (&v)[2][ZigZag<D>::NV]) {
+    float vp[3];
+    vp[0] = (0 < D) ? P.u[0] / dxc : P.u[0];
+    vp[1] = (1 < D) ? P.u[1] / dxc : P.u[1];
+    vp[2] = (2 < D) ? P.u[2] / dxc : P.u[2];
+    const float inv_energy = ONE / sqrtf(ONE + nsq(P.u));
+    if (isnan(vp[2]) || isinf(vp[2])) {
+      vp[2] = ZERO;
+    }
+    vp[0] *= inv_energy;
+    vp[1] *= inv_energy;
+    vp[2] *= inv_energy;
+    const float coeff = P.w * charge;
+    float       W[3][2], Fl[3][2];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const int   up = static_cast<int>(P.i[a] > P.ip[a]);
+      const float r  = static_cast<float>(P.i[a] == P.ip[a]) * (P.d[a] + P.dp[a]) * INV_2;
+      W[a][0]        = INV_2 * (r + P.dp[a] + static_cast<float>(up));
+      W[a][1]        = INV_2 * (P.d[a] + r + static_cast<float>(up + P.ip[a] - P.i[a]));
+      Fl[a][0]       = (static_cast<float>(up) + r - P.dp[a]) * coeff * inv_dt;
+      Fl[a][1] = (static_cast<float>(P.i[a] - P.ip[a] - up) + P.d[a] - r) * coeff * inv_dt;
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if constexpr (D == 1) {
+        const float F2 = HALF * vp[1] * coeff, F3 = HALF * vp[2] * coeff;
+        v[s][0] = Fl[0][s];
+        v[s][1] = F2 * (ONE - W[0][s]);
+        v[s][2] = F2 * W[0][s];
+        v[s][3] = F3 * (ONE - W[0][s]);
+        v[s][4] = F3 * W[0][s];
+      } else if constexpr (D == 2) {
+        const float F3 = HALF * vp[2] * coeff;
+        v[s][0] = Fl[0][s] * (ONE - W[1][s]);
+        v[s][1] = Fl[0][s] * W[1][s];
+        v[s][2] = Fl[1][s] * (ONE - W[0][s]);
+        v[s][3] = Fl[1][s] * W[0][s];
+        v[s][4] = F3 * (ONE - W[0][s]) * (ONE - W[1][s]);
+        v[s][5] = F3 * W[0][s] * (ONE - W[1][s]);
+        v[s][6] = F3 * (ONE - W[0][s]) * W[1][s];
+        v[s][7] = F3 * W[0][s] * W[1][s];
+      } else {
+        v[s][0]  = Fl[0][s] * (ONE - W[1][s]) * (ONE - W[2][s]);
+        v[s][1]  = Fl[0][s] * W[1][s] * (ONE - W[2][s]);
+        v[s][2]  = Fl[0][s] * (ONE - W[1][s]) * W[2][s];
+        v[s][3]  = Fl[0][s] * W[1][s] * W[2][s];
+        v[s][4]  = Fl[1][s] * (ONE - W[0][s]) * (ONE - W[2][s]);
+        v[s][5]  = Fl[1][s] * W[0][s] * (ONE - W[2][s]);
+        v[s][6]  = Fl[1][s] * (ONE - W[0][s]) * W[2][s];
+        v[s][7]  = Fl[1][s] * W[0][s] * W[2][s];
+        v[s][8]  = Fl[2][s] * (ONE - W[0][s]) * (ONE - W[1][s]);
+        v[s][9]  = Fl[2][s] * W[0][s] * (ONE - W[1][s]);
+        v[s][10] = Fl[2][s] * (ONE - W[0][s]) * W[1][s];
+        v[s][11] = Fl[2][s] * W[0][s] * W[1][s];
+      }
+    }
+  }
+
+  // element offset of node n of zigzag_values() relative to the cell's own node
+  template <int D>
+  __device__ __forceinline__ long zigzag_offset(int n, long N1, long N12, long plane) {
+    if constexpr (D == 1) {
+      const int  di[5] = { 0, 0, 1, 0, 1 };
+      const int  cc[5] = { jx1, jx2, jx2, jx3, jx3 };
+      return di[n] + plane * cc[n];
+    } else if constexpr (D == 2) {
+      const int di[8] = { 0, 0, 0, 1, 0, 1, 0, 1 };
+      const int dj[8] = { 0, 1, 0, 0, 0, 0, 1, 1 };
+      const int cc[8] = { jx1, jx1, jx2, jx2, jx3, jx3, jx3, jx3 };
+      return di[n] + N1 * dj[n] + plane * cc[n];
+    } else {
+      const int di[12] = { 0, 0, 0, 0, 0, 1, 0, 1, 0, 1, 0, 1 };
+      const int dj[12] = { 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 1, 1 };
+      const int dk[12] = { 0, 0, 1, 1, 0, 0, 1, 1, 0, 0, 0, 0 };
+      const int cc[12] = { jx1, jx1, jx1, jx1, jx2, jx2, jx2, jx2, jx3, jx3, jx3, jx3 };
+      return di[n] + N1 * dj[n] + N12 * dk[n] + plane * cc[n];
+    }
+  }
+
+  // Must be called by all 32 lanes of the warp; `active` = this lane has a particle to deposit.
+  template <int D, int O>
+  __device__ __forceinline__ void deposit_particle_aggregated(const Prtl<D>& P, bool active,
+                                                              float charge, float inv_dt,
+                                                              float dxc, int G,
+                                                              const FieldView<D>& J) {
+    if constexpr (O == 0) {
+      constexpr int NV = ZigZag<D>::NV;
+      float         v[2][NV];
+      int           key0 = -1, key1 = -1;
+      bool          cross = false;
+      if (active) {
+        zigzag_values<D>(P, charge, inv_dt, dxc, v);
+        key0 = (int)J.idx(P.ip[0] + G, (D > 1) ? P.ip[1] + G : 0, (D > 2) ? P.ip[2] + G : 0);
+        key1 = (int)J.idx(P.i[0] + G, (D > 1) ? P.i[1] + G : 0, (D > 2) ? P.i[2] + G : 0);
+        cross = key0 != key1;
+        if (!cross) {
+#pragma unroll
+          for (int n = 0; n < NV; ++n) v[0][n] += v[1][n];
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < NV; ++n) v[0][n] = ZERO;
+      }
+      const WarpRun run = warp_runs(key0);
+      const long    N12 = (long)J.N1 * J.N2;
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        const float s = run_sum(v[0][n], run);
+        if (run.head && key0 >= 0) {
+          atomicAdd(J.p + key0 + zigzag_offset<D>(n, J.N1, N12, J.plane), s);
+        }
+      }
+      if (cross) {
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+          atomicAdd(J.p + key1 + zigzag_offset<D>(n, J.N1, N12, J.plane), v[1][n]);
+        }
+      }
+    } else {
+      // Esirkepov: key = origin of the (O+2)^D window; every lane walks the full window with
+      // zero for the nodes it does not touch, so all lanes issue the same shuffles
+      Prtl<D> Q = P;
+      if (!active) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          Q.i[a] = Q.ip[a] = 0;
+          Q.d[a] = Q.dp[a] = ZERO;
+          Q.u[a]           = ZERO;
+        }
+        Q.w = ZERO;
+      }
+      bool    first = true;
+      WarpRun run;
+      deposit_particle<D, O>(Q, charge, inv_dt, dxc, G,
+                             [&](int i, int j, int k, int c, float val, bool guard = true) {
+                               if (first) {
+                                 run   = warp_runs(active ? (int)J.idx(i, j, k) : -1);
+                                 first = false;
+                               }
+                               const float s = run_sum(guard ? val : ZERO, run);
+                               if (run.head && active && s != ZERO) {
+                                 atomicAdd(&J.at(i, j, k, c), s);
+                               }
+                             });
     }
   }
 

@@ -80,47 +80,64 @@ namespace eb200 {
       store_pushed<D>(S, p, P, tag);
     }
 
-    template <int D, int O>
+    template <int D, int O, bool AGG>
     __global__ void __launch_bounds__(256)
       deposit_atomic_kernel(eb200_prtls_t S, uint32_t npart, float charge, float inv_dt,
                             float dxc, int G, FieldView<D> J) {
-      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-      if (p >= npart) {
-        return;
-      }
-      if (S.tag[p] == 0) {
-        return;
+      const uint32_t p      = blockIdx.x * blockDim.x + threadIdx.x;
+      const bool     active = (p < npart) && (S.tag[p] != 0);
+      if constexpr (!AGG) {
+        if (!active) {
+          return;
+        }
       }
       Prtl<D> P;
-      load_prtl<D>(S, p, P, true);
-      deposit_particle<D, O>(P, charge, inv_dt, dxc, G, [&](int i, int j, int k, int c, float v) {
-        atomicAdd(&J.at(i, j, k, c), v);
-      });
+      if (active) {
+        load_prtl<D>(S, p, P, true);
+      }
+      if constexpr (AGG) {
+        deposit_particle_aggregated<D, O>(P, active, charge, inv_dt, dxc, G, J);
+      } else {
+        deposit_particle<D, O>(P, charge, inv_dt, dxc, G,
+                               [&](int i, int j, int k, int c, float v, bool guard = true) {
+                                 if (guard) atomicAdd(&J.at(i, j, k, c), v);
+                               });
+      }
     }
 
-    template <int D, int O>
+    template <int D, int O, bool AGG>
     __global__ void __launch_bounds__(256)
       push_deposit_kernel(PushArgs A, eb200_prtls_t S, uint32_t npart, FieldView<D> EB,
                           float charge, float inv_dt, FieldView<D> J) {
-      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-      if (p >= npart) {
-        return;
+      const uint32_t p   = blockIdx.x * blockDim.x + threadIdx.x;
+      short          tag = 0;
+      if (p < npart) {
+        tag = S.tag[p];
       }
-      const short tag = S.tag[p];
-      if (tag != 1) {
-        return;
+      bool active = (tag == 1);
+      if constexpr (!AGG) {
+        if (!active) {
+          return;
+        }
       }
       Prtl<D> P;
-      load_prtl<D>(S, p, P, false);
-      P.tag  = tag;
-      auto F = [&](int i, int j, int k, int c) { return EB.ld(i, j, k, c); };
-      push_particle<D, O>(A, F, P);
-      store_pushed<D>(S, p, P, tag);
-      if (P.tag != 0) {
-        deposit_particle<D, O>(P, charge, inv_dt, A.c.dx, A.ng,
-                               [&](int i, int j, int k, int c, float v) {
-                                 atomicAdd(&J.at(i, j, k, c), v);
-                               });
+      if (active) {
+        load_prtl<D>(S, p, P, false);
+        P.tag  = tag;
+        auto F = [&](int i, int j, int k, int c) { return EB.ld(i, j, k, c); };
+        push_particle<D, O>(A, F, P);
+        store_pushed<D>(S, p, P, tag);
+        active = (P.tag != 0);
+      }
+      if constexpr (AGG) {
+        deposit_particle_aggregated<D, O>(P, active, charge, inv_dt, A.c.dx, A.ng, J);
+      } else {
+        if (active) {
+          deposit_particle<D, O>(P, charge, inv_dt, A.c.dx, A.ng,
+                                 [&](int i, int j, int k, int c, float v, bool guard = true) {
+                                   if (guard) atomicAdd(&J.at(i, j, k, c), v);
+                                 });
+        }
       }
     }
 
@@ -155,10 +172,12 @@ namespace eb200 {
         Prtl<D> P;
         load_prtl<D>(S, p, P, true);
         deposit_particle<D, O>(P, charge, inv_dt, dxc, G,
-                               [&](int i, int j, int k, int c, float v) {
-                                 kout[n] = (uint32_t)(J.idx(i, j, k) + J.plane * c);
-                                 vout[n] = v;
-                                 ++n;
+                               [&](int i, int j, int k, int c, float v, bool guard = true) {
+                                 if (guard) {
+                                   kout[n] = (uint32_t)(J.idx(i, j, k) + J.plane * c);
+                                   vout[n] = v;
+                                   ++n;
+                                 }
                                });
       }
       for (; n < K; ++n) {
@@ -204,7 +223,13 @@ namespace eb200 {
       FieldView<D> J(g, cur);
       const float  inv_dt = ONE / dt;
       if (mode == EB200_DEPOSIT_ATOMIC) {
-        deposit_atomic_kernel<D, O>
+        deposit_atomic_kernel<D, O, false>
+          <<<(npart + 255) / 256, 256, 0, st>>>(S, npart, charge, inv_dt, dxc, g.ng, J);
+        count_launch();
+        return cudaGetLastError();
+      }
+      if (mode == EB200_DEPOSIT_AGGREGATED) {
+        deposit_atomic_kernel<D, O, true>
           <<<(npart + 255) / 256, 256, 0, st>>>(S, npart, charge, inv_dt, dxc, g.ng, J);
         count_launch();
         return cudaGetLastError();
@@ -242,12 +267,17 @@ namespace eb200 {
     template <int D, int O>
     cudaError_t launch_push_deposit(const PushArgs& A, const eb200_prtls_t& S, uint32_t npart,
                                     const eb200_grid_t& g, const float* em, float* cur,
-                                    cudaStream_t st) {
+                                    int mode, cudaStream_t st) {
       if (npart == 0) return cudaSuccess;
       FieldView<D> EB(g, const_cast<float*>(em));
       FieldView<D> J(g, cur);
-      push_deposit_kernel<D, O><<<(npart + 255) / 256, 256, 0, st>>>(
-        A, S, npart, EB, A.c.charge, ONE / A.c.dt, J);
+      if (mode == EB200_DEPOSIT_AGGREGATED) {
+        push_deposit_kernel<D, O, true><<<(npart + 255) / 256, 256, 0, st>>>(
+          A, S, npart, EB, A.c.charge, ONE / A.c.dt, J);
+      } else {
+        push_deposit_kernel<D, O, false><<<(npart + 255) / 256, 256, 0, st>>>(
+          A, S, npart, EB, A.c.charge, ONE / A.c.dt, J);
+      }
       count_launch();
       return cudaGetLastError();
     }
@@ -292,13 +322,13 @@ namespace eb200 {
 
     cudaError_t push_deposit_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,
                                 const eb200_prtls_t& S, uint32_t npart, const float* em,
-                                float* cur, cudaStream_t st) {
+                                float* cur, int mode, cudaStream_t st) {
       PushArgs A;
       A.c   = c;
       A.ndh = HALF * (c.charge / c.mass) * c.omegaB0 * c.dt;
       A.ng  = g.ng;
       for (int a = 0; a < 3; ++a) A.ni[a] = g.n[a];
-#define CALL(D, O) launch_push_deposit<D, O>(A, S, npart, g, em, cur, st)
+#define CALL(D, O) launch_push_deposit<D, O>(A, S, npart, g, em, cur, mode, st)
       EB200_DISPATCH_DO(g.dim, order, CALL)
 #undef CALL
     }

@@ -11,7 +11,7 @@ PUSHER_NONE, PUSHER_PHOTON, PUSHER_BORIS, PUSHER_VAY, PUSHER_GCA = 0, 1, 2, 4, 8
 DRAG_NONE, DRAG_SYNCHROTRON, DRAG_COMPTON = 0, 1, 2
 PBC_NONE, PBC_PERIODIC, PBC_ABSORB, PBC_REFLECT, PBC_AXIS = 0, 1, 2, 3, 4
 FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC = 0, 1, 2, 3, 4
-DEPOSIT_ATOMIC, DEPOSIT_ORDERED = 0, 1
+DEPOSIT_ATOMIC, DEPOSIT_ORDERED, DEPOSIT_AGGREGATED = 0, 1, 2
 
 PHASES = ["FieldSolver", "PushDeposit", "CurrentFiltering", "Communications", "ParticleSort"]
 
@@ -128,7 +128,7 @@ def load():
     lib.eb200_deposit.argtypes = [ctxp, C.POINTER(Prtls), C.c_uint32, C.c_float, C.c_float, vp,
                                   C.c_int, vp]
     lib.eb200_push_deposit_sr.argtypes = [ctxp, C.POINTER(Pusher), C.POINTER(Prtls), C.c_uint32,
-                                          vp, vp, vp]
+                                          vp, vp, C.c_int, vp]
     lib.eb200_zero_currents.argtypes = [ctxp, vp, vp]
     lib.eb200_comm_fields.argtypes = [ctxp, vp, C.c_int, C.c_int, C.c_int, i32p, vp]
     lib.eb200_sync_currents.argtypes = [ctxp, vp, vp, i32p, vp]
@@ -272,10 +272,10 @@ class Context:
         self._check(self.lib.eb200_deposit(self.handle, C.byref(s), npart, charge, dt, _ptr(cur),
                                            mode, self._stream(stream)))
 
-    def push_deposit(self, pusher, arrays, npart, em, cur, stream=None):
+    def push_deposit(self, pusher, arrays, npart, em, cur, mode=DEPOSIT_ATOMIC, stream=None):
         s = self.prtls_struct(arrays)
         self._check(self.lib.eb200_push_deposit_sr(self.handle, C.byref(pusher), C.byref(s),
-                                                   npart, _ptr(em), _ptr(cur),
+                                                   npart, _ptr(em), _ptr(cur), mode,
                                                    self._stream(stream)))
 
     def zero_currents(self, cur, stream=None):

@@ -56,7 +56,12 @@ enum { EB200_PBC_NONE = 0, EB200_PBC_PERIODIC = 1, EB200_PBC_ABSORB = 2, EB200_P
 enum { EB200_FBC_NONE = 0, EB200_FBC_PERIODIC = 1, EB200_FBC_CONDUCTOR = 2, EB200_FBC_AXIS = 3, EB200_FBC_SYNC = 4 };
 enum { EB200_METRIC_MINKOWSKI = 0 };
 /* deposit modes */
-enum { EB200_DEPOSIT_ATOMIC = 0, EB200_DEPOSIT_ORDERED = 1 };
+enum {
+  EB200_DEPOSIT_ATOMIC     = 0, /* one atomic add per particle and node (what Kokkos ScatterView does on CUDA) */
+  EB200_DEPOSIT_ORDERED    = 1, /* deterministic: every J element summed in particle order */
+  EB200_DEPOSIT_AGGREGATED = 2  /* warp-aggregated: runs of same-cell lanes are reduced with shuffles,
+                                   one atomic per run and node; meant for cell-sorted particles */
+};
 
 typedef struct eb200_ctx eb200_ctx_t;
 typedef void*            eb200_stream_t;
@@ -156,14 +161,15 @@ int eb200_push_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher, const eb200_pr
                   uint32_t npart, const float* em, eb200_stream_t stream);
 /* one species of srpic::CurrentsDeposit (currents.h:32-62, currents_deposit.hpp:108-761):
  * accumulates into cur (the caller zeroes it once per step with eb200_zero_currents, as
- * currents.h:67 does). mode = EB200_DEPOSIT_ATOMIC | EB200_DEPOSIT_ORDERED; ORDERED sums every
- * J element in particle order (the reference's Serial-backend order) and is bit-reproducible. */
+ * currents.h:67 does). mode = EB200_DEPOSIT_*; ORDERED sums every J element in particle order
+ * (the reference's Serial-backend order) and is bit-reproducible. */
 int eb200_deposit(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, float charge,
                   float dt, float* cur, int mode, eb200_stream_t stream);
-/* fused ParticlePush + CurrentsDeposit of one species in a single pass over the particles */
+/* fused ParticlePush + CurrentsDeposit of one species in a single pass over the particles;
+ * mode = EB200_DEPOSIT_ATOMIC | EB200_DEPOSIT_AGGREGATED */
 int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
                           const eb200_prtls_t* prtls, uint32_t npart, const float* em, float* cur,
-                          eb200_stream_t stream);
+                          int mode, eb200_stream_t stream);
 int eb200_zero_currents(eb200_ctx_t* ctx, float* cur, eb200_stream_t stream);
 
 /* ------------------------------------------------- single-domain ghost exchange */

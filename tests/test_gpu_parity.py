@@ -155,11 +155,24 @@ def test_push_deposit_strict(eb, orc_mod, dim, order, case):
 @pytest.mark.parametrize("dim", [1, 2, 3])
 @pytest.mark.parametrize("order", [0, 1, 2, 3])
 @pytest.mark.parametrize("fused", [False, True])
-def test_push_deposit_fast(eb, orc_mod, dim, order, fused):
-    """Fast build (FMA contraction, atomic deposit, optional fusion): fp32 tolerance."""
+@pytest.mark.parametrize("mode", ["atomic", "aggregated", "aggregated_sorted"])
+def test_push_deposit_fast(eb, orc_mod, dim, order, fused, mode):
+    """Fast build (FMA contraction; atomic or warp-aggregated deposit on random-order and on
+    cell-sorted particles; optional fusion): fp32 tolerance."""
     orc = orc_mod.oracle()
     g, ctx, octx, gctx, em, p, pbc, dx = _setup_push(eb, orc_mod, dim, order, 0, False, n=20000)
     n = p.n
+    if mode == "aggregated_sorted":
+        # long runs of same-cell lanes: the case the aggregation is built for
+        key = p.i1.astype(np.int64)
+        if dim > 1:
+            key = key + g.n[0] * p.i2.astype(np.int64)
+        if dim > 2:
+            key = key + g.n[0] * g.n[1] * p.i3.astype(np.int64)
+        perm = np.argsort(key, kind="stable")
+        for nm in p.names():
+            getattr(p, nm)[:] = getattr(p, nm)[perm]
+    dmode = eb.DEPOSIT_ATOMIC if mode == "atomic" else eb.DEPOSIT_AGGREGATED
     d_em = dev(em)
     arr = to_device(p)
     j_ref = np.zeros(g.shape(3), np.float32)
@@ -167,10 +180,10 @@ def test_push_deposit_fast(eb, orc_mod, dim, order, fused):
     orc.push(g, order, octx, p, n, em)
     orc.deposit(g, order, p, n, -1.0, octx.dt, dx, j_ref)
     if fused:
-        ctx.push_deposit(gctx, arr, n, d_em, d_j)
+        ctx.push_deposit(gctx, arr, n, d_em, d_j, mode=dmode)
     else:
         ctx.push(gctx, arr, n, d_em)
-        ctx.deposit(arr, n, -1.0, octx.dt, d_j)
+        ctx.deposit(arr, n, -1.0, octx.dt, d_j, mode=dmode)
     q = to_host(arr, n)
     for nm in ("i1", "i2", "i3", "i1_prev", "i2_prev", "i3_prev", "tag"):
         # a particle within rounding of a cell face may land on the other side: allow a handful

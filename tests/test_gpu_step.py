@@ -70,11 +70,13 @@ def test_step_strict_exact(mods, case):
 
 
 @pytest.mark.parametrize("fused", [False, True])
-def test_step_fast_tolerance(mods, fused):
+@pytest.mark.parametrize("agg", [False, True])
+def test_step_fast_tolerance(mods, fused, agg):
     """fast-fp (FMA contraction, atomic deposit, optionally fused push+deposit, sorting on):
     particle counts identical, fields/currents/energy within fp32 tolerance over the window."""
     eb, wl, orc, pic = mods
-    sim = wl.two_stream((64, 48), ppc0=16, fused=fused, sort_interval=2)
+    sim = wl.two_stream((64, 48), ppc0=16, fused=fused, sort_interval=2,
+                        deposit_mode=eb.DEPOSIT_AGGREGATED if agg else eb.DEPOSIT_ATOMIC)
     osim = pic.from_device_sim(sim)
     for step in range(8):
         sim.step()
