@@ -69,6 +69,35 @@ def _compile(unit, verbose):
     return obj
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Experiment helper: a second copy of the library with extra -D flags on particles.cu
+    (fast variant only), written to build/variants/<name>.so; select it with EB200_LIB."""
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    build()
+    obj = os.path.join(vdir, f"particles.fast.{name}.o")
+    cmd = [NVCC, *ARCH, *COMMON, "-DEB200_STRICT=0", *defines, "-Xptxas=-v", "-c",
+           os.path.join(CSRC, "particles.cu"), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    info = [l for l in r.stderr.split("\n")]
+    for k, l in enumerate(info):
+        if "push_deposit_kernelILi2ELi0ELb1" in l and "Compiling" in l:
+            print(name, info[k + 2].strip(), "|", info[k + 3].strip() if k + 3 < len(info) else "")
+    objs = []
+    for src, tag, _ in UNITS:
+        o = os.path.join(OBJ, f"{os.path.splitext(src)[0]}.{tag}.o")
+        if os.path.exists(o):
+            objs.append(obj if (src, tag) == ("particles.cu", "fast") else o)
+    out = os.path.join(vdir, f"{name}.so")
+    r = subprocess.run([NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart_static", "-ldl",
+                        "-lrt", "-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    return out
+
+
 def build(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     if force:

@@ -116,6 +116,34 @@ namespace eb200 {
     }
   }
 
+  /* ------------------------------------------------- reciprocal / rsqrt / divide */
+  // Strict build: IEEE division and square root in the reference's operation order.
+  // Fast build: MUFU.RCP / MUFU.RSQ based forms (<= 2 ulp), an order of magnitude fewer
+  // instructions than the IEEE sequences; covered by the fast-build tolerances in tests/.
+  __device__ __forceinline__ float rcp_sqrt(float x) {
+#if EB200_STRICT
+    return ONE / sqrtf(x);
+#else
+    return rsqrtf(x);
+#endif
+  }
+
+  __device__ __forceinline__ float div_by_sqrt(float a, float x) {
+#if EB200_STRICT
+    return a / sqrtf(x);
+#else
+    return a * rsqrtf(x);
+#endif
+  }
+
+  __device__ __forceinline__ float fdiv(float a, float b) {
+#if EB200_STRICT
+    return a / b;
+#else
+    return __fdividef(a, b);
+#endif
+  }
+
   /* ---------------------------------------------------------------- vector ops */
   __device__ __forceinline__ float dot3(const float* a, const float* b) {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
@@ -248,11 +276,11 @@ namespace eb200 {
     e0[1] *= c;
     e0[2] *= c;
     float u0[3] = { u[0] + e0[0], u[1] + e0[1], u[2] + e0[2] };
-    c *= ONE / sqrtf(ONE + nsq(u0));
+    c *= rcp_sqrt(ONE + nsq(u0));
     b0[0] *= c;
     b0[1] *= c;
     b0[2] *= c;
-    c = TWO / (ONE + nsq(b0));
+    c = fdiv(TWO, ONE + nsq(b0));
     float x[3], u1[3];
     cross3(u0, b0, x);
     u1[0] = (u0[0] + x[0]) * c;
@@ -359,12 +387,28 @@ namespace eb200 {
     int            ng;
   };
 
-  template <int D, int O, class EM>
+  // LEAN: the context is known (host-side check, see lean_pusher()) to be a plain Boris push
+  // without drag, atmosphere or GCA; the optional branches are compiled out.
+  __host__ __device__ __forceinline__ bool lean_pusher(const eb200_pusher_t& c) {
+    return c.pusher_flags == EB200_PUSHER_BORIS && c.drag_flags == EB200_DRAG_NONE &&
+           !c.has_atmosphere;
+  }
+
+  template <int D, int O, class EM, bool LEAN = false>
   __device__ __forceinline__ void push_particle(const PushArgs& A, const EM& F, Prtl<D>& P) {
     const eb200_pusher_t& c  = A.c;
     const float           dt = c.dt;
     bool                  massive = true;
-    if (c.pusher_flags == EB200_PUSHER_PHOTON) {
+    if constexpr (LEAN) {
+      float ec[3], bc[3];
+      gather_fields<D, O>(F, A.ng, P, ec, bc);
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        ec[a] = ec[a] * c.dx;
+        bc[a] = bc[a] * c.dx;
+      }
+      boris(A.ndh, P.u, ec, bc);
+    } else if (c.pusher_flags == EB200_PUSHER_PHOTON) {
       massive = false;
     } else {
       float ec[3], bc[3];
@@ -440,12 +484,12 @@ namespace eb200 {
     // Cartesian i+dx position update
     const float g2 = massive ? (ONE + SQR(P.u[0]) + SQR(P.u[1]) + SQR(P.u[2]))
                              : (SQR(P.u[0]) + SQR(P.u[1]) + SQR(P.u[2]));
-    const float dt_inv_energy = dt / sqrtf(g2);
+    const float dt_inv_energy = div_by_sqrt(dt, g2);
 #pragma unroll
     for (int a = 0; a < D; ++a) {
       P.ip[a]  = P.i[a];
       P.dp[a]  = P.d[a];
-      float dx = P.d[a] + (P.u[a] / c.dx) * dt_inv_energy;
+      float dx = P.d[a] + fdiv(P.u[a], c.dx) * dt_inv_energy;
       P.i[a]  += static_cast<int>(dx >= ONE) - static_cast<int>(dx < ZERO);
       dx      -= static_cast<float>(dx >= ONE);
       dx      += static_cast<float>(dx < ZERO);
@@ -503,10 +547,10 @@ namespace eb200 {
                                                    float dxc, int G, SINK&& J) {
     float vp[3];
     {
-      vp[0] = (0 < D) ? P.u[0] / dxc : P.u[0];
-      vp[1] = (1 < D) ? P.u[1] / dxc : P.u[1];
-      vp[2] = (2 < D) ? P.u[2] / dxc : P.u[2];
-      const float inv_energy = ONE / sqrtf(ONE + nsq(P.u));
+      vp[0] = (0 < D) ? fdiv(P.u[0], dxc) : P.u[0];
+      vp[1] = (1 < D) ? fdiv(P.u[1], dxc) : P.u[1];
+      vp[2] = (2 < D) ? fdiv(P.u[2], dxc) : P.u[2];
+      const float inv_energy = rcp_sqrt(ONE + nsq(P.u));
       if (isnan(vp[2]) || isinf(vp[2])) {
         vp[2] = ZERO;
       }
@@ -735,8 +779,8 @@ namespace eb200 {
   // the head lane of each run issues the atomic. Correct for any order of the particles:
   // an unsorted warp just degrades to one run per lane.
   struct WarpRun {
-    bool head;
-    int  end; // last lane of the run this lane belongs to
+    bool  head;
+    float m[5]; // m[l] = 1 if lane + 2^l is still inside this lane's run, else 0
   };
 
   __device__ __forceinline__ WarpRun warp_runs(int key) {
@@ -746,20 +790,21 @@ namespace eb200 {
     const unsigned heads = __ballot_sync(0xffffffffu, head);
     const unsigned above = (lane == 31u) ? 0u : (heads & ~((2u << lane) - 1u));
     WarpRun        r;
-    r.head = head;
-    r.end  = above ? (__ffs(above) - 2) : 31;
+    r.head        = head;
+    const int end = above ? (__ffs(above) - 2) : 31; // last lane of this lane's run
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      r.m[l] = (static_cast<int>(lane) + (1 << l) <= end) ? ONE : ZERO;
+    }
     return r;
   }
 
   // sum of v over the run; valid on the head lane
   __device__ __forceinline__ float run_sum(float v, const WarpRun& r) {
-    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const float o = __shfl_down_sync(0xffffffffu, v, d);
-      if (lane + d <= r.end) {
-        v += o;
-      }
+    for (int l = 0; l < 5; ++l) {
+      // one FFMA per level; o * 1 and o * 0 are exact for finite o
+      v = fmaf(__shfl_down_sync(0xffffffffu, v, 1 << l), r.m[l], v);
     }
     return v;
   }
@@ -775,10 +820,10 @@ namespace eb200 {
   __device__ __forceinline__ void zigzag_values(const Prtl<D>& P, float charge, float inv_dt,
                                                 float dxc, float (&v)[2][ZigZag<D>::NV]) {
     float vp[3];
-    vp[0] = (0 < D) ? P.u[0] / dxc : P.u[0];
-    vp[1] = (1 < D) ? P.u[1] / dxc : P.u[1];
-    vp[2] = (2 < D) ? P.u[2] / dxc : P.u[2];
-    const float inv_energy = ONE / sqrtf(ONE + nsq(P.u));
+    vp[0] = (0 < D) ? fdiv(P.u[0], dxc) : P.u[0];
+    vp[1] = (1 < D) ? fdiv(P.u[1], dxc) : P.u[1];
+    vp[2] = (2 < D) ? fdiv(P.u[2], dxc) : P.u[2];
+    const float inv_energy = rcp_sqrt(ONE + nsq(P.u));
     if (isnan(vp[2]) || isinf(vp[2])) {
       vp[2] = ZERO;
     }
@@ -789,12 +834,25 @@ namespace eb200 {
     float       W[3][2], Fl[3][2];
 #pragma unroll
     for (int a = 0; a < D; ++a) {
+#if EB200_STRICT
       const int   up = static_cast<int>(P.i[a] > P.ip[a]);
       const float r  = static_cast<float>(P.i[a] == P.ip[a]) * (P.d[a] + P.dp[a]) * INV_2;
       W[a][0]        = INV_2 * (r + P.dp[a] + static_cast<float>(up));
       W[a][1]        = INV_2 * (P.d[a] + r + static_cast<float>(up + P.ip[a] - P.i[a]));
       Fl[a][0]       = (static_cast<float>(up) + r - P.dp[a]) * coeff * inv_dt;
       Fl[a][1] = (static_cast<float>(P.i[a] - P.ip[a] - up) + P.d[a] - r) * coeff * inv_dt;
+#else
+      // same relay point, written with selects: r0 / r1 = relay coordinate seen from the old /
+      // new cell (midpoint when the particle stays, the shared face when it crosses)
+      const int   di = P.i[a] - P.ip[a];
+      const float r0 = (di == 0) ? INV_2 * (P.d[a] + P.dp[a]) : ((di > 0) ? ONE : ZERO);
+      const float r1 = (di == 0) ? r0 : ((di > 0) ? ZERO : ONE);
+      const float Q  = coeff * inv_dt;
+      W[a][0]        = INV_2 * (r0 + P.dp[a]);
+      W[a][1]        = INV_2 * (P.d[a] + r1);
+      Fl[a][0]       = (r0 - P.dp[a]) * Q;
+      Fl[a][1]       = (P.d[a] - r1) * Q;
+#endif
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -830,6 +888,66 @@ namespace eb200 {
         v[s][11] = Fl[2][s] * W[0][s] * W[1][s];
       }
     }
+  }
+
+  // Zig-zag contributions of a particle that stays inside its cell, both segments summed.
+  // Algebraically identical to zigzag_values() (the relay point is the midpoint, so both
+  // half-segments carry half of the displacement and the node weights are evaluated at the
+  // quarter points); the closed form needs ~1/4 of the operations. Fast build only: the
+  // rounding differs from the reference's operation order at the 1e-7 level.
+  template <int D>
+  __device__ __forceinline__ void zigzag_values_incell(const Prtl<D>& P, float charge,
+                                                       float inv_dt, float dxc,
+                                                       float (&v)[ZigZag<D>::NV]) {
+    const float inv_energy = rcp_sqrt(ONE + nsq(P.u));
+    const float coeff      = P.w * charge;
+    const float Q          = coeff * inv_dt;
+    float       m[3], dl[3];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      m[a]  = HALF * (P.d[a] + P.dp[a]);
+      dl[a] = P.d[a] - P.dp[a];
+    }
+    if constexpr (D == 1) {
+      float v2 = P.u[1] * inv_energy, v3 = P.u[2] * inv_energy;
+      if (isnan(v3) || isinf(v3)) v3 = ZERO;
+      const float F2 = v2 * coeff, F3 = v3 * coeff;
+      v[0] = Q * dl[0];
+      v[1] = F2 * (ONE - m[0]);
+      v[2] = F2 * m[0];
+      v[3] = F3 * (ONE - m[0]);
+      v[4] = F3 * m[0];
+    } else if constexpr (D == 2) {
+      float v3 = P.u[2] * inv_energy;
+      if (isnan(v3) || isinf(v3)) v3 = ZERO;
+      const float A = Q * dl[0], B = Q * dl[1], F = v3 * coeff;
+      v[0]          = A * (ONE - m[1]);
+      v[1]          = A * m[1];
+      v[2]          = B * (ONE - m[0]);
+      v[3]          = B * m[0];
+      const float c = INV_16 * dl[0] * dl[1]; // (dx/4)(dy/4): the two quarter-point products
+      v[4]          = F * ((ONE - m[0]) * (ONE - m[1]) + c);
+      v[5]          = F * (m[0] * (ONE - m[1]) - c);
+      v[6]          = F * ((ONE - m[0]) * m[1] - c);
+      v[7]          = F * (m[0] * m[1] + c);
+    } else {
+      const float A = Q * dl[0], B = Q * dl[1], C = Q * dl[2];
+      const float c12 = INV_16 * dl[0] * dl[1], c13 = INV_16 * dl[0] * dl[2],
+                  c23 = INV_16 * dl[1] * dl[2];
+      v[0]  = A * ((ONE - m[1]) * (ONE - m[2]) + c23);
+      v[1]  = A * (m[1] * (ONE - m[2]) - c23);
+      v[2]  = A * ((ONE - m[1]) * m[2] - c23);
+      v[3]  = A * (m[1] * m[2] + c23);
+      v[4]  = B * ((ONE - m[0]) * (ONE - m[2]) + c13);
+      v[5]  = B * (m[0] * (ONE - m[2]) - c13);
+      v[6]  = B * ((ONE - m[0]) * m[2] - c13);
+      v[7]  = B * (m[0] * m[2] + c13);
+      v[8]  = C * ((ONE - m[0]) * (ONE - m[1]) + c12);
+      v[9]  = C * (m[0] * (ONE - m[1]) - c12);
+      v[10] = C * ((ONE - m[0]) * m[1] - c12);
+      v[11] = C * (m[0] * m[1] + c12);
+    }
+    (void)dxc;
   }
 
   // element offset of node n of zigzag_values() relative to the cell's own node
@@ -881,8 +999,16 @@ namespace eb200 {
       const long    N12 = (long)J.N1 * J.N2;
 #pragma unroll
       for (int n = 0; n < NV; ++n) {
+#ifdef EB200_X_NOREDUCE
+        const float s = v[0][n];
+#else
         const float s = run_sum(v[0][n], run);
+#endif
+#ifdef EB200_X_NORED
+        if (run.head && key0 >= 0 && s == 1.2345e-30f) {
+#else
         if (run.head && key0 >= 0) {
+#endif
           atomicAdd(J.p + key0 + zigzag_offset<D>(n, J.N1, N12, J.plane), s);
         }
       }

@@ -105,14 +105,20 @@ namespace eb200 {
       }
     }
 
+#ifndef EB200_PD_MINBLOCKS
+  #define EB200_PD_MINBLOCKS 1
+#endif
     template <int D, int O, bool AGG>
-    __global__ void __launch_bounds__(256)
-      push_deposit_kernel(PushArgs A, eb200_prtls_t S, uint32_t npart, FieldView<D> EB,
-                          float charge, float inv_dt, FieldView<D> J) {
-      const uint32_t p   = blockIdx.x * blockDim.x + threadIdx.x;
+    __global__ void __launch_bounds__(256, EB200_PD_MINBLOCKS)
+      push_deposit_kernel(PushArgs A, eb200_prtls_t S, uint32_t p_begin, uint32_t npart,
+                          FieldView<D> EB, float charge, float inv_dt, FieldView<D> J) {
+      const uint32_t p   = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
       short          tag = 0;
+      Prtl<D>        P;
       if (p < npart) {
+        // tag and state are requested together: one DRAM round trip, not two
         tag = S.tag[p];
+        load_prtl<D>(S, p, P, false);
       }
       bool active = (tag == 1);
       if constexpr (!AGG) {
@@ -120,15 +126,23 @@ namespace eb200 {
           return;
         }
       }
-      Prtl<D> P;
       if (active) {
-        load_prtl<D>(S, p, P, false);
         P.tag  = tag;
+#ifdef EB200_X_NOGATHER
+        auto F = [&](int i, int j, int k, int c) { return 1e-3f * (float)(c + 1) + 1e-6f * (float)i; };
+#else
         auto F = [&](int i, int j, int k, int c) { return EB.ld(i, j, k, c); };
+#endif
         push_particle<D, O>(A, F, P);
+#ifdef EB200_X_NOSTORE
+        if (P.u[0] == 1.2345e-30f)
+#endif
         store_pushed<D>(S, p, P, tag);
         active = (P.tag != 0);
       }
+#ifdef EB200_X_NODEPOSIT
+      if (P.u[1] != 1.2345e-30f) return;
+#endif
       if constexpr (AGG) {
         deposit_particle_aggregated<D, O>(P, active, charge, inv_dt, A.c.dx, A.ng, J);
       } else {
@@ -138,6 +152,251 @@ namespace eb200 {
                                    if (guard) atomicAdd(&J.at(i, j, k, c), v);
                                  });
         }
+      }
+    }
+
+
+    /* ------------------------------------------- TMA-staged persistent push + deposit */
+    // The throughput kernel. One persistent CTA per SM slot streams chunks of 256 particles:
+    //  * the SoA slices of a chunk travel global -> shared with cp.async.bulk (TMA), three
+    //    chunks deep, completion tracked by mbarriers: no warp ever waits on DRAM, no
+    //    registers hold loads in flight, and there is no per-thread address arithmetic;
+    //  * results go shared -> global with cp.async.bulk as well; i_prev / dx_prev are stored
+    //    straight from the staged input slices (they ARE the old i / dx);
+    //  * the deposit is the warp-aggregated one (one atomic per run of same-cell lanes).
+    // Chunks that are not a full 256 particles are left to the per-thread kernel.
+    namespace tma {
+      __device__ __forceinline__ uint32_t saddr(const void* p) {
+        return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+      }
+
+      __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count));
+      }
+
+      __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)),
+                     "r"(bytes)
+                     : "memory");
+      }
+
+      __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "WAIT_%=:\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                     "@p bra DONE_%=;\n"
+                     "bra WAIT_%=;\n"
+                     "DONE_%=:\n"
+                     "}" ::"r"(saddr(bar)),
+                     "r"(parity)
+                     : "memory");
+      }
+
+      __device__ __forceinline__ void g2s(void* dst, const void* src, unsigned bytes,
+                                          uint64_t* bar) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+                     "[%1], %2, [%3];" ::"r"(saddr(dst)),
+                     "l"(src), "r"(bytes), "r"(saddr(bar))
+                     : "memory");
+      }
+
+      __device__ __forceinline__ void s2g(void* dst, const void* src, unsigned bytes) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                     "r"(saddr(src)), "r"(bytes)
+                     : "memory");
+      }
+
+      __device__ __forceinline__ void commit() {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+
+      __device__ __forceinline__ void wait_read_all() {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+
+      __device__ __forceinline__ void wait_all() {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+
+      __device__ __forceinline__ void fence_async_smem() {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+
+      __device__ __forceinline__ void fence_mbar_init() {
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+    } // namespace tma
+
+    constexpr int STREAM_CHUNK  = 256;
+    constexpr int STREAM_STAGES = 3;
+
+    template <int D>
+    struct alignas(128) StreamIn {
+      int   i[D][STREAM_CHUNK];
+      float d[D][STREAM_CHUNK];
+      float u[3][STREAM_CHUNK];
+      float w[STREAM_CHUNK];
+      short tag[STREAM_CHUNK];
+    };
+
+    template <int D>
+    struct alignas(128) StreamOut {
+      int   i[D][STREAM_CHUNK];
+      float d[D][STREAM_CHUNK];
+      float u[3][STREAM_CHUNK];
+    };
+
+    template <int D>
+    struct StreamSmem {
+      StreamIn<D>  in[STREAM_STAGES];
+      StreamOut<D> out;
+      uint64_t     full[STREAM_STAGES];
+    };
+
+    template <int D>
+    __device__ __forceinline__ void stream_issue_load(StreamIn<D>& st, uint64_t* bar,
+                                                      const eb200_prtls_t& S, size_t p0) {
+      constexpr unsigned B4 = STREAM_CHUNK * 4, B2 = STREAM_CHUNK * 2;
+      tma::mbar_expect_tx(bar, (2 * D + 4) * B4 + B2);
+      const int*   ii[3] = { S.i1, S.i2, S.i3 };
+      const float* dd[3] = { S.dx1, S.dx2, S.dx3 };
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        tma::g2s(st.i[a], ii[a] + p0, B4, bar);
+        tma::g2s(st.d[a], dd[a] + p0, B4, bar);
+      }
+      tma::g2s(st.u[0], S.ux1 + p0, B4, bar);
+      tma::g2s(st.u[1], S.ux2 + p0, B4, bar);
+      tma::g2s(st.u[2], S.ux3 + p0, B4, bar);
+      tma::g2s(st.w, S.weight + p0, B4, bar);
+      tma::g2s(st.tag, S.tag + p0, B2, bar);
+    }
+
+#ifndef EB200_STREAM_MINBLOCKS
+  #define EB200_STREAM_MINBLOCKS 3
+#endif
+    // resident CTAs per SM the register allocation aims for: the zig-zag body fits 3 x 256
+    // threads; the Esirkepov windows need the registers more than the occupancy
+    constexpr int stream_minblocks(int D, int O) {
+      return (O == 0) ? EB200_STREAM_MINBLOCKS : ((D == 3 && O >= 2) ? 1 : 2);
+    }
+
+    template <int D, int O, bool LEAN>
+    __global__ void __launch_bounds__(STREAM_CHUNK, stream_minblocks(D, O))
+      push_deposit_stream_kernel(PushArgs A, eb200_prtls_t S, uint32_t nchunks, FieldView<D> EB,
+                                 float charge, float inv_dt, FieldView<D> J) {
+      extern __shared__ __align__(128) unsigned char smem_raw[];
+      StreamSmem<D>& sm  = *reinterpret_cast<StreamSmem<D>*>(smem_raw);
+      const int      tid = threadIdx.x;
+      if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STREAM_STAGES; ++s) tma::mbar_init(&sm.full[s], 1);
+        tma::fence_mbar_init();
+      }
+      __syncthreads();
+      // chunks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+      const uint32_t first = blockIdx.x, stride = gridDim.x;
+      if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STREAM_STAGES - 1; ++s) {
+          const uint32_t c = first + s * stride;
+          if (c < nchunks) {
+            stream_issue_load<D>(sm.in[s], &sm.full[s], S, (size_t)c * STREAM_CHUNK);
+          }
+        }
+      }
+      auto F = [&](int i, int j, int k, int c) { return EB.ld(i, j, k, c); };
+      int      stage = 0;
+      unsigned phase = 0;
+      for (uint32_t c = first; c < nchunks; c += stride) {
+        StreamIn<D>& st = sm.in[stage];
+        tma::mbar_wait(&sm.full[stage], phase);
+        const size_t p   = (size_t)c * STREAM_CHUNK + tid;
+        const short  tag = st.tag[tid];
+        Prtl<D>      P;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          P.i[a] = P.ip[a] = (a < D) ? st.i[a][tid] : 0;
+          P.d[a] = P.dp[a] = (a < D) ? st.d[a][tid] : ZERO;
+          P.u[a]           = st.u[a][tid];
+        }
+        P.w         = st.w[tid];
+        P.tag       = tag;
+        bool active = (tag == 1);
+        if (active) {
+          push_particle<D, O, decltype(F), LEAN>(A, F, P);
+          if (P.tag != tag) {
+            S.tag[p] = P.tag;
+          }
+        }
+        deposit_particle_aggregated<D, O>(P, active && P.tag != 0, charge, inv_dt, A.c.dx, A.ng,
+                                          J);
+        // the previous chunk's bulk stores must have finished reading `out` (and the stage
+        // that is refilled below) before anybody overwrites them
+        if (tid == 0) {
+          tma::wait_read_all();
+        }
+        const int not_all_alive = __syncthreads_or(!active);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (a < D) {
+            sm.out.i[a][tid] = P.i[a];
+            sm.out.d[a][tid] = P.d[a];
+            if (P.ip[a] != st.i[a][tid]) {
+              st.i[a][tid] = P.ip[a]; // periodic wrap shifts i_prev too (sr.hpp:664-677)
+            }
+          }
+          sm.out.u[a][tid] = P.u[a];
+        }
+        if (not_all_alive && active) {
+          // particles that are not pushed keep their i_prev / dx_prev: no bulk store of the
+          // staged slices for this chunk, alive particles write theirs one by one
+          int*   iip[3] = { S.i1_prev, S.i2_prev, S.i3_prev };
+          float* ddp[3] = { S.dx1_prev, S.dx2_prev, S.dx3_prev };
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            iip[a][p] = P.ip[a];
+            ddp[a][p] = P.dp[a];
+          }
+        }
+        tma::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          constexpr unsigned B4 = STREAM_CHUNK * 4;
+          const size_t       p0 = (size_t)c * STREAM_CHUNK;
+          int*   ii[3]  = { S.i1, S.i2, S.i3 };
+          float* dd[3]  = { S.dx1, S.dx2, S.dx3 };
+          int*   iip[3] = { S.i1_prev, S.i2_prev, S.i3_prev };
+          float* ddp[3] = { S.dx1_prev, S.dx2_prev, S.dx3_prev };
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            tma::s2g(ii[a] + p0, sm.out.i[a], B4);
+            tma::s2g(dd[a] + p0, sm.out.d[a], B4);
+            if (!not_all_alive) {
+              tma::s2g(iip[a] + p0, st.i[a], B4);
+              tma::s2g(ddp[a] + p0, st.d[a], B4);
+            }
+          }
+          tma::s2g(S.ux1 + p0, sm.out.u[0], B4);
+          tma::s2g(S.ux2 + p0, sm.out.u[1], B4);
+          tma::s2g(S.ux3 + p0, sm.out.u[2], B4);
+          tma::commit();
+          // refill the stage that was consumed one iteration ago (its stores were waited for
+          // above) with the chunk two iterations ahead
+          const uint32_t cn = c + (STREAM_STAGES - 1) * stride;
+          if (cn < nchunks) {
+            const int sn = (stage + STREAM_STAGES - 1) % STREAM_STAGES;
+            stream_issue_load<D>(sm.in[sn], &sm.full[sn], S, (size_t)cn * STREAM_CHUNK);
+          }
+        }
+        if (++stage == STREAM_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (tid == 0) {
+        tma::wait_all();
       }
     }
 
@@ -205,6 +464,19 @@ namespace eb200 {
     }
 
     /* ----------------------------------------------------------------- launchers */
+    // 128-bit particle loads need 16-byte aligned arrays (8-byte for the int16 tags)
+    static bool aligned16(const eb200_prtls_t& S, int dim) {
+      const void* a4[] = { S.i1, S.dx1, S.i1_prev, S.dx1_prev, S.ux1, S.ux2, S.ux3, S.weight,
+                           dim > 1 ? (const void*)S.i2 : nullptr, dim > 1 ? S.dx2 : nullptr,
+                           dim > 1 ? (const void*)S.i2_prev : nullptr, dim > 1 ? S.dx2_prev : nullptr,
+                           dim > 2 ? (const void*)S.i3 : nullptr, dim > 2 ? S.dx3 : nullptr,
+                           dim > 2 ? (const void*)S.i3_prev : nullptr, dim > 2 ? S.dx3_prev : nullptr };
+      for (const void* q : a4) {
+        if (q && (reinterpret_cast<uintptr_t>(q) & 15u)) return false;
+      }
+      return (reinterpret_cast<uintptr_t>(S.tag) & 7u) == 0;
+    }
+
     template <int D, int O>
     cudaError_t launch_push(const PushArgs& A, const eb200_prtls_t& S, uint32_t npart,
                             const eb200_grid_t& g, const float* em, cudaStream_t st) {
@@ -271,12 +543,37 @@ namespace eb200 {
       if (npart == 0) return cudaSuccess;
       FieldView<D> EB(g, const_cast<float*>(em));
       FieldView<D> J(g, cur);
+      const float inv_dt = ONE / A.c.dt;
+      uint32_t    p_begin = 0;
+      if (mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) && npart >= (uint32_t)STREAM_CHUNK) {
+        // full 256-particle chunks: TMA-staged persistent kernel; the tail goes below
+        const uint32_t nchunks = npart / STREAM_CHUNK;
+        const bool     lean    = lean_pusher(A.c);
+        auto           kern    = lean ? push_deposit_stream_kernel<D, O, true>
+                                      : push_deposit_stream_kernel<D, O, false>;
+        const size_t   smem    = sizeof(StreamSmem<D>);
+        static int     slots[2] = { 0, 0 }; // resident CTAs per device for (lean, full)
+        if (slots[lean] == 0) {
+          int dev = 0, nsm = 0, per_sm = 0;
+          cudaGetDevice(&dev);
+          cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STREAM_CHUNK, smem);
+          slots[lean] = nsm * (per_sm > 0 ? per_sm : 1);
+        }
+        const uint32_t grid = nchunks < (uint32_t)slots[lean] ? nchunks : (uint32_t)slots[lean];
+        kern<<<grid, STREAM_CHUNK, smem, st>>>(A, S, nchunks, EB, A.c.charge, inv_dt, J);
+        count_launch();
+        p_begin = nchunks * STREAM_CHUNK;
+        if (p_begin == npart) return cudaGetLastError();
+      }
+      const uint32_t nrest = npart - p_begin;
       if (mode == EB200_DEPOSIT_AGGREGATED) {
-        push_deposit_kernel<D, O, true><<<(npart + 255) / 256, 256, 0, st>>>(
-          A, S, npart, EB, A.c.charge, ONE / A.c.dt, J);
+        push_deposit_kernel<D, O, true><<<(nrest + 255) / 256, 256, 0, st>>>(
+          A, S, p_begin, npart, EB, A.c.charge, inv_dt, J);
       } else {
-        push_deposit_kernel<D, O, false><<<(npart + 255) / 256, 256, 0, st>>>(
-          A, S, npart, EB, A.c.charge, ONE / A.c.dt, J);
+        push_deposit_kernel<D, O, false><<<(nrest + 255) / 256, 256, 0, st>>>(
+          A, S, p_begin, npart, EB, A.c.charge, inv_dt, J);
       }
       count_launch();
       return cudaGetLastError();

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libentity_b200.so")
+LIB_PATH = os.environ.get("EB200_LIB") or os.path.join(HERE, "libentity_b200.so")
 
 PUSHER_NONE, PUSHER_PHOTON, PUSHER_BORIS, PUSHER_VAY, PUSHER_GCA = 0, 1, 2, 4, 8
 DRAG_NONE, DRAG_SYNCHROTRON, DRAG_COMPTON = 0, 1, 2
