@@ -21,11 +21,24 @@ namespace eb200 {
   struct EngineState;
   EngineState* engine_state_new();
   void         engine_state_delete(EngineState*);
+
+  // comm.cu
+  struct Comm;
+  Comm*       comm_new();
+  void        comm_delete(Comm*);
+  const char* comm_error(const Comm*);
+  int         comm_setup(Comm&, const eb200_grid_t&, const eb200_metadomain_t&, const char* id);
+  int         comm_unique_id(char* out, std::string& err);
+  int         comm_fields(Comm&, float* fld, int c0, int c1, cudaStream_t st);
+  int         comm_sync_currents(Comm&, float* cur, cudaStream_t st);
+  int         comm_particles(Comm&, eb200_species_t* species, int nspecies, cudaStream_t st);
+  const eb200_domain_info_t* comm_info(const Comm*);
 } // namespace eb200
 
 struct eb200_ctx {
   eb200_config_t cfg;
   eb200::EngineState* engine = nullptr;
+  eb200::Comm*   comm = nullptr; // attached by eb200_comm_init (multi-domain exchange)
   eb200::Scratch scratch;
   std::string    err;
   uint64_t       launches_at_init;
@@ -123,6 +136,7 @@ void eb200_finalize(eb200_ctx_t* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   ctx->scratch.release();
+  if (ctx->comm) eb200::comm_delete(ctx->comm);
   eb200::engine_state_delete(ctx->engine);
   delete ctx;
 }
@@ -189,8 +203,13 @@ int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const i
     if (e != cudaSuccess) return check_cuda(ctx, e, "filter copy");
     e = VARIANT_CALL(ctx, filter_pass(ctx->cfg.grid, cur, buff, fbc, st));
     if (e != cudaSuccess) return check_cuda(ctx, e, "filter pass");
-    e = VARIANT_CALL(ctx, comm_fields_self(ctx->cfg.grid, cur, 0, 3, fbc, st));
-    if (e != cudaSuccess) return check_cuda(ctx, e, "filter ghost exchange");
+    if (ctx->comm) {
+      int rc = eb200::comm_fields(*ctx->comm, cur, 0, 3, st);
+      if (rc != EB200_OK) return fail(ctx, rc, eb200::comm_error(ctx->comm));
+    } else {
+      e = VARIANT_CALL(ctx, comm_fields_self(ctx->cfg.grid, cur, 0, 3, fbc, st));
+      if (e != cudaSuccess) return check_cuda(ctx, e, "filter ghost exchange");
+    }
   }
   return EB200_OK;
 }
@@ -285,6 +304,10 @@ int eb200_comm_fields(eb200_ctx_t* ctx, float* fld, int ncomp, int c0, int c1, c
   ENTER(ctx);
   REQUIRE(ctx, fld != nullptr && fbc != nullptr, "null argument");
   REQUIRE(ctx, 0 <= c0 && c0 < c1 && c1 <= ncomp, "bad component range");
+  if (ctx->comm) {
+    int rc = eb200::comm_fields(*ctx->comm, fld, c0, c1, (cudaStream_t)stream);
+    return rc == EB200_OK ? rc : fail(ctx, rc, eb200::comm_error(ctx->comm));
+  }
   return check_cuda(ctx,
                     VARIANT_CALL(ctx, comm_fields_self(ctx->cfg.grid, fld, c0, c1, fbc,
                                                        (cudaStream_t)stream)),
@@ -295,6 +318,10 @@ int eb200_sync_currents(eb200_ctx_t* ctx, float* cur, float* buff, const int* fb
                         eb200_stream_t stream) {
   ENTER(ctx);
   REQUIRE(ctx, cur != nullptr && fbc != nullptr, "null argument");
+  if (ctx->comm) {
+    int rc = eb200::comm_sync_currents(*ctx->comm, cur, (cudaStream_t)stream);
+    return rc == EB200_OK ? rc : fail(ctx, rc, eb200::comm_error(ctx->comm));
+  }
   return check_cuda(ctx,
                     VARIANT_CALL(ctx, sync_currents_self(ctx->cfg.grid, cur, buff, fbc,
                                                          (cudaStream_t)stream)),
@@ -314,5 +341,47 @@ int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t*
   if (remove_dead) *npart_inout = n_alive;
   return EB200_OK;
 }
+
+int eb200_comm_unique_id(char* id_out) {
+  if (!id_out) return fail(nullptr, EB200_ERR_ARG, "eb200_comm_unique_id: null argument");
+  std::string err;
+  int rc = eb200::comm_unique_id(id_out, err);
+  return rc == EB200_OK ? rc : fail(nullptr, rc, err);
+}
+
+int eb200_comm_init(eb200_ctx_t* ctx, const eb200_metadomain_t* md, const char* id) {
+  ENTER(ctx);
+  REQUIRE(ctx, md != nullptr, "metadomain is null");
+  REQUIRE(ctx, id != nullptr || md->nranks == 1, "a unique id is required for nranks > 1");
+  if (ctx->comm) {
+    eb200::comm_delete(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  eb200::Comm* c = eb200::comm_new();
+  int rc = eb200::comm_setup(*c, ctx->cfg.grid, *md, id);
+  if (rc != EB200_OK) {
+    fail(ctx, rc, eb200::comm_error(c));
+    eb200::comm_delete(c);
+    return rc;
+  }
+  ctx->comm = c;
+  return EB200_OK;
+}
+
+int eb200_comm_particles(eb200_ctx_t* ctx, eb200_species_t* species, int nspecies,
+                         eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, nspecies == 0 || species != nullptr, "species is null");
+  if (!ctx->comm) return EB200_OK; // a single self-periodic domain migrates nothing
+  for (int s = 0; s < nspecies; ++s) {
+    int rc = check_prtls(ctx, &species[s].arrays, species[s].npart);
+    if (rc) return rc;
+  }
+  int rc = eb200::comm_particles(*ctx->comm, species, nspecies, (cudaStream_t)stream);
+  return rc == EB200_OK ? rc : fail(ctx, rc, eb200::comm_error(ctx->comm));
+}
+
+// internal: 1 when a communicator / decomposition is attached (engine.cu)
+int eb200_ctx_has_comm(const eb200_ctx_t* ctx) { return ctx && ctx->comm ? 1 : 0; }
 
 } // extern "C"

@@ -66,6 +66,7 @@ namespace eb200 {
 } // namespace eb200
 
 extern "C" eb200::EngineState* eb200_ctx_engine_state(eb200_ctx_t* ctx);
+extern "C" int                 eb200_ctx_has_comm(const eb200_ctx_t* ctx);
 
 namespace eb200 {
   namespace srpic {
@@ -266,7 +267,12 @@ namespace eb200 {
         PHASE(dom, EB200_PHASE_FILTER);
         TRY(CurrentsFilter(dom));
       }
-      // CommunicateParticles: a single periodic domain has no neighbour to migrate to
+      // CommunicateParticles (srpic.hpp:130-132): a single self-periodic domain has no
+      // neighbour to migrate to; species without a pusher never carry a send tag
+      if (eb200_ctx_has_comm(dom.ctx)) {
+        PHASE(dom, EB200_PHASE_COMM);
+        TRY(eb200_comm_particles(dom.ctx, dom.species, dom.nspecies, dom.stream));
+      }
       if (p.fieldsolver_enabled) {
         {
           PHASE(dom, EB200_PHASE_FIELDSOLVER);

@@ -96,6 +96,21 @@ class ParamsC(C.Structure):
 
 
 
+class MetadomainC(C.Structure):
+    _fields_ = [("dim", C.c_int), ("rank", C.c_int), ("nranks", C.c_int),
+                ("ndoms", C.c_int * 3), ("extents", C.POINTER(C.c_int) * 3),
+                ("fbc", C.c_int * 6), ("pbc", C.c_int * 6)]
+
+
+class DomainInfoC(C.Structure):
+    _fields_ = [("offset", C.c_int * 3), ("n", C.c_int * 3), ("cell_offset", C.c_int * 3),
+                ("face_fbc", C.c_int * 6), ("face_pbc", C.c_int * 6),
+                ("dir_fbc", C.c_int * 27), ("neighbor", C.c_int * 27),
+                ("enabled", C.c_int * 27)]
+
+
+UNIQUE_ID_BYTES = 128
+
 _lib = None
 
 
@@ -144,6 +159,13 @@ def load():
                                           C.c_int, C.c_uint32, C.c_double,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.eb200_srpic_step_host.restype = C.c_int
+    lib.eb200_decompose.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p]
+    lib.eb200_domain_info.argtypes = [C.POINTER(MetadomainC), C.POINTER(DomainInfoC)]
+    lib.eb200_comm_unique_id.argtypes = [C.c_char_p]
+    lib.eb200_comm_init.argtypes = [ctxp, C.POINTER(MetadomainC), C.c_char_p]
+    lib.eb200_comm_particles.argtypes = [ctxp, C.POINTER(SpeciesC), C.c_int, vp]
+    for name in ("decompose", "domain_info", "comm_unique_id", "comm_init", "comm_particles"):
+        getattr(lib, "eb200_" + name).restype = C.c_int
     for name in ("init", "faraday", "ampere", "currents_ampere", "filter", "push_sr", "deposit",
                  "push_deposit_sr", "zero_currents", "comm_fields", "sync_currents",
                  "sort_particles"):
@@ -158,6 +180,60 @@ def exported_symbols():
     hdr = os.path.join(os.path.dirname(HERE), "include", "entity_b200.h")
     txt = open(hdr).read()
     return sorted(set(re.findall(r"\b(eb200_[a-z_0-9]+)\s*\(", txt)))
+
+
+def decompose(ndomains, ncells, decomposition=None):
+    """tools::Decompose through the library's host code: returns the list, per dimension, of
+    the active-cell extents of the domains along it."""
+    lib = load()
+    dim = len(ncells)
+    dec = list(decomposition) if decomposition is not None else [-1] * dim
+    nd = (C.c_int * 3)()
+    outs = [(C.c_int * max(ndomains, 1))() for _ in range(3)]
+    rc = lib.eb200_decompose(ndomains, dim, (C.c_int * dim)(*ncells), (C.c_int * dim)(*dec), nd,
+                             outs[0], outs[1], outs[2])
+    if rc != 0:
+        raise EB200Error(f"Decomposition error for {ndomains} domains over {list(ncells)} "
+                         f"with {dec}")
+    return [[int(outs[a][k]) for k in range(nd[a])] for a in range(dim)]
+
+
+def make_metadomain(rank, extents, fbc=None, pbc=None):
+    """eb200_metadomain_t for `rank` of the Cartesian product of `extents` (list per dimension)."""
+    dim = len(extents)
+    md = MetadomainC()
+    md.dim, md.rank = dim, rank
+    md.nranks = 1
+    keep = []
+    for a in range(3):
+        if a < dim:
+            arr = (C.c_int * len(extents[a]))(*extents[a])
+            keep.append(arr)
+            md.extents[a] = C.cast(arr, C.POINTER(C.c_int))
+            md.ndoms[a] = len(extents[a])
+            md.nranks *= len(extents[a])
+        else:
+            md.ndoms[a] = 1
+    md.fbc = (C.c_int * 6)(*(fbc or [FBC_PERIODIC] * 6))
+    md.pbc = (C.c_int * 6)(*(pbc or [PBC_PERIODIC] * 6))
+    md._keep = keep  # the C struct borrows these arrays
+    return md
+
+
+def domain_info(md) -> DomainInfoC:
+    info = DomainInfoC()
+    if load().eb200_domain_info(C.byref(md), C.byref(info)) != 0:
+        raise EB200Error("invalid metadomain description")
+    return info
+
+
+def unique_id() -> bytes:
+    """ncclGetUniqueId through the library (needs NCCL, i.e. a GPU box)."""
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    lib = load()
+    if lib.eb200_comm_unique_id(buf) != 0:
+        raise EB200Error(lib.eb200_last_error(None).decode())
+    return buf.raw
 
 
 def _ptr(t):
@@ -288,6 +364,11 @@ class Context:
     def sync_currents(self, cur, buff, fbc, stream=None):
         self._check(self.lib.eb200_sync_currents(self.handle, _ptr(cur), _ptr(buff),
                                                  (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    def comm_init(self, md, uid: bytes | None):
+        """Attach the decomposition (and, with `uid`, an NCCL communicator) to this context."""
+        self._md = md
+        self._check(self.lib.eb200_comm_init(self.handle, C.byref(md), uid))
 
     def sort_particles(self, arrays, npart, remove_dead=False, stream=None):
         s = self.prtls_struct(arrays)

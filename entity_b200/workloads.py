@@ -101,8 +101,12 @@ def two_stream(n=(256, 256), ppc0=64, nfilter=4, seed=0x1234, **kw) -> Simulatio
     return sim
 
 
-def reconnection(n=(4096, 2048), ppc0=32, nfilter=8, seed=0x5678, sheets=True, **kw) -> Simulation:
-    """configs[1]: 2D pair-plasma Harris sheet(s), periodic-core variant."""
+def reconnection(n=(4096, 2048), ppc0=32, nfilter=8, seed=0x5678, sheets=True,
+                 capacity_factor=1.0, **kw) -> Simulation:
+    """configs[1]: 2D pair-plasma Harris sheet(s), periodic-core variant. The box is doubly
+    periodic, so a multi-domain run tiles it: every block of `n` cells holds the same two
+    sheets (own seed) and the global plasma is an array of Harris sheets. `capacity_factor`
+    leaves room in the particle arrays for migration (maxnpart of the reference)."""
     torch_n1, torch_n2 = n
     Lx = 1000.0 * (n[0] / 4096.0)
     dx = Lx / n[0]
@@ -127,7 +131,7 @@ def reconnection(n=(4096, 2048), ppc0=32, nfilter=8, seed=0x5678, sheets=True, *
     if sheets:
         n_cs = int(over * 2.0 * (cs_width / dx) * n[0] * (ppc0 // 2)) * 2
     for charge in (-1.0, +1.0):
-        arr = _alloc(sim, n_bg + n_cs)
+        arr = _alloc(sim, n_bg + n_cs, int((n_bg + n_cs) * capacity_factor))
         _uniform_positions(sim, arr, n_bg, gen)
         _maxwellian(sim, arr, n_bg, gen, 1e-4)
         if n_cs:

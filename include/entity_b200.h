@@ -182,6 +182,53 @@ int eb200_comm_fields(eb200_ctx_t* ctx, float* fld, int ncomp, int c0, int c1,
 int eb200_sync_currents(eb200_ctx_t* ctx, float* cur, float* buff, const int* fbc_host,
                         eb200_stream_t stream);
 
+/* ------------------------------------------------------- multi-domain (NCCL) */
+/* The decomposition of the global mesh, as Metadomain builds it
+ * (src/framework/domain/metadomain.cpp:101-196, 196-330): domains form a Cartesian product,
+ * domain index = rank = o1 + nd1*(o2 + nd2*o3) (tools::TensorProduct, tools.h:62-77),
+ * neighbours wrap around (redefineNeighbors), internal faces are SYNC and a periodic face whose
+ * neighbour is another domain becomes SYNC (redefineBoundaries). */
+typedef struct {
+  int        dim;
+  int        rank, nranks;  /* one domain per rank */
+  int        ndoms[3];      /* domains per dimension; product = nranks */
+  const int* extents[3];    /* extents[a][k] = active cells of the k-th domain along a (host) */
+  int        fbc[6];        /* EB200_FBC_* of the GLOBAL mesh faces */
+  int        pbc[6];        /* EB200_PBC_* of the GLOBAL mesh faces */
+} eb200_metadomain_t;
+
+/* what Metadomain derives for one domain; direction index = lexicographic over {-1,0,1}^dim
+ * with x1 slowest (dir::Directions<D>::all order incl. the null direction at the centre) */
+typedef struct {
+  int offset[3];      /* offset_ndomains */
+  int n[3];           /* local active cells */
+  int cell_offset[3]; /* offset_ncells */
+  int face_fbc[6];    /* local EB200_FBC_* per face (SYNC where another domain adjoins) */
+  int face_pbc[6];    /* local EB200_PBC_* per face (NONE where particles leave to a neighbour) */
+  int dir_fbc[27];    /* per direction: first non-periodic among the associated faces */
+  int neighbor[27];   /* rank of the neighbour in each direction (wraps around) */
+  int enabled[27];    /* 1: fields/particles are exchanged in this direction */
+} eb200_domain_info_t;
+
+/* tools::Decompose (src/global/utils/tools.h:166-275): decomposition[a] <= 0 means "choose".
+ * ndoms_out[3]; extents_out[a] must hold ndoms_out[a] ints (pass arrays of >= ndomains).
+ * Pure host code. Fails (EB200_ERR_ARG) where the reference raises. */
+int eb200_decompose(int ndomains, int dim, const int* ncells, const int* decomposition,
+                    int* ndoms_out, int* extents1_out, int* extents2_out, int* extents3_out);
+/* pure host code: the tables above for md->rank */
+int eb200_domain_info(const eb200_metadomain_t* md, eb200_domain_info_t* out);
+
+#define EB200_UNIQUE_ID_BYTES 128
+/* ncclGetUniqueId; rank 0 calls it and the launcher distributes the bytes
+ * (the reference bootstraps through MPI_Init, src/global/global.cpp:9-14) */
+int eb200_comm_unique_id(char* id_out /* EB200_UNIQUE_ID_BYTES */);
+/* attaches a communicator (ncclCommInitRank) and the decomposition to the context; the
+ * context's grid must be this rank's block. From here on eb200_comm_fields,
+ * eb200_sync_currents, eb200_filter and eb200_srpic_step exchange with the neighbour
+ * domains (packed by device kernels, one grouped ncclSend/ncclRecv per peer and round)
+ * instead of the self-periodic copy. id = NULL: decomposition tables only (no transport);
+ * valid for nranks == 1. */
+int eb200_comm_init(eb200_ctx_t* ctx, const eb200_metadomain_t* md, const char* id);
 /* ------------------------------------------------------------- sort / compaction */
 /* Particles::SortSpatially (particles_sort.cpp:197-253): stable sort by cell index
  * (i1 fastest, matching the field layout), dead particles moved to the end.
@@ -230,6 +277,14 @@ typedef struct {
 int eb200_srpic_step(eb200_ctx_t* ctx, const eb200_srpic_params_t* prm, float* em, float* cur,
                      float* buff, eb200_species_t* species, int nspecies, uint32_t step,
                      double time, eb200_stream_t stream);
+
+/* Metadomain::CommunicateParticles + Particles::Communicate for all species in one round
+ * (metadomain_comm.cpp:565-653, particles_comm.cpp:180-389, kernels/comm.hpp): particles
+ * tagged by the pusher with a send tag move to the neighbour in that direction with their
+ * cell indices shifted; received particles fill dead/sent slots first, then extend npart.
+ * Synchronises the stream once (particle counts are host-visible results). */
+int eb200_comm_particles(eb200_ctx_t* ctx, eb200_species_t* species, int nspecies,
+                         eb200_stream_t stream);
 
 /* ------------------------------------------------------------------- profiling */
 /* Phases of eb200_srpic_step, bracketed by CUDA events on the caller's stream when profiling

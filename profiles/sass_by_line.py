@@ -13,7 +13,12 @@ src_csv, sass, kern = sys.argv[1:4]
 rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[2:] if len(r) > 10]
+data = []
+for r in rows[2:]:
+    if r and r[0] == "Kernel Name":
+        break  # further launches of the same kernel follow; the first one is enough
+    if len(r) > 10:
+        data.append(r)
 lines = open(sass).read().split("\n")
 start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and kern in l)
 cur = None
