@@ -25,7 +25,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 # (source, object suffix, extra flags)
 UNITS = [
     ("particles.cu", "strict", ["-DEB200_STRICT=1", "--fmad=false"]),
-    ("particles.cu", "fast", ["-DEB200_STRICT=0"]),
+    ("particles.cu", "fast", ["-DEB200_STRICT=0", "-ftz=true"]),
     ("fields.cu", "strict", ["-DEB200_STRICT=1", "--fmad=false"]),
     ("fields.cu", "fast", ["-DEB200_STRICT=0"]),
     ("sort.cu", "one", []),

@@ -42,6 +42,7 @@ struct eb200_ctx {
   eb200::Scratch scratch;
   std::string    err;
   uint64_t       launches_at_init;
+  int            pd_kernel = 0; // eb200_set_pd_kernel
 };
 
 static std::string g_last_error;
@@ -286,9 +287,17 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
   REQUIRE(ctx, em != nullptr && cur != nullptr, "null field");
   return check_cuda(ctx,
                     VARIANT_CALL(ctx, push_deposit_sr(ctx->cfg.grid, ctx->cfg.shape_order,
-                                                      *pusher, *prtls, npart, em, cur, mode,
+                                                      *pusher, *prtls, npart, em, cur,
+                                                      mode | (ctx->pd_kernel << 8),
                                                       (cudaStream_t)stream)),
                     "push_deposit_sr");
+}
+
+int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which) {
+  ENTER(ctx);
+  REQUIRE(ctx, which >= 0 && which <= 3, "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4");
+  ctx->pd_kernel = which;
+  return EB200_OK;
 }
 
 int eb200_zero_currents(eb200_ctx_t* ctx, float* cur, eb200_stream_t stream) {

@@ -11,6 +11,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace eb200 {
 
   template <int D>
@@ -144,6 +146,17 @@ namespace eb200 {
 #endif
   }
 
+  // a / dx with the cell size's reciprocal precomputed on the host (fast build only)
+  __device__ __forceinline__ float div_dx(float a, float dx, float inv_dx) {
+#if EB200_STRICT
+    (void)inv_dx;
+    return a / dx;
+#else
+    (void)dx;
+    return a * inv_dx;
+#endif
+  }
+
   /* ---------------------------------------------------------------- vector ops */
   __device__ __forceinline__ float dot3(const float* a, const float* b) {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
@@ -269,6 +282,80 @@ namespace eb200 {
     }
   }
 
+  // Zig-zag (O = 0) gather straight from a FieldView: one 32-bit element index per particle,
+  // the primal/dual choice is an element offset, the 2^D nodes of a component are immediate or
+  // row-stride offsets from one pointer. Same weights and summation order as gather_fields().
+  template <int D>
+  __device__ __forceinline__ void gather_fields_direct(const FieldView<D>& EB, int ng,
+                                                       const Prtl<D>& P, float* e0, float* b0) {
+    float     wp[3][2], wd[3][2];
+    int       od[3]  = { 0, 0, 0 };
+    const int st[3]  = { 1, EB.N1, EB.N1 * EB.N2 };
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const int ind = static_cast<int>(P.d[a] + HALF);
+      od[a]         = (ind - 1) * st[a];
+      wp[a][0]      = ONE - P.d[a];
+      wp[a][1]      = P.d[a];
+      wd[a][0]      = static_cast<float>(ind + 1) - (P.d[a] + HALF);
+      wd[a][1]      = ONE - wd[a][0];
+    }
+    const int e = static_cast<int>(
+      EB.idx(P.i[0] + ng, (D > 1) ? P.i[1] + ng : 0, (D > 2) ? P.i[2] + ng : 0));
+    auto lerp = [&](int c, bool sx, bool sy, bool sz, bool wy_dual) -> float {
+      const float* bc = EB.p + EB.plane * c;
+      const int    o  = e + (sx ? od[0] : 0) + ((D > 1 && sy) ? od[1] : 0) +
+                    ((D > 2 && sz) ? od[2] : 0);
+      const float* wx = sx ? wd[0] : wp[0];
+      const float* q  = bc + o;
+      if constexpr (D == 1) {
+        return __ldg(q) * wx[0] + __ldg(q + 1) * wx[1];
+      } else if constexpr (D == 2) {
+        const float* wy  = wy_dual ? wd[1] : wp[1];
+        const float* r   = bc + (o + st[1]);
+        const float  c00 = __ldg(q) * wx[0] + __ldg(q + 1) * wx[1];
+        const float  c10 = __ldg(r) * wx[0] + __ldg(r + 1) * wx[1];
+        return c00 * wy[0] + c10 * wy[1];
+      } else {
+        const float* wy  = wy_dual ? wd[1] : wp[1];
+        const float* wz  = sz ? wd[2] : wp[2];
+        const float* r   = bc + (o + st[1]);
+        const float* q2  = bc + (o + st[2]);
+        const float* r2  = bc + (o + st[1] + st[2]);
+        const float  c00 = __ldg(q) * wx[0] + __ldg(q + 1) * wx[1];
+        const float  c10 = __ldg(r) * wx[0] + __ldg(r + 1) * wx[1];
+        const float  c0  = c00 * wy[0] + c10 * wy[1];
+        const float  c01 = __ldg(q2) * wx[0] + __ldg(q2 + 1) * wx[1];
+        const float  c11 = __ldg(r2) * wx[0] + __ldg(r2 + 1) * wx[1];
+        const float  c1  = c01 * wy[0] + c11 * wy[1];
+        return c0 * wz[0] + c1 * wz[1];
+      }
+    };
+    e0[0] = lerp(ex1, true, false, false, false);
+    e0[1] = lerp(ex2, false, true, false, true);
+    e0[2] = lerp(ex3, false, false, true, false);
+    b0[0] = lerp(bx1, false, true, true, true);
+    b0[1] = lerp(bx2, true, false, true, false);
+    b0[2] = lerp(bx3, true, true, false, D != 3);
+  }
+
+  // what push_particle() calls: a FieldView goes through the direct gather where one exists,
+  // any other callable through the generic one
+  template <int D, int O, class EM>
+  __device__ __forceinline__ void gather_any(const EM& F, int ng, const Prtl<D>& P, float* e0,
+                                             float* b0) {
+    if constexpr (std::is_same<EM, FieldView<D>>::value) {
+      if constexpr (O == 0) {
+        gather_fields_direct<D>(F, ng, P, e0, b0);
+      } else {
+        gather_fields<D, O>([&](int i, int j, int k, int c) { return F.ld(i, j, k, c); }, ng, P,
+                            e0, b0);
+      }
+    } else {
+      gather_fields<D, O>(F, ng, P, e0, b0);
+    }
+  }
+
   /* ---------------------------------------------------------- velocity updates */
   __device__ __forceinline__ void boris(float ndh, float* u, float* e0, float* b0) {
     float c = ndh;
@@ -385,6 +472,7 @@ namespace eb200 {
     float          ndh; // 1/2 (q/m) omegaB0 dt  (sr.hpp:111)
     int            ni[3];
     int            ng;
+    float          inv_dx; // 1 / c.dx
   };
 
   // LEAN: the context is known (host-side check, see lean_pusher()) to be a plain Boris push
@@ -401,7 +489,7 @@ namespace eb200 {
     bool                  massive = true;
     if constexpr (LEAN) {
       float ec[3], bc[3];
-      gather_fields<D, O>(F, A.ng, P, ec, bc);
+      gather_any<D, O>(F, A.ng, P, ec, bc);
 #pragma unroll
       for (int a = 0; a < D; ++a) {
         ec[a] = ec[a] * c.dx;
@@ -412,7 +500,7 @@ namespace eb200 {
       massive = false;
     } else {
       float ec[3], bc[3];
-      gather_fields<D, O>(F, A.ng, P, ec, bc);
+      gather_any<D, O>(F, A.ng, P, ec, bc);
       // contravariant -> Cartesian: in-plane components scale with the cell size
 #pragma unroll
       for (int a = 0; a < D; ++a) {
@@ -489,7 +577,7 @@ namespace eb200 {
     for (int a = 0; a < D; ++a) {
       P.ip[a]  = P.i[a];
       P.dp[a]  = P.d[a];
-      float dx = P.d[a] + fdiv(P.u[a], c.dx) * dt_inv_energy;
+      float dx = P.d[a] + div_dx(P.u[a], c.dx, A.inv_dx) * dt_inv_energy;
       P.i[a]  += static_cast<int>(dx >= ONE) - static_cast<int>(dx < ZERO);
       dx      -= static_cast<float>(dx >= ONE);
       dx      += static_cast<float>(dx < ZERO);

@@ -207,6 +207,11 @@ namespace eb200 {
                      : "memory");
       }
 
+      __device__ __forceinline__ void prefetch_l2(const void* src, unsigned bytes) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes)
+                     : "memory");
+      }
+
       __device__ __forceinline__ void commit() {
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -400,6 +405,194 @@ namespace eb200 {
       }
     }
 
+    /* ------------------------------------ vectorised push + deposit (zig-zag, O = 0) */
+    // Four consecutive particles per thread. Every SoA array is read and written with one
+    // 128-bit streaming access per thread (a warp covers 512 contiguous bytes per array), so
+    // the kernel needs no staging, no barriers and ~1/4 of the load/store instructions of the
+    // one-particle-per-thread form. With cell-sorted particles the four particles of a thread
+    // mostly sit in the same cell: their zig-zag contributions are summed in registers and only
+    // a change of cell inside the thread issues atomics; what is left per thread goes through
+    // the warp's segmented shuffle reduction once per FOUR particles.
+    constexpr int VEC = 4;
+
+    template <class T4, class T>
+    __device__ __forceinline__ void ld4(const T* p, T (&v)[VEC]) {
+      const T4 t = __ldcs(reinterpret_cast<const T4*>(p));
+      v[0]       = t.x;
+      v[1]       = t.y;
+      v[2]       = t.z;
+      v[3]       = t.w;
+    }
+
+    template <class T4, class T>
+    __device__ __forceinline__ void st4(T* p, const T (&v)[VEC]) {
+      T4 t;
+      t.x = v[0];
+      t.y = v[1];
+      t.z = v[2];
+      t.w = v[3];
+      __stcs(reinterpret_cast<T4*>(p), t);
+    }
+
+#ifndef EB200_VEC_MINBLOCKS
+  #define EB200_VEC_MINBLOCKS 3
+#endif
+    // resident CTAs per SM the register allocation aims for: 1D/2D bodies fit 3 x 256 threads
+    // without spilling (80 registers), the 3D body (12 nodes per segment) needs 128
+    constexpr int vec_minblocks(int D) { return (D == 3) ? 2 : EB200_VEC_MINBLOCKS; }
+
+    template <int D, bool LEAN>
+    __global__ void __launch_bounds__(256, vec_minblocks(D))
+      push_deposit_vec_kernel(PushArgs A, eb200_prtls_t S, uint32_t ngroups, uint32_t ahead,
+                              FieldView<D> EB, float charge, float inv_dt, FieldView<D> J) {
+      constexpr int  NV       = ZigZag<D>::NV;
+      const uint32_t g        = blockIdx.x * blockDim.x + threadIdx.x;
+      const bool     in_range = g < ngroups;
+      const size_t   p0       = (size_t)g * VEC;
+      int*           ii[3]    = { S.i1, S.i2, S.i3 };
+      float*         dd[3]    = { S.dx1, S.dx2, S.dx3 };
+      int*           iip[3]   = { S.i1_prev, S.i2_prev, S.i3_prev };
+      float*         ddp[3]   = { S.dx1_prev, S.dx2_prev, S.dx3_prev };
+      int            iv[3][VEC];
+      float          dv[3][VEC], uv[3][VEC], wv[VEC];
+      short          tv[VEC] = { 0, 0, 0, 0 };
+      bool           all_pushed = false;
+#ifndef EB200_VEC_NOPREFETCH
+      // CTAs are dispatched in index order: pull the slices of the CTA that will run
+      // `ahead` blocks later (about one resident wave) from DRAM into L2 now, so that its
+      // first loads are L2 hits. One bulk prefetch per array, issued by one thread.
+      if (threadIdx.x == 0) {
+        const size_t q0 = ((size_t)blockIdx.x + ahead) * blockDim.x * VEC;
+        if (q0 + (size_t)blockDim.x * VEC <= (size_t)ngroups * VEC) {
+          const unsigned b4 = blockDim.x * VEC * 4, b2 = blockDim.x * VEC * 2;
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            tma::prefetch_l2(ii[a] + q0, b4);
+            tma::prefetch_l2(dd[a] + q0, b4);
+          }
+          tma::prefetch_l2(S.ux1 + q0, b4);
+          tma::prefetch_l2(S.ux2 + q0, b4);
+          tma::prefetch_l2(S.ux3 + q0, b4);
+          tma::prefetch_l2(S.weight + q0, b4);
+          tma::prefetch_l2(S.tag + q0, b2);
+        }
+      }
+#endif
+      if (in_range) {
+        ld4<short4>(S.tag + p0, tv);
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          ld4<int4>(ii[a] + p0, iv[a]);
+          ld4<float4>(dd[a] + p0, dv[a]);
+        }
+        ld4<float4>(S.ux1 + p0, uv[0]);
+        ld4<float4>(S.ux2 + p0, uv[1]);
+        ld4<float4>(S.ux3 + p0, uv[2]);
+        ld4<float4>(S.weight + p0, wv);
+        all_pushed = (tv[0] == 1) && (tv[1] == 1) && (tv[2] == 1) && (tv[3] == 1);
+        if (all_pushed) {
+          // i_prev / dx_prev of a pushed particle ARE its old i / dx: stored right away; a
+          // periodic wrap (which shifts i_prev too, sr.hpp:664-677) patches its element below
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            st4<int4>(iip[a] + p0, iv[a]);
+            st4<float4>(ddp[a] + p0, dv[a]);
+          }
+        }
+      }
+      const long N12 = (long)J.N1 * J.N2;
+      auto       red = [&](int key, const float (&a)[NV]) {
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+          atomicAdd(J.p + key + zigzag_offset<D>(n, J.N1, N12, J.plane), a[n]);
+        }
+      };
+      float acc[NV];
+#pragma unroll
+      for (int n = 0; n < NV; ++n) acc[n] = ZERO;
+      int cur = -1; // cell whose contributions `acc` holds
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const short tag = tv[k];
+        if (tag != 1) {
+          continue; // neither pushed nor deposited (tv = 0 for threads past the end)
+        }
+        Prtl<D> P;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          P.i[a] = P.ip[a] = (a < D) ? iv[a][k] : 0;
+          P.d[a] = P.dp[a] = (a < D) ? dv[a][k] : ZERO;
+          P.u[a]           = uv[a][k];
+        }
+        P.w   = wv[k];
+        P.tag = tag;
+        push_particle<D, 0, FieldView<D>, LEAN>(A, EB, P);
+        if (P.tag != tag) {
+          S.tag[p0 + k] = P.tag;
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          if (!all_pushed || P.ip[a] != iv[a][k]) {
+            iip[a][p0 + k] = P.ip[a];
+          }
+          if (!all_pushed) {
+            ddp[a][p0 + k] = P.dp[a];
+          }
+          iv[a][k] = P.i[a];
+          dv[a][k] = P.d[a];
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) uv[a][k] = P.u[a];
+        if (P.tag == 0) {
+          continue; // absorbed by a boundary: no current
+        }
+        float v[2][NV];
+        zigzag_values<D>(P, charge, inv_dt, A.c.dx, v);
+        const int G    = A.ng;
+        const int key0 = (int)J.idx(P.ip[0] + G, (D > 1) ? P.ip[1] + G : 0,
+                                    (D > 2) ? P.ip[2] + G : 0);
+        const int key1 = (int)J.idx(P.i[0] + G, (D > 1) ? P.i[1] + G : 0,
+                                    (D > 2) ? P.i[2] + G : 0);
+        const bool cross = key0 != key1;
+        if (cross) {
+          red(key1, v[1]);
+        } else {
+#pragma unroll
+          for (int n = 0; n < NV; ++n) v[0][n] += v[1][n];
+        }
+        if (key0 != cur) {
+          if (cur >= 0) {
+            red(cur, acc);
+          }
+          cur = key0;
+#pragma unroll
+          for (int n = 0; n < NV; ++n) acc[n] = v[0][n];
+        } else {
+#pragma unroll
+          for (int n = 0; n < NV; ++n) acc[n] += v[0][n];
+        }
+      }
+      if (in_range) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          st4<int4>(ii[a] + p0, iv[a]);
+          st4<float4>(dd[a] + p0, dv[a]);
+        }
+        st4<float4>(S.ux1 + p0, uv[0]);
+        st4<float4>(S.ux2 + p0, uv[1]);
+        st4<float4>(S.ux3 + p0, uv[2]);
+      }
+      // what is left in `acc`: one segmented reduction over the warp, keyed by `cur`
+      const WarpRun run = warp_runs(cur);
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        const float s = run_sum(acc[n], run);
+        if (run.head && cur >= 0) {
+          atomicAdd(J.p + cur + zigzag_offset<D>(n, J.N1, N12, J.plane), s);
+        }
+      }
+    }
+
     /* --------------------------------------------------- ordered (serial) deposit */
     // Every particle writes its contributions, in program order, as (key, value) pairs into a
     // fixed-size slot range [p*K, (p+1)*K); unused slots carry key = 0xFFFFFFFF. A stable radix
@@ -545,7 +738,35 @@ namespace eb200 {
       FieldView<D> J(g, cur);
       const float inv_dt = ONE / A.c.dt;
       uint32_t    p_begin = 0;
-      if (mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) && npart >= (uint32_t)STREAM_CHUNK) {
+      // which fused kernel (eb200_set_pd_kernel): 0 auto, 1 one particle per thread,
+      // 2 TMA-staged persistent, 3 four particles per thread (zig-zag only)
+      const int which = (mode >> 8) & 0xff;
+      mode &= 0xff;
+      const bool want_vec = (O == 0) && (which == 0 || which == 3);
+      if constexpr (O == 0) {
+        if (want_vec && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) && npart >= VEC &&
+            J.plane < 0x7fffffffL) {
+          const uint32_t ngroups = npart / VEC;
+          const bool     lean    = lean_pusher(A.c);
+          auto           kern    = lean ? push_deposit_vec_kernel<D, true>
+                                        : push_deposit_vec_kernel<D, false>;
+          static int wave[2] = { 0, 0 }; // resident CTAs of one wave for (full, lean)
+          if (wave[lean] == 0) {
+            int dev = 0, nsm = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+            wave[lean] = nsm * (per_sm > 0 ? per_sm : 1);
+          }
+          kern<<<(ngroups + 255) / 256, 256, 0, st>>>(A, S, ngroups, (uint32_t)wave[lean], EB,
+                                                       A.c.charge, inv_dt, J);
+          count_launch();
+          p_begin = ngroups * VEC;
+          if (p_begin == npart) return cudaGetLastError();
+        }
+      }
+      if (p_begin == 0 && which != 1 && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) &&
+          npart >= (uint32_t)STREAM_CHUNK) {
         // full 256-particle chunks: TMA-staged persistent kernel; the tail goes below
         const uint32_t nchunks = npart / STREAM_CHUNK;
         const bool     lean    = lean_pusher(A.c);
@@ -603,6 +824,7 @@ namespace eb200 {
       A.c   = c;
       A.ndh = HALF * (c.charge / c.mass) * c.omegaB0 * c.dt;
       A.ng  = g.ng;
+      A.inv_dx = ONE / c.dx;
       for (int a = 0; a < 3; ++a) A.ni[a] = g.n[a];
 #define CALL(D, O) launch_push<D, O>(A, S, npart, g, em, st)
       EB200_DISPATCH_DO(g.dim, order, CALL)
@@ -624,6 +846,7 @@ namespace eb200 {
       A.c   = c;
       A.ndh = HALF * (c.charge / c.mass) * c.omegaB0 * c.dt;
       A.ng  = g.ng;
+      A.inv_dx = ONE / c.dx;
       for (int a = 0; a < 3; ++a) A.ni[a] = g.n[a];
 #define CALL(D, O) launch_push_deposit<D, O>(A, S, npart, g, em, cur, mode, st)
       EB200_DISPATCH_DO(g.dim, order, CALL)

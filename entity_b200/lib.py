@@ -145,6 +145,7 @@ def load():
     lib.eb200_push_deposit_sr.argtypes = [ctxp, C.POINTER(Pusher), C.POINTER(Prtls), C.c_uint32,
                                           vp, vp, C.c_int, vp]
     lib.eb200_zero_currents.argtypes = [ctxp, vp, vp]
+    lib.eb200_set_pd_kernel.argtypes = [ctxp, C.c_int]
     lib.eb200_comm_fields.argtypes = [ctxp, vp, C.c_int, C.c_int, C.c_int, i32p, vp]
     lib.eb200_sync_currents.argtypes = [ctxp, vp, vp, i32p, vp]
     lib.eb200_sort_particles.argtypes = [ctxp, C.POINTER(Prtls), C.POINTER(C.c_uint32), C.c_int, vp]
@@ -262,6 +263,13 @@ class Context:
         rc = self.lib.eb200_init(C.byref(cfg), C.byref(self.handle))
         if rc != 0:
             raise EB200Error(self.lib.eb200_last_error(None).decode())
+        which = int(os.environ.get("EB200_PD_KERNEL", "0"))
+        if which:
+            self.set_pd_kernel(which)
+
+    def set_pd_kernel(self, which: int):
+        """0 auto, 1 one particle per thread, 2 TMA-staged chunks, 3 four particles per thread."""
+        self._check(self.lib.eb200_set_pd_kernel(self.handle, which))
 
     def close(self):
         if self.handle:

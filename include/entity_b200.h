@@ -171,6 +171,11 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
                           const eb200_prtls_t* prtls, uint32_t npart, const float* em, float* cur,
                           int mode, eb200_stream_t stream);
 int eb200_zero_currents(eb200_ctx_t* ctx, float* cur, eb200_stream_t stream);
+/* which fused kernel eb200_push_deposit_sr / eb200_srpic_step launch in AGGREGATED mode:
+ * 0 = automatic (default), 1 = one particle per thread, 2 = TMA-staged persistent chunks,
+ * 3 = four particles per thread with 128-bit accesses (zig-zag only). A tuning knob for
+ * measurements; results are the same up to the summation order of J. */
+int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which);
 
 /* ------------------------------------------------- single-domain ghost exchange */
 /* Metadomain::CommunicateFields for a domain that is its own periodic neighbour
