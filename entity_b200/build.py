@@ -28,6 +28,7 @@ UNITS = [
     ("particles.cu", "fast", ["-DEB200_STRICT=0", "-ftz=true"]),
     ("fields.cu", "strict", ["-DEB200_STRICT=1", "--fmad=false"]),
     ("fields.cu", "fast", ["-DEB200_STRICT=0"]),
+    ("curv.cu", "one", ["--fmad=false"]),
     ("sort.cu", "one", []),
     ("comm.cu", "one", []),
     ("engine.cu", "one", []),

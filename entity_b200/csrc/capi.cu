@@ -2,6 +2,7 @@
 // the strict / fast kernel variants. No compute happens on the host and there is no CPU
 // fallback: without a usable CUDA device every entry point fails.
 #include "launch.h"
+#include "metrics.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -43,6 +44,7 @@ struct eb200_ctx {
   std::string    err;
   uint64_t       launches_at_init;
   int            pd_kernel = 0; // eb200_set_pd_kernel
+  eb200::MetricParams metric {}; // curvilinear / GR contexts
 };
 
 static std::string g_last_error;
@@ -78,6 +80,68 @@ static int check_cuda(eb200_ctx* ctx, cudaError_t e, const char* what) {
 #define VARIANT_CALL(ctx, expr)                                                                \
   ((ctx)->cfg.strict_fp ? eb200::strict_fp::expr : eb200::fast_fp::expr)
 
+/* ------------------------------------------------------------- metric evaluation (host) */
+namespace {
+  template <class M>
+  void eval_sr_metric(const eb200::MetricParams& m, int nq, const float* x1, const float* x2,
+                      float* out) {
+    for (int q = 0; q < nq; ++q) {
+      float* o = out + 16 * q;
+      o[0]  = M::h11(m, x1[q], x2[q]);
+      o[1]  = M::h22(m, x1[q], x2[q]);
+      o[2]  = M::h33(m, x1[q], x2[q]);
+      o[3]  = M::sqrt_h11(m, x1[q], x2[q]);
+      o[4]  = M::sqrt_h22(m, x1[q], x2[q]);
+      o[5]  = M::sqrt_h33(m, x1[q], x2[q]);
+      o[6]  = M::sqrt_det_h(m, x1[q], x2[q]);
+      o[7]  = M::polar_area(m, x1[q]);
+      o[8]  = M::r(m, x1[q]);
+      o[9]  = M::theta(m, x2[q]);
+      o[10] = M::x1_of_r(m, o[8]);
+      o[11] = M::x2_of_theta(m, o[9]);
+      for (int k = 12; k < 16; ++k) o[k] = 0.0f;
+    }
+  }
+
+  template <class M>
+  void eval_gr_metric(const eb200::MetricParams& m, int nq, const float* x1, const float* x2,
+                      float* out) {
+    for (int q = 0; q < nq; ++q) {
+      float*      o = out + 32 * q;
+      const float a = x1[q], b = x2[q];
+      o[0]  = M::h_11(m, a, b);
+      o[1]  = M::h_22(m, a, b);
+      o[2]  = M::h_33(m, a, b);
+      o[3]  = M::h_13(m, a, b);
+      o[4]  = M::h11(m, a, b);
+      o[5]  = M::h22(m, a, b);
+      o[6]  = M::h33(m, a, b);
+      o[7]  = M::h13(m, a, b);
+      o[8]  = M::alpha(m, a, b);
+      o[9]  = M::beta1(m, a, b);
+      o[10] = M::sqrt_det_h(m, a, b);
+      o[11] = M::sqrt_det_h_tilde(m, a, b);
+      o[12] = M::polar_area(m, a);
+      o[13] = M::dr_alpha(m, a, b);
+      o[14] = M::dt_alpha(m, a, b);
+      o[15] = M::dr_beta1(m, a, b);
+      o[16] = M::dt_beta1(m, a, b);
+      o[17] = M::dr_h11(m, a, b);
+      o[18] = M::dr_h22(m, a, b);
+      o[19] = M::dr_h33(m, a, b);
+      o[20] = M::dr_h13(m, a, b);
+      o[21] = M::dt_h11(m, a, b);
+      o[22] = M::dt_h22(m, a, b);
+      o[23] = M::dt_h33(m, a, b);
+      o[24] = M::dt_h13(m, a, b);
+      o[25] = M::theta(m, b);
+      o[26] = M::x2_of_theta(m, o[25]);
+      for (int k = 27; k < 32; ++k) o[k] = 0.0f;
+    }
+  }
+} // namespace
+
+
 extern "C" {
 
 int eb200_version(void) { return EB200_VERSION; }
@@ -112,8 +176,22 @@ int eb200_init(const eb200_config_t* cfg, eb200_ctx_t** out) {
   if (cfg->shape_order < 0 || cfg->shape_order > 3) {
     return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_init: shape_order must be 0..3");
   }
+  if (cfg->metric < EB200_METRIC_MINKOWSKI || cfg->metric > EB200_METRIC_KERR_SCHILD_0) {
+    return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_init: unknown metric");
+  }
   if (cfg->metric != EB200_METRIC_MINKOWSKI) {
-    return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_init: only the Minkowski metric is built");
+    // the reference's curvilinear metrics are 2D only (static_asserts in src/metrics/*.h)
+    if (cfg->grid.dim != 2) {
+      return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_init: curvilinear metrics are 2D only");
+    }
+    const float* mp = cfg->metric_params;
+    if (!(mp[1] > mp[0]) || !(mp[3] > mp[2])) {
+      return fail(nullptr, EB200_ERR_ARG, "eb200_init: metric_params must hold x1min < x1max, x2min < x2max");
+    }
+    const bool quasi = cfg->metric == EB200_METRIC_QSPHERICAL || cfg->metric == EB200_METRIC_QKERR_SCHILD;
+    if (quasi && !(mp[0] - mp[4] > 0.0f)) {
+      return fail(nullptr, EB200_ERR_ARG, "eb200_init: x1min must exceed qsph_r0");
+    }
   }
   const int need_ng = cfg->shape_order == 0 ? 2 : (cfg->shape_order + 1) / 2 + 1;
   if (cfg->grid.ng < need_ng) {
@@ -129,6 +207,11 @@ int eb200_init(const eb200_config_t* cfg, eb200_ctx_t** out) {
   ctx->launches_at_init = eb200::launches();
   ctx->engine           = eb200::engine_state_new();
   for (int a = cfg->grid.dim; a < 3; ++a) ctx->cfg.grid.n[a] = 1;
+  if (cfg->metric != EB200_METRIC_MINKOWSKI) {
+    const float* mp = cfg->metric_params;
+    ctx->metric = eb200::make_metric(cfg->metric, cfg->grid.n[0], cfg->grid.n[1], mp[0], mp[1],
+                                     mp[2], mp[3], mp[4], mp[5], mp[6]);
+  }
   *out = ctx;
   return EB200_OK;
 }
@@ -153,10 +236,20 @@ int eb200_ctx_grid(const eb200_ctx_t* ctx, eb200_grid_t* grid, float* dx, float*
   return EB200_OK;
 }
 
+static bool is_sr_curv(const eb200_ctx* ctx) {
+  return ctx->cfg.metric == EB200_METRIC_SPHERICAL || ctx->cfg.metric == EB200_METRIC_QSPHERICAL;
+}
+
+static bool is_gr(const eb200_ctx* ctx) { return ctx->cfg.metric >= EB200_METRIC_KERR_SCHILD; }
+
+#define REQUIRE_MINK(ctx, what)                                                                \
+  REQUIRE(ctx, (ctx)->cfg.metric == EB200_METRIC_MINKOWSKI, what ": Minkowski contexts only")
+
 int eb200_faraday(eb200_ctx_t* ctx, float* em, float coeff1, float coeff2,
                   const float* stencil9_host, eb200_stream_t stream) {
   ENTER(ctx);
   REQUIRE(ctx, em != nullptr, "em is null");
+  REQUIRE_MINK(ctx, "eb200_faraday");
   return check_cuda(ctx,
                     VARIANT_CALL(ctx, faraday(ctx->cfg.grid, em, coeff1, coeff2, stencil9_host,
                                               (cudaStream_t)stream)),
@@ -166,6 +259,7 @@ int eb200_faraday(eb200_ctx_t* ctx, float* em, float coeff1, float coeff2,
 int eb200_ampere(eb200_ctx_t* ctx, float* em, float coeff1, float coeff2, eb200_stream_t stream) {
   ENTER(ctx);
   REQUIRE(ctx, em != nullptr, "em is null");
+  REQUIRE_MINK(ctx, "eb200_ampere");
   return check_cuda(ctx, VARIANT_CALL(ctx, ampere(ctx->cfg.grid, em, coeff1, coeff2, (cudaStream_t)stream)),
                     "ampere");
 }
@@ -174,6 +268,7 @@ int eb200_currents_ampere(eb200_ctx_t* ctx, float* em, float* cur, float coeff, 
                           eb200_stream_t stream) {
   ENTER(ctx);
   REQUIRE(ctx, em != nullptr && cur != nullptr, "null field");
+  REQUIRE_MINK(ctx, "eb200_currents_ampere");
   return check_cuda(ctx,
                     VARIANT_CALL(ctx, currents_ampere(ctx->cfg.grid, em, cur, coeff, ppc0,
                                                       (cudaStream_t)stream)),
@@ -192,6 +287,19 @@ int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const i
   REQUIRE(ctx, cur != nullptr && buff != nullptr && fbc != nullptr, "null argument");
   REQUIRE(ctx, nfilter >= 0, "nfilter < 0");
   cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->cfg.metric != EB200_METRIC_MINKOWSKI) {
+    // spherical-type coordinates: axis-aware stencil; a single domain has no periodic
+    // neighbour, so the per-pass J exchange of currents.h:117 has nothing to do
+    REQUIRE(ctx, ctx->comm == nullptr, "curvilinear filter: multi-domain exchange not built");
+    const size_t nb = field_bytes(ctx->cfg.grid, 3);
+    for (int pass = 0; pass < nfilter; ++pass) {
+      cudaError_t e = cudaMemcpyAsync(buff, cur, nb, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return check_cuda(ctx, e, "filter copy");
+      e = eb200::curv::filter_sph_pass(ctx->cfg.grid, cur, buff, fbc, st);
+      if (e != cudaSuccess) return check_cuda(ctx, e, "filter pass");
+    }
+    return EB200_OK;
+  }
   for (int a = 0; a < 2 * ctx->cfg.grid.dim; ++a) {
     if (fbc[a] == EB200_FBC_AXIS) {
       return fail(ctx, EB200_ERR_UNSUPPORTED, "eb200_filter: axis boundaries need a spherical metric");
@@ -238,7 +346,9 @@ static int check_pusher(eb200_ctx* ctx, const eb200_pusher_t* c) {
       !(c->pusher_flags & (EB200_PUSHER_BORIS | EB200_PUSHER_VAY))) {
     return fail(ctx, EB200_ERR_ARG, "Invalid pusher algorithm");
   }
-  if (!(c->dx > 0.0f)) return fail(ctx, EB200_ERR_ARG, "pusher.dx must be positive");
+  if (ctx->cfg.metric == EB200_METRIC_MINKOWSKI && !(c->dx > 0.0f)) {
+    return fail(ctx, EB200_ERR_ARG, "pusher.dx must be positive");
+  }
   return EB200_OK;
 }
 
@@ -250,6 +360,16 @@ int eb200_push_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher, const eb200_pr
   rc = check_prtls(ctx, prtls, npart);
   if (rc) return rc;
   REQUIRE(ctx, em != nullptr, "em is null");
+  REQUIRE(ctx, !is_gr(ctx), "eb200_push_sr on a GR context: use eb200_push_gr");
+  if (is_sr_curv(ctx)) {
+    REQUIRE(ctx, npart == 0 || prtls->phi != nullptr, "curvilinear 2D pusher needs prtls->phi");
+    REQUIRE(ctx, !pusher->has_atmosphere || (pusher->atm_gx2 == 0.0f && pusher->atm_gx3 == 0.0f),
+            "Invalid force for coordinate system"); // sr.hpp:1466, 1480
+    return check_cuda(ctx,
+                      eb200::curv::push_sr(ctx->metric, ctx->cfg.grid, ctx->cfg.shape_order,
+                                           *pusher, *prtls, npart, em, (cudaStream_t)stream),
+                      "push_sr (curvilinear)");
+  }
   return check_cuda(ctx,
                     VARIANT_CALL(ctx, push_sr(ctx->cfg.grid, ctx->cfg.shape_order, *pusher,
                                               *prtls, npart, em, (cudaStream_t)stream)),
@@ -265,6 +385,20 @@ int eb200_deposit(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, 
   REQUIRE(ctx, dt > 0.0f, "dt must be positive");
   REQUIRE(ctx, mode == EB200_DEPOSIT_ATOMIC || mode == EB200_DEPOSIT_ORDERED ||
                  mode == EB200_DEPOSIT_AGGREGATED, "bad deposit mode");
+  if (ctx->cfg.metric != EB200_METRIC_MINKOWSKI) {
+    REQUIRE(ctx, mode != EB200_DEPOSIT_ORDERED,
+            "curvilinear deposit: ATOMIC and AGGREGATED modes are built");
+    REQUIRE(ctx, npart == 0 || is_gr(ctx) || prtls->phi != nullptr,
+            "curvilinear 2D deposit needs prtls->phi");
+    cudaError_t e = is_gr(ctx)
+                      ? eb200::curv::deposit_gr(ctx->metric, ctx->cfg.grid, ctx->cfg.shape_order,
+                                                *prtls, npart, charge, dt, cur, mode,
+                                                (cudaStream_t)stream)
+                      : eb200::curv::deposit_sr(ctx->metric, ctx->cfg.grid, ctx->cfg.shape_order,
+                                                *prtls, npart, charge, dt, cur, mode,
+                                                (cudaStream_t)stream);
+    return check_cuda(ctx, e, "deposit (curvilinear)");
+  }
   const float dx = ctx->cfg.metric_params[0];
   REQUIRE(ctx, dx > 0.0f, "metric_params[0] (dx) must be positive");
   return check_cuda(ctx,
@@ -280,6 +414,7 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
   ENTER(ctx);
   REQUIRE(ctx, mode == EB200_DEPOSIT_ATOMIC || mode == EB200_DEPOSIT_AGGREGATED,
           "fused push+deposit supports the ATOMIC and AGGREGATED modes");
+  REQUIRE_MINK(ctx, "eb200_push_deposit_sr");
   int rc = check_pusher(ctx, pusher);
   if (rc) return rc;
   rc = check_prtls(ctx, prtls, npart);
@@ -291,6 +426,141 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
                                                       mode | (ctx->pd_kernel << 8),
                                                       (cudaStream_t)stream)),
                     "push_deposit_sr");
+}
+
+/* ------------------------------------------------------ curvilinear SR field solvers */
+int eb200_faraday_sr(eb200_ctx_t* ctx, float* em, float coeff, const int* fbc,
+                     eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, em != nullptr && fbc != nullptr, "null argument");
+  REQUIRE(ctx, is_sr_curv(ctx), "eb200_faraday_sr: spherical / qspherical contexts only");
+  return check_cuda(ctx,
+                    eb200::curv::faraday_sr(ctx->metric, ctx->cfg.grid, em, coeff, fbc,
+                                            (cudaStream_t)stream),
+                    "faraday_sr");
+}
+
+int eb200_ampere_sr(eb200_ctx_t* ctx, float* em, float coeff, const int* fbc,
+                    eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, em != nullptr && fbc != nullptr, "null argument");
+  REQUIRE(ctx, is_sr_curv(ctx), "eb200_ampere_sr: spherical / qspherical contexts only");
+  return check_cuda(ctx,
+                    eb200::curv::ampere_sr(ctx->metric, ctx->cfg.grid, em, coeff, fbc,
+                                           (cudaStream_t)stream),
+                    "ampere_sr");
+}
+
+int eb200_currents_ampere_sr(eb200_ctx_t* ctx, float* em, float* cur, float coeff, float inv_n0,
+                             const int* fbc, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, em != nullptr && cur != nullptr && fbc != nullptr, "null argument");
+  REQUIRE(ctx, is_sr_curv(ctx), "eb200_currents_ampere_sr: spherical / qspherical contexts only");
+  return check_cuda(ctx,
+                    eb200::curv::currents_ampere_sr(ctx->metric, ctx->cfg.grid, em, cur, coeff,
+                                                    inv_n0, fbc, (cudaStream_t)stream),
+                    "currents_ampere_sr");
+}
+
+/* --------------------------------------------------------------------------- GRPIC */
+int eb200_push_gr(eb200_ctx_t* ctx, const eb200_pusher_gr_t* pusher, const eb200_prtls_t* prtls,
+                  uint32_t npart, const float* em, const float* em0, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, is_gr(ctx), "eb200_push_gr: Kerr-Schild type contexts only");
+  REQUIRE(ctx, pusher != nullptr, "pusher context is null");
+  // grpic::ParticlePush: PHOTON or BORIS, anything else raises "not implemented"
+  REQUIRE(ctx, pusher->pusher_flags == EB200_PUSHER_PHOTON || pusher->pusher_flags == EB200_PUSHER_BORIS,
+          "not implemented");
+  REQUIRE(ctx, pusher->niter >= 0, "niter < 0");
+  int rc = check_prtls(ctx, prtls, npart);
+  if (rc) return rc;
+  REQUIRE(ctx, em != nullptr && em0 != nullptr, "null field");
+  return check_cuda(ctx,
+                    eb200::curv::push_gr(ctx->metric, ctx->cfg.grid, ctx->cfg.shape_order, *pusher,
+                                         *prtls, npart, em, em0, (cudaStream_t)stream),
+                    "push_gr");
+}
+
+static int gr_aux(eb200_ctx_t* ctx, int which_h, const float* d, const float* b, float* out,
+                  const int* fbc, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, is_gr(ctx), "GR aux fields: Kerr-Schild type contexts only");
+  REQUIRE(ctx, d != nullptr && b != nullptr && out != nullptr && fbc != nullptr, "null argument");
+  return check_cuda(ctx,
+                    eb200::curv::aux_gr(ctx->metric, ctx->cfg.grid, which_h, d, b, out, fbc,
+                                        (cudaStream_t)stream),
+                    which_h ? "gr_aux_h" : "gr_aux_e");
+}
+
+int eb200_gr_aux_e(eb200_ctx_t* ctx, const float* d, const float* b, float* e_out,
+                   const int* fbc, eb200_stream_t stream) {
+  return gr_aux(ctx, 0, d, b, e_out, fbc, stream);
+}
+
+int eb200_gr_aux_h(eb200_ctx_t* ctx, const float* d, const float* b, float* h_out,
+                   const int* fbc, eb200_stream_t stream) {
+  return gr_aux(ctx, 1, d, b, h_out, fbc, stream);
+}
+
+int eb200_faraday_gr(eb200_ctx_t* ctx, const float* b_in, float* b_out, const float* e_aux,
+                     float coeff, const int* fbc, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, is_gr(ctx), "eb200_faraday_gr: Kerr-Schild type contexts only");
+  REQUIRE(ctx, b_in && b_out && e_aux && fbc, "null argument");
+  return check_cuda(ctx,
+                    eb200::curv::faraday_gr(ctx->metric, ctx->cfg.grid, b_in, b_out, e_aux, coeff,
+                                            fbc, (cudaStream_t)stream),
+                    "faraday_gr");
+}
+
+int eb200_ampere_gr(eb200_ctx_t* ctx, const float* d_in, float* d_out, const float* h_aux,
+                    float coeff, const int* fbc, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, is_gr(ctx), "eb200_ampere_gr: Kerr-Schild type contexts only");
+  REQUIRE(ctx, d_in && d_out && h_aux && fbc, "null argument");
+  return check_cuda(ctx,
+                    eb200::curv::ampere_gr(ctx->metric, ctx->cfg.grid, d_in, d_out, h_aux, coeff,
+                                           fbc, (cudaStream_t)stream),
+                    "ampere_gr");
+}
+
+int eb200_currents_ampere_gr(eb200_ctx_t* ctx, float* d_fld, const float* cur, float coeff,
+                             const int* fbc, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, is_gr(ctx), "eb200_currents_ampere_gr: Kerr-Schild type contexts only");
+  REQUIRE(ctx, d_fld && cur && fbc, "null argument");
+  return check_cuda(ctx,
+                    eb200::curv::currents_ampere_gr(ctx->metric, ctx->cfg.grid, d_fld, cur, coeff,
+                                                    fbc, (cudaStream_t)stream),
+                    "currents_ampere_gr");
+}
+
+int eb200_time_average(eb200_ctx_t* ctx, float* a, const float* b, int ncomp,
+                       eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, ctx->cfg.grid.dim == 2, "eb200_time_average: 2D only");
+  REQUIRE(ctx, a && b && ncomp > 0, "bad argument");
+  return check_cuda(ctx, eb200::curv::time_average(ctx->cfg.grid, a, b, ncomp, (cudaStream_t)stream),
+                    "time_average");
+}
+
+int eb200_metric_eval(int metric, const int* n_active, const float* metric_params, int nq,
+                      const float* x1, const float* x2, float* out) {
+  if (!n_active || !metric_params || !x1 || !x2 || !out || nq < 0) {
+    return fail(nullptr, EB200_ERR_ARG, "eb200_metric_eval: bad argument");
+  }
+  const float*              mp = metric_params;
+  const eb200::MetricParams m  = eb200::make_metric(metric, n_active[0], n_active[1], mp[0], mp[1],
+                                                    mp[2], mp[3], mp[4], mp[5], mp[6]);
+  switch (metric) {
+    case EB200_METRIC_SPHERICAL: eval_sr_metric<eb200::Spherical>(m, nq, x1, x2, out); break;
+    case EB200_METRIC_QSPHERICAL: eval_sr_metric<eb200::QSpherical>(m, nq, x1, x2, out); break;
+    case EB200_METRIC_KERR_SCHILD: eval_gr_metric<eb200::KerrSchild>(m, nq, x1, x2, out); break;
+    case EB200_METRIC_QKERR_SCHILD: eval_gr_metric<eb200::QKerrSchild>(m, nq, x1, x2, out); break;
+    case EB200_METRIC_KERR_SCHILD_0: eval_gr_metric<eb200::KerrSchild0>(m, nq, x1, x2, out); break;
+    default: return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_metric_eval: unknown metric");
+  }
+  return EB200_OK;
 }
 
 int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which) {

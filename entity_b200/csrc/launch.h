@@ -61,6 +61,45 @@ namespace eb200 {
   EB200_DECLARE_VARIANT(strict_fp)
   EB200_DECLARE_VARIANT(fast_fp)
 
+  // curvilinear SR and GR kernels: curv.cu (one build, IEEE division, no FMA contraction)
+  struct MetricParams;
+  namespace curv {
+    cudaError_t push_sr(const MetricParams& m, const eb200_grid_t& g, int order,
+                        const eb200_pusher_t& c, const eb200_prtls_t& S, uint32_t npart,
+                        const float* em, cudaStream_t st);
+    cudaError_t deposit_sr(const MetricParams& m, const eb200_grid_t& g, int order,
+                           const eb200_prtls_t& S, uint32_t npart, float charge, float dt,
+                           float* cur, int mode, cudaStream_t st);
+    cudaError_t faraday_sr(const MetricParams& m, const eb200_grid_t& g, float* em, float coeff,
+                           const int* fbc, cudaStream_t st);
+    cudaError_t ampere_sr(const MetricParams& m, const eb200_grid_t& g, float* em, float coeff,
+                          const int* fbc, cudaStream_t st);
+    cudaError_t currents_ampere_sr(const MetricParams& m, const eb200_grid_t& g, float* em,
+                                   float* cur, float coeff, float inv_n0, const int* fbc,
+                                   cudaStream_t st);
+    cudaError_t filter_sph_pass(const eb200_grid_t& g, float* cur, const float* buff,
+                                const int* fbc, cudaStream_t st);
+    cudaError_t push_gr(const MetricParams& m, const eb200_grid_t& g, int order,
+                        const eb200_pusher_gr_t& c, const eb200_prtls_t& S, uint32_t npart,
+                        const float* em, const float* em0, cudaStream_t st);
+    cudaError_t deposit_gr(const MetricParams& m, const eb200_grid_t& g, int order,
+                           const eb200_prtls_t& S, uint32_t npart, float charge, float dt,
+                           float* cur, int mode, cudaStream_t st);
+    cudaError_t aux_gr(const MetricParams& m, const eb200_grid_t& g, int which_h, const float* Df,
+                       const float* Bf, float* out, const int* fbc, cudaStream_t st);
+    cudaError_t faraday_gr(const MetricParams& m, const eb200_grid_t& g, const float* Bin,
+                           float* Bout, const float* E, float coeff, const int* fbc,
+                           cudaStream_t st);
+    cudaError_t ampere_gr(const MetricParams& m, const eb200_grid_t& g, const float* Din,
+                          float* Dout, const float* H, float coeff, const int* fbc,
+                          cudaStream_t st);
+    cudaError_t currents_ampere_gr(const MetricParams& m, const eb200_grid_t& g, float* Df,
+                                   const float* cur, float coeff, const int* fbc,
+                                   cudaStream_t st);
+    cudaError_t time_average(const eb200_grid_t& g, float* a, const float* b, int ncomp,
+                             cudaStream_t st);
+  } // namespace curv
+
   // variant-independent (integer / copy work): sort.cu
   cudaError_t sort_particles(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
                              uint32_t maxnpart, int remove_dead, uint32_t* n_alive_out,

@@ -466,6 +466,63 @@ namespace eb200 {
     u[2] -= coeff * g * up[2];
   }
 
+  /* ---------------------------------------------- velocity update of a massive particle */
+  // Everything between the Cartesian fields at the particle and the position update
+  // (sr.hpp:206-309): optional half-kicks by an external force, hybrid GCA / Boris / Vay,
+  // radiative drag. `ec`, `bc`, `fext` are Cartesian; `fext` is only read when
+  // c.has_atmosphere is set.
+  __device__ __forceinline__ void velocity_update(const eb200_pusher_t& c, float ndh, float* u,
+                                                  float* ec, float* bc, const float* fext) {
+    const float dt        = c.dt;
+    float       up[3] = { ZERO, ZERO, ZERO }, er[3] = { ZERO, ZERO, ZERO },
+          br[3]       = { ZERO, ZERO, ZERO };
+    const bool drag   = c.drag_flags != EB200_DRAG_NONE;
+    if (drag) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        er[a] = ec[a];
+        br[a] = bc[a];
+        up[a] = u[a];
+      }
+    }
+    bool is_gca = false;
+    if (c.pusher_flags & EB200_PUSHER_GCA) {
+      const float E2 = nsq(ec), B2 = nsq(bc);
+      const float rL = sqrtf(ONE + nsq(u)) * dt / (TWO * fabsf(ndh) * sqrtf(B2));
+      is_gca = (B2 > ZERO) && (rL < c.gca_larmor_max) && ((E2 / B2) < c.gca_e_ovr_b_sqr_max);
+    }
+    if (is_gca) {
+      gca(ndh, dt, u, c.has_atmosphere ? fext : nullptr, ec, bc);
+    } else {
+      if (c.has_atmosphere) {
+        u[0] += HALF * dt * fext[0];
+        u[1] += HALF * dt * fext[1];
+        u[2] += HALF * dt * fext[2];
+      }
+      if (c.pusher_flags & EB200_PUSHER_BORIS) {
+        boris(ndh, u, ec, bc);
+      } else if (c.pusher_flags & EB200_PUSHER_VAY) {
+        vay(ndh, u, ec, bc);
+      }
+      if (c.has_atmosphere) {
+        u[0] += HALF * dt * fext[0];
+        u[1] += HALF * dt * fext[1];
+        u[2] += HALF * dt * fext[2];
+      }
+      if (drag) {
+        up[0] = HALF * (up[0] + u[0]);
+        up[1] = HALF * (up[1] + u[1]);
+        up[2] = HALF * (up[2] + u[2]);
+        if (c.drag_flags & EB200_DRAG_SYNCHROTRON) {
+          synchrotron_drag(c.sync_coeff, u, up, er, br);
+        }
+        if (c.drag_flags & EB200_DRAG_COMPTON) {
+          compton_drag(c.compton_coeff, u, up);
+        }
+      }
+    }
+  }
+
   /* ------------------------------------------------------------- one full push */
   struct PushArgs {
     eb200_pusher_t c;
@@ -507,18 +564,7 @@ namespace eb200 {
         ec[a] = ec[a] * c.dx;
         bc[a] = bc[a] * c.dx;
       }
-      float       fext[3] = { ZERO, ZERO, ZERO };
-      float       up[3] = { ZERO, ZERO, ZERO }, er[3] = { ZERO, ZERO, ZERO },
-            br[3]       = { ZERO, ZERO, ZERO };
-      const bool drag   = c.drag_flags != EB200_DRAG_NONE;
-      if (drag) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          er[a] = ec[a];
-          br[a] = bc[a];
-          up[a] = P.u[a];
-        }
-      }
+      float fext[3] = { ZERO, ZERO, ZERO };
       if (c.has_atmosphere) {
         const float gg[3] = { c.atm_gx1, c.atm_gx2, c.atm_gx3 };
 #pragma unroll
@@ -532,42 +578,7 @@ namespace eb200 {
           }
         }
       }
-      bool is_gca = false;
-      if (c.pusher_flags & EB200_PUSHER_GCA) {
-        const float E2 = nsq(ec), B2 = nsq(bc);
-        const float rL = sqrtf(ONE + nsq(P.u)) * dt / (TWO * fabsf(A.ndh) * sqrtf(B2));
-        is_gca = (B2 > ZERO) && (rL < c.gca_larmor_max) && ((E2 / B2) < c.gca_e_ovr_b_sqr_max);
-      }
-      if (is_gca) {
-        gca(A.ndh, dt, P.u, c.has_atmosphere ? fext : nullptr, ec, bc);
-      } else {
-        if (c.has_atmosphere) {
-          P.u[0] += HALF * dt * fext[0];
-          P.u[1] += HALF * dt * fext[1];
-          P.u[2] += HALF * dt * fext[2];
-        }
-        if (c.pusher_flags & EB200_PUSHER_BORIS) {
-          boris(A.ndh, P.u, ec, bc);
-        } else if (c.pusher_flags & EB200_PUSHER_VAY) {
-          vay(A.ndh, P.u, ec, bc);
-        }
-        if (c.has_atmosphere) {
-          P.u[0] += HALF * dt * fext[0];
-          P.u[1] += HALF * dt * fext[1];
-          P.u[2] += HALF * dt * fext[2];
-        }
-        if (drag) {
-          up[0] = HALF * (up[0] + P.u[0]);
-          up[1] = HALF * (up[1] + P.u[1]);
-          up[2] = HALF * (up[2] + P.u[2]);
-          if (c.drag_flags & EB200_DRAG_SYNCHROTRON) {
-            synchrotron_drag(c.sync_coeff, P.u, up, er, br);
-          }
-          if (c.drag_flags & EB200_DRAG_COMPTON) {
-            compton_drag(c.compton_coeff, P.u, up);
-          }
-        }
-      }
+      velocity_update(c, A.ndh, P.u, ec, bc, fext);
     }
     // Cartesian i+dx position update
     const float g2 = massive ? (ONE + SQR(P.u[0]) + SQR(P.u[1]) + SQR(P.u[2]))
@@ -630,11 +641,18 @@ namespace eb200 {
   /* ------------------------------------------------------------------ deposit */
   // SINK: callable (i, j, k, comp, value) in ghost-inclusive indices. Calls are issued in the
   // reference's program order so that an order-preserving sink reproduces its sums exactly.
+  // `vp_ext` (optional): the particle's coordinate velocity u^i / gamma as a curvilinear or GR
+  // metric gives it (currents_deposit.hpp:113-163); null = Cartesian, computed here.
   template <int D, int O, class SINK>
   __device__ __forceinline__ void deposit_particle(const Prtl<D>& P, float charge, float inv_dt,
-                                                   float dxc, int G, SINK&& J) {
+                                                   float dxc, int G, SINK&& J,
+                                                   const float* vp_ext = nullptr) {
     float vp[3];
-    {
+    if (vp_ext != nullptr) {
+      vp[0] = vp_ext[0];
+      vp[1] = vp_ext[1];
+      vp[2] = vp_ext[2];
+    } else {
       vp[0] = (0 < D) ? fdiv(P.u[0], dxc) : P.u[0];
       vp[1] = (1 < D) ? fdiv(P.u[1], dxc) : P.u[1];
       vp[2] = (2 < D) ? fdiv(P.u[2], dxc) : P.u[2];
@@ -906,18 +924,25 @@ namespace eb200 {
   // the NV nodes around the respective cell, in the node order of zigzag_offsets().
   template <int D>
   __device__ __forceinline__ void zigzag_values(const Prtl<D>& P, float charge, float inv_dt,
-                                                float dxc, float (&v)[2][ZigZag<D>::NV]) {
+                                                float dxc, float (&v)[2][ZigZag<D>::NV],
+                                                const float* vp_ext = nullptr) {
     float vp[3];
-    vp[0] = (0 < D) ? fdiv(P.u[0], dxc) : P.u[0];
-    vp[1] = (1 < D) ? fdiv(P.u[1], dxc) : P.u[1];
-    vp[2] = (2 < D) ? fdiv(P.u[2], dxc) : P.u[2];
-    const float inv_energy = rcp_sqrt(ONE + nsq(P.u));
-    if (isnan(vp[2]) || isinf(vp[2])) {
-      vp[2] = ZERO;
+    if (vp_ext != nullptr) {
+      vp[0] = vp_ext[0];
+      vp[1] = vp_ext[1];
+      vp[2] = vp_ext[2];
+    } else {
+      vp[0] = (0 < D) ? fdiv(P.u[0], dxc) : P.u[0];
+      vp[1] = (1 < D) ? fdiv(P.u[1], dxc) : P.u[1];
+      vp[2] = (2 < D) ? fdiv(P.u[2], dxc) : P.u[2];
+      const float inv_energy = rcp_sqrt(ONE + nsq(P.u));
+      if (isnan(vp[2]) || isinf(vp[2])) {
+        vp[2] = ZERO;
+      }
+      vp[0] *= inv_energy;
+      vp[1] *= inv_energy;
+      vp[2] *= inv_energy;
     }
-    vp[0] *= inv_energy;
-    vp[1] *= inv_energy;
-    vp[2] *= inv_energy;
     const float coeff = P.w * charge;
     float       W[3][2], Fl[3][2];
 #pragma unroll
@@ -1064,14 +1089,15 @@ namespace eb200 {
   __device__ __forceinline__ void deposit_particle_aggregated(const Prtl<D>& P, bool active,
                                                               float charge, float inv_dt,
                                                               float dxc, int G,
-                                                              const FieldView<D>& J) {
+                                                              const FieldView<D>& J,
+                                                              const float* vp_ext = nullptr) {
     if constexpr (O == 0) {
       constexpr int NV = ZigZag<D>::NV;
       float         v[2][NV];
       int           key0 = -1, key1 = -1;
       bool          cross = false;
       if (active) {
-        zigzag_values<D>(P, charge, inv_dt, dxc, v);
+        zigzag_values<D>(P, charge, inv_dt, dxc, v, vp_ext);
         key0 = (int)J.idx(P.ip[0] + G, (D > 1) ? P.ip[1] + G : 0, (D > 2) ? P.ip[2] + G : 0);
         key1 = (int)J.idx(P.i[0] + G, (D > 1) ? P.i[1] + G : 0, (D > 2) ? P.i[2] + G : 0);
         cross = key0 != key1;
@@ -1131,7 +1157,8 @@ namespace eb200 {
                                if (run.head && active && s != ZERO) {
                                  atomicAdd(&J.at(i, j, k, c), s);
                                }
-                             });
+                             },
+                             vp_ext);
     }
   }
 

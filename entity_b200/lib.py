@@ -67,6 +67,17 @@ class Pusher(C.Structure):
     ]
 
 
+class PusherGR(C.Structure):
+    """eb200_pusher_gr_t"""
+    _fields_ = [("pusher_flags", C.c_int), ("mass", C.c_float), ("charge", C.c_float),
+                ("dt", C.c_float), ("omegaB0", C.c_float), ("epsilon", C.c_float),
+                ("niter", C.c_int), ("pbc", C.c_int * 6), ("tag_outgoing", C.c_int)]
+
+
+METRIC_MINKOWSKI, METRIC_SPHERICAL, METRIC_QSPHERICAL = 0, 1, 2
+METRIC_KERR_SCHILD, METRIC_QKERR_SCHILD, METRIC_KERR_SCHILD_0 = 3, 4, 5
+
+
 class Config(C.Structure):
     _fields_ = [
         ("device", C.c_int), ("strict_fp", C.c_int),
@@ -146,6 +157,19 @@ def load():
                                           vp, vp, C.c_int, vp]
     lib.eb200_zero_currents.argtypes = [ctxp, vp, vp]
     lib.eb200_set_pd_kernel.argtypes = [ctxp, C.c_int]
+    f32p = C.POINTER(C.c_float)
+    lib.eb200_metric_eval.argtypes = [C.c_int, i32p, f32p, C.c_int, f32p, f32p, f32p]
+    lib.eb200_faraday_sr.argtypes = [ctxp, vp, C.c_float, i32p, vp]
+    lib.eb200_ampere_sr.argtypes = [ctxp, vp, C.c_float, i32p, vp]
+    lib.eb200_currents_ampere_sr.argtypes = [ctxp, vp, vp, C.c_float, C.c_float, i32p, vp]
+    lib.eb200_push_gr.argtypes = [ctxp, C.POINTER(PusherGR), C.POINTER(Prtls), C.c_uint32, vp,
+                                  vp, vp]
+    lib.eb200_gr_aux_e.argtypes = [ctxp, vp, vp, vp, i32p, vp]
+    lib.eb200_gr_aux_h.argtypes = [ctxp, vp, vp, vp, i32p, vp]
+    lib.eb200_faraday_gr.argtypes = [ctxp, vp, vp, vp, C.c_float, i32p, vp]
+    lib.eb200_ampere_gr.argtypes = [ctxp, vp, vp, vp, C.c_float, i32p, vp]
+    lib.eb200_currents_ampere_gr.argtypes = [ctxp, vp, vp, C.c_float, i32p, vp]
+    lib.eb200_time_average.argtypes = [ctxp, vp, vp, C.c_int, vp]
     lib.eb200_comm_fields.argtypes = [ctxp, vp, C.c_int, C.c_int, C.c_int, i32p, vp]
     lib.eb200_sync_currents.argtypes = [ctxp, vp, vp, i32p, vp]
     lib.eb200_sort_particles.argtypes = [ctxp, C.POINTER(Prtls), C.POINTER(C.c_uint32), C.c_int, vp]
@@ -237,6 +261,23 @@ def unique_id() -> bytes:
     return buf.raw
 
 
+def metric_eval(metric, n, metric_params, x1, x2):
+    """Host evaluation of the metric functions the kernels use (eb200_metric_eval): numpy in,
+    numpy out ([nq][16] for the SR metrics, [nq][32] for the GR ones)."""
+    import numpy as np
+    x1 = np.ascontiguousarray(x1, np.float32)
+    x2 = np.ascontiguousarray(x2, np.float32)
+    out = np.zeros((x1.size, 16 if metric <= METRIC_QSPHERICAL else 32), np.float32)
+    f32p = C.POINTER(C.c_float)
+    rc = load().eb200_metric_eval(metric, (C.c_int * 2)(*n),
+                                  (C.c_float * 8)(*(list(metric_params) + [0.0] * 8)[:8]),
+                                  x1.size, x1.ctypes.data_as(f32p), x2.ctypes.data_as(f32p),
+                                  out.ctypes.data_as(f32p))
+    if rc != 0:
+        raise EB200Error(load().eb200_last_error(None).decode())
+    return out
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -245,7 +286,7 @@ class Context:
     """One eb200 context (one local domain on one device)."""
 
     def __init__(self, n, order=0, strict=False, device=0, dx=1.0, xmin=(0.0, 0.0, 0.0),
-                 ng=None, maxnpart=0):
+                 ng=None, maxnpart=0, metric=METRIC_MINKOWSKI, metric_params=None):
         self.lib = load()
         self.order = order
         self.grid = Grid.make(n, nghosts_for(order) if ng is None else ng)
@@ -254,8 +295,13 @@ class Context:
         cfg.strict_fp = int(strict)
         cfg.grid = self.grid
         cfg.shape_order = order
-        cfg.metric = 0
-        cfg.metric_params = (C.c_float * 8)(dx, *xmin, 0, 0, 0, 0)
+        cfg.metric = metric
+        if metric == METRIC_MINKOWSKI:
+            cfg.metric_params = (C.c_float * 8)(dx, *xmin, 0, 0, 0, 0)
+        else:
+            # x1min, x1max, x2min, x2max, qsph_r0, qsph_h, ks_a
+            cfg.metric_params = (C.c_float * 8)(*(list(metric_params) + [0.0] * 8)[:8])
+        self.metric = metric
         cfg.maxnpart = maxnpart
         self.dx = dx
         self.xmin = tuple(xmin)
@@ -344,6 +390,61 @@ class Context:
     def filter(self, cur, buff, nfilter, fbc, stream=None):
         self._check(self.lib.eb200_filter(self.handle, _ptr(cur), _ptr(buff), nfilter,
                                           (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    # -- curvilinear SR field solvers (spherical / qspherical contexts)
+    def faraday_sr(self, em, coeff, fbc, stream=None):
+        self._check(self.lib.eb200_faraday_sr(self.handle, _ptr(em), coeff, (C.c_int * 6)(*fbc),
+                                              self._stream(stream)))
+
+    def ampere_sr(self, em, coeff, fbc, stream=None):
+        self._check(self.lib.eb200_ampere_sr(self.handle, _ptr(em), coeff, (C.c_int * 6)(*fbc),
+                                             self._stream(stream)))
+
+    def currents_ampere_sr(self, em, cur, coeff, inv_n0, fbc, stream=None):
+        self._check(self.lib.eb200_currents_ampere_sr(self.handle, _ptr(em), _ptr(cur), coeff,
+                                                      inv_n0, (C.c_int * 6)(*fbc),
+                                                      self._stream(stream)))
+
+    # -- GRPIC
+    @staticmethod
+    def make_pusher_gr(**kw) -> PusherGR:
+        p = PusherGR()
+        p.pusher_flags = kw.get("pusher_flags", PUSHER_BORIS)
+        p.mass, p.charge = kw.get("mass", 1.0), kw.get("charge", -1.0)
+        p.dt, p.omegaB0 = kw["dt"], kw.get("omegaB0", 1.0)
+        p.epsilon, p.niter = kw.get("epsilon", 1e-2), kw.get("niter", 10)
+        p.pbc = (C.c_int * 6)(*kw.get("pbc", [PBC_ABSORB, PBC_ABSORB, PBC_AXIS, PBC_AXIS, 0, 0]))
+        p.tag_outgoing = kw.get("tag_outgoing", 0)
+        return p
+
+    def push_gr(self, pusher, arrays, npart, em, em0, stream=None):
+        s = self.prtls_struct(arrays)
+        self._check(self.lib.eb200_push_gr(self.handle, C.byref(pusher), C.byref(s), npart,
+                                           _ptr(em), _ptr(em0), self._stream(stream)))
+
+    def gr_aux_e(self, d, b, out, fbc, stream=None):
+        self._check(self.lib.eb200_gr_aux_e(self.handle, _ptr(d), _ptr(b), _ptr(out),
+                                            (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    def gr_aux_h(self, d, b, out, fbc, stream=None):
+        self._check(self.lib.eb200_gr_aux_h(self.handle, _ptr(d), _ptr(b), _ptr(out),
+                                            (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    def faraday_gr(self, b_in, b_out, e_aux, coeff, fbc, stream=None):
+        self._check(self.lib.eb200_faraday_gr(self.handle, _ptr(b_in), _ptr(b_out), _ptr(e_aux),
+                                              coeff, (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    def ampere_gr(self, d_in, d_out, h_aux, coeff, fbc, stream=None):
+        self._check(self.lib.eb200_ampere_gr(self.handle, _ptr(d_in), _ptr(d_out), _ptr(h_aux),
+                                             coeff, (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    def currents_ampere_gr(self, d, cur, coeff, fbc, stream=None):
+        self._check(self.lib.eb200_currents_ampere_gr(self.handle, _ptr(d), _ptr(cur), coeff,
+                                                      (C.c_int * 6)(*fbc), self._stream(stream)))
+
+    def time_average(self, a, b, stream=None):
+        self._check(self.lib.eb200_time_average(self.handle, _ptr(a), _ptr(b), a.shape[0],
+                                                self._stream(stream)))
 
     # -- particles
     def push(self, pusher, arrays, npart, em, stream=None):

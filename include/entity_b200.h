@@ -54,7 +54,16 @@ enum { EB200_DRAG_NONE = 0, EB200_DRAG_SYNCHROTRON = 1, EB200_DRAG_COMPTON = 2 }
 enum { EB200_PBC_NONE = 0, EB200_PBC_PERIODIC = 1, EB200_PBC_ABSORB = 2, EB200_PBC_REFLECT = 3, EB200_PBC_AXIS = 4 };
 /* field boundary per face, as far as filter and ghost exchange need it (ntt::FldsBC) */
 enum { EB200_FBC_NONE = 0, EB200_FBC_PERIODIC = 1, EB200_FBC_CONDUCTOR = 2, EB200_FBC_AXIS = 3, EB200_FBC_SYNC = 4 };
-enum { EB200_METRIC_MINKOWSKI = 0 };
+/* ntt::Metric (src/global/enums.h): the curvilinear metrics are 2D axisymmetric, like the
+ * reference's (static_asserts in src/metrics/qspherical.h:34-35 etc.) */
+enum {
+  EB200_METRIC_MINKOWSKI     = 0,
+  EB200_METRIC_SPHERICAL     = 1, /* src/metrics/spherical.h */
+  EB200_METRIC_QSPHERICAL    = 2, /* src/metrics/qspherical.h */
+  EB200_METRIC_KERR_SCHILD   = 3, /* src/metrics/kerr_schild.h */
+  EB200_METRIC_QKERR_SCHILD  = 4, /* src/metrics/qkerr_schild.h */
+  EB200_METRIC_KERR_SCHILD_0 = 5  /* src/metrics/kerr_schild_0.h */
+};
 /* deposit modes */
 enum {
   EB200_DEPOSIT_ATOMIC     = 0, /* one atomic add per particle and node (what Kokkos ScatterView does on CUDA) */
@@ -123,7 +132,9 @@ typedef struct {
   eb200_grid_t grid;        /* local mesh */
   int          shape_order; /* SHAPE_ORDER of the reference build: 0 (zig-zag), 1..3 (Esirkepov) */
   int          metric;      /* EB200_METRIC_* */
-  float        metric_params[8]; /* Minkowski: dx, x1min, x2min, x3min */
+  float        metric_params[8]; /* Minkowski: dx, x1min, x2min, x3min;
+                                    curvilinear / GR: x1min, x1max, x2min, x2max (physical extent of
+                                    THIS domain), qsph_r0, qsph_h, ks_a */
   uint32_t     maxnpart;    /* capacity of each particle array handed to this context */
 } eb200_config_t;
 
@@ -316,6 +327,73 @@ int eb200_profile_read(eb200_ctx_t* ctx, float* ms_host, int* calls_host);
 int eb200_srpic_step_host(eb200_ctx_t* ctx, const eb200_srpic_params_t* prm, float* em_host,
                           float* cur_host, eb200_species_t* species_host, int nspecies,
                           uint32_t step, double time, uint64_t* bytes_h2d, uint64_t* bytes_d2h);
+
+/* ============================================================ curvilinear SR (2D) */
+/* For EB200_METRIC_SPHERICAL / QSPHERICAL contexts eb200_push_sr and eb200_deposit run the
+ * curvilinear branches of the same reference kernels (sr.hpp:573-657 position push through
+ * Cartesian space, phi carried in prtls->phi; currents_deposit.hpp:133-139 velocity transform).
+ * pusher->dx / xmin are ignored; atm_gx2 / atm_gx3 must be zero (the reference raises). The
+ * field solvers of the curvilinear path have their own argument lists: */
+/* kernel::sr::Faraday_kernel (src/kernels/faraday_sr.hpp:53-89), coeff = dT;
+ * fbc_host[6]: only the AXIS flags of the x2 faces are read */
+int eb200_faraday_sr(eb200_ctx_t* ctx, float* em, float coeff, const int* fbc_host,
+                     eb200_stream_t stream);
+/* kernel::sr::Ampere_kernel (src/kernels/ampere_sr.hpp:58-109) over srpic::RangeWithAxisBCs */
+int eb200_ampere_sr(eb200_ctx_t* ctx, float* em, float coeff, const int* fbc_host,
+                    eb200_stream_t stream);
+/* kernel::sr::CurrentsAmpere_kernel (ampere_sr.hpp:163-209): coeff = -dt q0 n0 / B0 */
+int eb200_currents_ampere_sr(eb200_ctx_t* ctx, float* em, float* cur, float coeff, float inv_n0,
+                             const int* fbc_host, eb200_stream_t stream);
+/* eb200_filter on such a context runs DigitalFilter_kernel<Dim::_2D, Coord::Spherical>
+ * (digital_filter.hpp:196-281) with the axis rows treated as the reference does. */
+
+/* ====================================================================== GRPIC (2D) */
+/* kernel::gr::PusherContext + PusherBoundaries (src/kernels/pushers/context.h:182-228) */
+typedef struct {
+  int   pusher_flags; /* EB200_PUSHER_BORIS (massive) or EB200_PUSHER_PHOTON (massless) */
+  float mass, charge;
+  float dt, omegaB0;
+  float epsilon;      /* algorithms.gr.pusher_eps (unused by the analytic-derivative pusher) */
+  int   niter;        /* algorithms.gr.pusher_niter */
+  int   pbc[6];       /* EB200_PBC_ABSORB (incl. HORIZON) on x1 faces, EB200_PBC_AXIS on x2 faces */
+  int   tag_outgoing;
+} eb200_pusher_gr_t;
+/* grpic::ParticlePush for one species (src/engines/grpic/particle_pusher.h:27-89,
+ * src/kernels/pushers/gr.hpp:668-865): em holds D (components 0..2), em0 holds B (3..5);
+ * ux1..3 are the covariant momentum components. */
+int eb200_push_gr(eb200_ctx_t* ctx, const eb200_pusher_gr_t* pusher, const eb200_prtls_t* prtls,
+                  uint32_t npart, const float* em, const float* em0, eb200_stream_t stream);
+/* kernel::gr::ComputeAuxE_kernel / ComputeAuxH_kernel (src/kernels/aux_fields_gr.hpp:49-226)
+ * over grpic::range_with_axis_BCs; D / B / out are 6-component fields (the reference passes
+ * em or em0 for either, src/engines/grpic/fieldsolvers.h:79-128) */
+int eb200_gr_aux_e(eb200_ctx_t* ctx, const float* d_fld, const float* b_fld, float* e_out,
+                   const int* fbc_host, eb200_stream_t stream);
+int eb200_gr_aux_h(eb200_ctx_t* ctx, const float* d_fld, const float* b_fld, float* h_out,
+                   const int* fbc_host, eb200_stream_t stream);
+/* kernel::gr::Faraday_kernel (src/kernels/faraday_gr.hpp:63-93): b_out = b_in + dT curl E */
+int eb200_faraday_gr(eb200_ctx_t* ctx, const float* b_in, float* b_out, const float* e_aux,
+                     float coeff, const int* fbc_host, eb200_stream_t stream);
+/* kernel::gr::Ampere_kernel (src/kernels/ampere_gr.hpp:65-102): d_out = d_in + dT curl H. In
+ * place (d_in == d_out) the axis rows follow the reference's serial row order. */
+int eb200_ampere_gr(eb200_ctx_t* ctx, const float* d_in, float* d_out, const float* h_aux,
+                    float coeff, const int* fbc_host, eb200_stream_t stream);
+/* kernel::gr::CurrentsAmpere_kernel (ampere_gr.hpp:143-176): coeff = -dt q0 / B0 */
+int eb200_currents_ampere_gr(eb200_ctx_t* ctx, float* d_fld, const float* cur, float coeff,
+                             const int* fbc_host, eb200_stream_t stream);
+/* kernel::gr::TimeAverageDB_kernel / TimeAverageJ_kernel (aux_fields_gr.hpp:253-302):
+ * a = (a + b) / 2 on the active cells of an ncomp-component field */
+int eb200_time_average(eb200_ctx_t* ctx, float* a, const float* b, int ncomp,
+                       eb200_stream_t stream);
+
+/* Host-side evaluation of the metric functions the kernels use (same source, compiled for the
+ * host): what the reference's setup code gets from metric.h_<i,j>() etc. (src/metrics/*.h).
+ * n_active[2], metric_params[8] as in eb200_config_t. out[nq][16] for the SR metrics:
+ * h_11 h_22 h_33 sqrt_h_11 sqrt_h_22 sqrt_h_33 sqrt_det_h polar_area r theta x1(r) x2(theta);
+ * out[nq][32] for the GR metrics: h_11 h_22 h_33 h_13 h^11 h^22 h^33 h^13 alpha beta^1
+ * sqrt_det_h sqrt_det_h_tilde polar_area dr_alpha dt_alpha dr_beta1 dt_beta1 dr_h11 dr_h22
+ * dr_h33 dr_h13 dt_h11 dt_h22 dt_h33 dt_h13 theta x2(theta). Needs no device. */
+int eb200_metric_eval(int metric, const int* n_active, const float* metric_params, int nq,
+                      const float* x1_host, const float* x2_host, float* out_host);
 
 #ifdef __cplusplus
 }
