@@ -565,7 +565,8 @@ int eb200_metric_eval(int metric, const int* n_active, const float* metric_param
 
 int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which) {
   ENTER(ctx);
-  REQUIRE(ctx, which >= 0 && which <= 3, "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4");
+  REQUIRE(ctx, which >= 0 && which <= 4,
+          "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4, 4 shared-memory tiles");
   ctx->pd_kernel = which;
   return EB200_OK;
 }

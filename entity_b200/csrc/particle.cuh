@@ -303,6 +303,9 @@ namespace eb200 {
     const int e = static_cast<int>(
       EB.idx(P.i[0] + ng, (D > 1) ? P.i[1] + ng : 0, (D > 2) ? P.i[2] + ng : 0));
     auto lerp = [&](int c, bool sx, bool sy, bool sz, bool wy_dual) -> float {
+#ifdef EB200_X_NOGATHER
+      return 1e-3f * static_cast<float>(c + 1) + 1e-6f * static_cast<float>(e) + wp[0][0];
+#endif
       const float* bc = EB.p + EB.plane * c;
       const int    o  = e + (sx ? od[0] : 0) + ((D > 1 && sy) ? od[1] : 0) +
                     ((D > 2 && sz) ? od[2] : 0);
@@ -339,12 +342,70 @@ namespace eb200 {
     b0[2] = lerp(bx3, true, true, false, D != 3);
   }
 
+  // A CTA's shared-memory copy of the E/B nodes around its (cell-sorted) particles: TR rows of
+  // TC columns per component, origin (c0, r0) in ghost-inclusive node indices. Particles whose
+  // 3 x 3 gather neighbourhood lies inside read shared memory (immediate offsets from one
+  // local index); the others -- strays of a not quite sorted array -- read global memory.
+  template <int TC, int TR>
+  struct TileEM {
+    const float* t;
+    int          c0, r0;
+    FieldView<2> G;
+  };
+
+  template <class T>
+  struct is_tile_em : std::false_type {};
+  template <int TC, int TR>
+  struct is_tile_em<TileEM<TC, TR>> : std::true_type {};
+
+  template <int TC, int TR>
+  __device__ __forceinline__ void gather_tile(const TileEM<TC, TR>& T, int ng, const Prtl<2>& P,
+                                              float* e0, float* b0) {
+    const int lc = P.i[0] + ng - T.c0, lr = P.i[1] + ng - T.r0;
+    if (static_cast<unsigned>(lc - 1) <= static_cast<unsigned>(TC - 3) &&
+        static_cast<unsigned>(lr - 1) <= static_cast<unsigned>(TR - 3)) {
+      constexpr int TN = TC * TR;
+      float         wp[2][2], wd[2][2];
+      int           od[2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int ind = static_cast<int>(P.d[a] + HALF);
+        od[a]         = (ind - 1) * (a == 0 ? 1 : TC);
+        wp[a][0]      = ONE - P.d[a];
+        wp[a][1]      = P.d[a];
+        wd[a][0]      = static_cast<float>(ind + 1) - (P.d[a] + HALF);
+        wd[a][1]      = ONE - wd[a][0];
+      }
+      const float* pp = T.t + (lr * TC + lc);
+      const float* dp = pp + od[0];
+      const float* pd = pp + od[1];
+      const float* dd = dp + od[1];
+      auto lerp = [&](const float* q, int c, const float* wx, const float* wy) -> float {
+        q += c * TN;
+        const float c00 = q[0] * wx[0] + q[1] * wx[1];
+        const float c10 = q[TC] * wx[0] + q[TC + 1] * wx[1];
+        return c00 * wy[0] + c10 * wy[1];
+      };
+      e0[0] = lerp(dp, ex1, wd[0], wp[1]);
+      e0[1] = lerp(pd, ex2, wp[0], wd[1]);
+      e0[2] = lerp(pp, ex3, wp[0], wp[1]);
+      b0[0] = lerp(pd, bx1, wp[0], wd[1]);
+      b0[1] = lerp(dp, bx2, wd[0], wp[1]);
+      b0[2] = lerp(dd, bx3, wd[0], wd[1]);
+    } else {
+      gather_fields_direct<2>(T.G, ng, P, e0, b0);
+    }
+  }
+
   // what push_particle() calls: a FieldView goes through the direct gather where one exists,
   // any other callable through the generic one
   template <int D, int O, class EM>
   __device__ __forceinline__ void gather_any(const EM& F, int ng, const Prtl<D>& P, float* e0,
                                              float* b0) {
-    if constexpr (std::is_same<EM, FieldView<D>>::value) {
+    if constexpr (is_tile_em<EM>::value) {
+      static_assert(D == 2 && O == 0, "field tiles: 2D zig-zag only");
+      gather_tile(F, ng, P, e0, b0);
+    } else if constexpr (std::is_same<EM, FieldView<D>>::value) {
       if constexpr (O == 0) {
         gather_fields_direct<D>(F, ng, P, e0, b0);
       } else {

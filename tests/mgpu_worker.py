@@ -36,7 +36,8 @@ def main(decomp2d=None, decomp3d=None):
     torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    uid = bootstrap_unique_id()
+    # an ncclUniqueId names ONE communicator: every eb200_comm_init gets a fresh one
+    fresh_uid = bootstrap_unique_id
     orc.build(ref=False)
     o = orc.oracle()
 
@@ -66,7 +67,7 @@ def main(decomp2d=None, decomp3d=None):
             dom, I = doms[rank], infos[rank]
             ctx = eb.Context(dom.n, order=order, strict=True, device=local)
             md = L.make_metadomain(rank, extents)
-            ctx.comm_init(md, uid)
+            ctx.comm_init(md, fresh_uid())
             f = dev(np.nan_to_num(flds[rank], nan=-777.0))
             ctx.comm_fields(f, 0, 6, [I.face_fbc[k] for k in range(6)])
             torch.cuda.synchronize()
@@ -97,7 +98,7 @@ def main(decomp2d=None, decomp3d=None):
         sets, counts = T._split_particles(p, infos, doms, cap=6000)
         dom, I = doms[rank], infos[rank]
         ctx = eb.Context(dom.n, order=0, strict=True, device=local, dx=1.0)
-        ctx.comm_init(L.make_metadomain(rank, extents), uid)
+        ctx.comm_init(L.make_metadomain(rank, extents), fresh_uid())
         arr = to_device(sets[rank])
         npart = counts[rank]
         em0 = torch.zeros(ctx.grid.shape(6), dtype=torch.float32, device="cuda")
@@ -159,7 +160,7 @@ def main(decomp2d=None, decomp3d=None):
         nper = ncell * ppc0 // 2
         sim = Simulation(mdm.local_n, order, scales, nfilter=2, fused=fused, deposit_mode=mode,
                          device=local)
-        mdm.attach(sim, uid)
+        mdm.attach(sim, fresh_uid())
         I = mdm.info
         win = (slice(None),) + tuple(
             slice(G + I.cell_offset[a], G + I.cell_offset[a] + mdm.local_n[a]) for a in reversed(range(dim)))

@@ -233,3 +233,67 @@ def test_errors(eb):
     ctx = eb.Context((8, 8), order=0)
     with pytest.raises(eb.EB200Error, match="No particle pusher"):
         ctx.push(ctx.make_pusher(dt=0.1, pusher_flags=0), {}, 0, None)
+
+
+@pytest.mark.parametrize("which", [1, 2, 3, 4])
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("order_kind", ["sorted", "stale", "random"])
+def test_fused_kernels_wide_mesh(eb, orc_mod, which, strict, order_kind):
+    """Every fused push+deposit kernel (1 per-thread, 2 TMA chunks, 3 four particles per thread,
+    4 shared-memory field tile) on a mesh wide enough for the tile kernel, on cell-sorted
+    particles, on a 'stale' order (sorted, then pushed twice without re-sorting: the state
+    between two sorts) and on a random order; two consecutive steps so that crossings, periodic
+    wraps and strays outside the tile all occur. Strict build: particles bit-exact (the pusher
+    arithmetic is the same whichever kernel runs), J within fp32 summation-order tolerance;
+    fast build: the tolerances of test_push_deposit_fast."""
+    orc = orc_mod.oracle()
+    n_cells = (252, 24)  # 252 + 2*2 ghosts = 256 columns: 16-byte aligned rows
+    g = orc_mod.Grid.make(n_cells, 2)
+    dx = 0.5
+    common = dict(dt=0.45 * dx, omegaB0=0.7, mass=1.0, charge=-1.0, dx=dx, xmin=[0.1, 0.2, 0.3],
+                  pbc=[orc_mod.PBC_PERIODIC] * 6, pusher_flags=2)
+    octx = orc_mod.make_pusher(**common)
+    ctx = eb.Context(n_cells, order=0, strict=strict, dx=dx, xmin=(0.1, 0.2, 0.3))
+    ctx.set_pd_kernel(which)
+    gctx = ctx.make_pusher(**common)
+    em = smooth_fields(g, 77, amp=0.6)
+    n = 40000 + 3
+    p = random_particles(g, n, 4242, umag=1.0, dead_frac=0.03)
+
+    def sort_by_cell(q):
+        key = q.i1.astype(np.int64) + g.n[0] * q.i2.astype(np.int64)
+        key[q.tag == 0] = 1 << 40
+        perm = np.argsort(key, kind="stable")
+        for nm in q.names():
+            getattr(q, nm)[:] = getattr(q, nm)[perm]
+
+    if order_kind != "random":
+        sort_by_cell(p)
+    if order_kind == "stale":
+        for _ in range(2):
+            orc.push(g, 0, octx, p, n, em)
+    d_em = dev(em)
+    arr = to_device(p)
+    launches0 = ctx.launch_count
+    for step in range(2):
+        j_ref = np.zeros(g.shape(3), np.float32)
+        d_j = dev(j_ref)
+        orc.push(g, 0, octx, p, n, em)
+        orc.deposit(g, 0, p, n, -1.0, octx.dt, dx, j_ref)
+        ctx.push_deposit(gctx, arr, n, d_em, d_j, mode=eb.DEPOSIT_AGGREGATED)
+        q = to_host(arr, n)
+        if strict:
+            assert_prtls_values_equal(q, p, what=f"kernel {which} step {step}")
+        else:
+            same = np.ones(n, bool)
+            for nm in ("i1", "i2", "i1_prev", "i2_prev", "tag"):
+                same &= getattr(q, nm) == getattr(p, nm)
+            assert (~same).sum() <= 4
+            for nm in ("ux1", "ux2", "ux3", "dx1", "dx2"):
+                np.testing.assert_allclose(getattr(q, nm)[same], getattr(p, nm)[same], rtol=1e-4,
+                                           atol=2e-5, err_msg=nm)
+            # keep both sides on the same trajectory for the second step
+            arr = to_device(p)
+        scale = np.abs(j_ref).max()
+        assert np.abs(host(d_j) - j_ref).max() <= 2e-4 * scale, f"kernel {which} step {step}"
+    assert ctx.launch_count - launches0 >= 2
