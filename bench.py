@@ -349,13 +349,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, nargs=2, default=[4096, 2048])
     ap.add_argument("--ppc", type=int, default=32)
     ap.add_argument("--filters", type=int, default=8)
-    ap.add_argument("--sort-interval", type=int, default=20)
+    ap.add_argument("--sort-interval", type=int, default=40)
     ap.add_argument("--deposit", default="aggregated", choices=["atomic", "aggregated", "ordered"])
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -336,29 +336,51 @@ namespace eb200 {
 
     // one thread per cell of the ghost-inclusive box; a ghost cell takes the value of its
     // periodic image (an active cell) when every face it lies beyond is periodic
+    // Threads cover only the 2 D ghost slabs (thickness G, full extent in the other dimensions;
+    // corner cells belong to several slabs and are written more than once with the same value).
     template <int D>
     __global__ void __launch_bounds__(256)
       ghost_fill_kernel(Box box, FieldView<D> F, int c0, int c1, Periodic per) {
-      const long t  = (long)blockIdx.x * blockDim.x + threadIdx.x;
-      const long N1 = F.N1, N2 = F.N2, N3 = F.N3;
-      if (t >= N1 * N2 * N3) return;
-      int x[3] = { (int)(t % N1), (int)((t / N1) % N2), (int)(t / (N1 * N2)) };
-      int s[3] = { x[0], x[1], x[2] };
-      bool ghost = false;
+      long      t    = (long)blockIdx.x * blockDim.x + threadIdx.x;
+      const int G    = box.G;
+      const int N[3] = { F.N1, F.N2, F.N3 };
+      int       x[3] = { 0, 0, 0 };
+      bool      found = false;
 #pragma unroll
       for (int a = 0; a < D; ++a) {
-        const int G = box.G, n = box.n[a];
+        // slab pair of dimension a: 2 G layers x the full extents of the other dimensions
+        long other = 1;
+#pragma unroll
+        for (int b = 0; b < D; ++b) other *= (b == a) ? 1 : N[b];
+        const long sz = 2L * G * other;
+        if (!found && t < sz) {
+          const int layer = (int)(t / other); // 0 .. 2G-1
+          long      r     = t % other;
+          x[a]            = (layer < G) ? layer : (box.n[a] + layer); // hi: n + G + (layer - G)
+#pragma unroll
+          for (int b = 0; b < D; ++b) {
+            if (b != a) {
+              x[b] = (int)(r % N[b]);
+              r   /= N[b];
+            }
+          }
+          found = true;
+        }
+        if (!found) t -= sz;
+      }
+      if (!found) return;
+      int s[3] = { x[0], x[1], x[2] };
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        const int n = box.n[a];
         if (x[a] < G) {
           if (!per.per[a]) return;
-          s[a]  = x[a] + n;
-          ghost = true;
+          s[a] = x[a] + n;
         } else if (x[a] >= n + G) {
           if (!per.per[a]) return;
-          s[a]  = x[a] - n;
-          ghost = true;
+          s[a] = x[a] - n;
         }
       }
-      if (!ghost) return;
       for (int c = c0; c < c1; ++c) {
         F.at(x[0], x[1], x[2], c) = F.at(s[0], s[1], s[2], c);
       }
@@ -417,6 +439,67 @@ namespace eb200 {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         J.at(x[0], x[1], x[2], c) += acc[c];
+      }
+    }
+
+    /* ------------------------------------- fused binomial passes (2D, doubly periodic) */
+    // `P` consecutive filter passes in one sweep over memory (temporal blocking): a CTA stages
+    // its FT_X x FT_Y output tile plus a P-cell halo of one component in shared memory (halo
+    // cells read the periodic image of the ACTIVE cells, which is what the per-pass ghost
+    // exchange of srpic::CurrentsFilter provides, currents.h:108-118), runs the passes between
+    // two shared buffers on a region that shrinks by one cell per pass, and writes the tile.
+    // Every cell of every pass is computed with the reference's interior expression
+    // (digital_filter.hpp:267-280) from the same nine values as the pass-by-pass path, so the
+    // strict build gives identical bits. Traffic per P passes: ~1.7 reads + 1 write per value
+    // instead of P x (copy + stencil + ghost fill).
+    constexpr int FT_X = 64, FT_Y = 16, FT_PMAX = 4;
+
+    template <int P>
+    __global__ void __launch_bounds__(256)
+      filter_fused2d_kernel(FieldView<2> src, FieldView<2> dst, int n1, int n2, int G) {
+      constexpr int W = FT_X + 2 * P, H = FT_Y + 2 * P;
+      __shared__ float buf[2][H * W];
+      const int c  = blockIdx.z;
+      const int x0 = blockIdx.x * FT_X - P, y0 = blockIdx.y * FT_Y - P; // active coordinates
+      // periodic image of an active coordinate; one wrap suffices unless the mesh is smaller
+      // than tile + halo, then the general modulo is taken
+      auto wrap = [](int g, int n) {
+        if (g < 0) g += n;
+        if (g >= n) g -= n;
+        if (g < 0 || g >= n) {
+          g %= n;
+          g += (g < 0) ? n : 0;
+        }
+        return g;
+      };
+      for (int e = threadIdx.x; e < W * H; e += 256) {
+        const int ly = e / W, lx = e - ly * W;
+        buf[0][e] = src.ld(wrap(x0 + lx, n1) + G, wrap(y0 + ly, n2) + G, 0, c);
+      }
+      __syncthreads();
+      int cur = 0;
+#pragma unroll
+      for (int p = 1; p <= P; ++p) {
+        const float* b = buf[cur];
+        float*       a = buf[cur ^ 1];
+        const int    w = W - 2 * p, h = H - 2 * p; // compile-time after unrolling
+        for (int e = threadIdx.x; e < w * h; e += 256) {
+          const int    ly = e / w, lx = e - ly * w;
+          const float* q  = b + (ly + p) * W + (lx + p);
+          a[(ly + p) * W + (lx + p)] =
+            INV_4 * q[0] + INV_8 * (q[-1] + q[1] + q[-W] + q[W]) +
+            INV_16 * (q[-W - 1] + q[W + 1] + q[W - 1] + q[-W + 1]);
+        }
+        cur ^= 1;
+        __syncthreads();
+      }
+      const float* r = buf[cur];
+      for (int e = threadIdx.x; e < FT_X * FT_Y; e += 256) {
+        const int ly = e / FT_X, lx = e - ly * FT_X;
+        const int gx = blockIdx.x * FT_X + lx, gy = blockIdx.y * FT_Y + ly;
+        if (gx < n1 && gy < n2) {
+          dst.at(gx + G, gy + G, 0, c) = r[(ly + P) * W + (lx + P)];
+        }
       }
     }
 
@@ -515,6 +598,21 @@ namespace eb200 {
       return cudaGetLastError();
     }
 
+    cudaError_t filter_fused(const eb200_grid_t& g, const float* src, float* dst, int passes,
+                             cudaStream_t st) {
+      if (g.dim != 2 || passes < 1 || passes > FT_PMAX) return cudaErrorInvalidValue;
+      const dim3 grid((g.n[0] + FT_X - 1) / FT_X, (g.n[1] + FT_Y - 1) / FT_Y, 3);
+      const FieldView<2> S(g, const_cast<float*>(src)), Dd(g, dst);
+      switch (passes) {
+        case 1: filter_fused2d_kernel<1><<<grid, 256, 0, st>>>(S, Dd, g.n[0], g.n[1], g.ng); break;
+        case 2: filter_fused2d_kernel<2><<<grid, 256, 0, st>>>(S, Dd, g.n[0], g.n[1], g.ng); break;
+        case 3: filter_fused2d_kernel<3><<<grid, 256, 0, st>>>(S, Dd, g.n[0], g.n[1], g.ng); break;
+        default: filter_fused2d_kernel<4><<<grid, 256, 0, st>>>(S, Dd, g.n[0], g.n[1], g.ng); break;
+      }
+      count_launch();
+      return cudaGetLastError();
+    }
+
     static Periodic periodic_of(const eb200_grid_t& g, const int* fbc) {
       Periodic p;
       for (int a = 0; a < 3; ++a) {
@@ -529,7 +627,12 @@ namespace eb200 {
       const Box      box = make_box(g);
       const Periodic per = periodic_of(g, fbc);
       if (!(per.per[0] || per.per[1] || per.per[2])) return cudaSuccess;
-      const long n = n_total(g);
+      long n = 0; // cells of the ghost slabs
+      for (int a = 0; a < g.dim; ++a) {
+        long other = 1;
+        for (int b = 0; b < g.dim; ++b) other *= (b == a) ? 1 : (g.n[b] + 2 * g.ng);
+        n += 2L * g.ng * other;
+      }
 #define CALL(D)                                                                                \
   ghost_fill_kernel<D><<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, fld), c0, c1, per);
       BY_DIM(g, CALL)

@@ -16,13 +16,11 @@ namespace eb200 {
   template <int D>
   __global__ void __launch_bounds__(256)
     sort_keys_kernel(eb200_prtls_t S, uint32_t npart, int n1, int n2, int n3, uint32_t ncells,
-                     uint32_t* keys, uint32_t* idx, uint32_t* n_alive) {
+                     uint32_t* keys, uint32_t* idx) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t       alive = 0;
     if (p < npart) {
       uint32_t key = ncells; // dead (or any non-alive tag) goes last
       if (S.tag[p] == 1) {
-        alive = 1;
         int i = min(max(S.i1[p], 0), n1 - 1);
         key   = (uint32_t)i;
         if constexpr (D > 1) {
@@ -37,11 +35,23 @@ namespace eb200 {
       keys[p] = key;
       idx[p]  = p;
     }
-    // block-aggregated count of alive particles
-    const uint32_t w = __reduce_add_sync(0xffffffffu, alive);
-    if ((threadIdx.x & 31) == 0 && w) {
-      atomicAdd(n_alive, w);
+  }
+
+  // number of alive particles = position of the first key == ncells in the sorted keys
+  // (a binary search by one thread; a per-warp atomic counter on one address costs ~1 ns per
+  // warp, 5 ms for 1.7e8 particles)
+  __global__ void count_alive_kernel(const uint32_t* __restrict__ sorted_keys, uint32_t npart,
+                                     uint32_t ncells, uint32_t* n_alive) {
+    uint32_t lo = 0, hi = npart;
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (sorted_keys[mid] < ncells) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
     }
+    *n_alive = lo;
   }
 
   template <class T>
@@ -62,6 +72,40 @@ namespace eb200 {
     cudaMemcpyAsync(arr, tmp, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st);
   }
 
+  // up to four 4-byte arrays through the same permutation: the index is read once
+  struct Quad {
+    uint32_t* p[4];
+  };
+
+  __global__ void __launch_bounds__(256)
+    gather4_kernel(Quad src, Quad dst, int na, const uint32_t* __restrict__ perm, uint32_t n) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) {
+      const uint32_t s = perm[q];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (a < na) dst.p[a][q] = src.p[a][s];
+      }
+    }
+  }
+
+  static void permute_words(uint32_t* const* arrs, int na, const uint32_t* perm, uint32_t n,
+                            char* tmp, size_t stride, cudaStream_t st) {
+    for (int a0 = 0; a0 < na; a0 += 4) {
+      const int m = (na - a0 < 4) ? (na - a0) : 4;
+      Quad      src {}, dst {};
+      for (int a = 0; a < m; ++a) {
+        src.p[a] = arrs[a0 + a];
+        dst.p[a] = (uint32_t*)(tmp + (size_t)a * stride);
+      }
+      gather4_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, m, perm, n);
+      count_launch();
+      for (int a = 0; a < m; ++a) {
+        cudaMemcpyAsync(src.p[a], dst.p[a], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+      }
+    }
+  }
+
   cudaError_t sort_particles(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
                              uint32_t maxnpart, int remove_dead, uint32_t* n_alive_out,
                              Scratch& scratch, cudaStream_t st) {
@@ -80,7 +124,7 @@ namespace eb200 {
                                     (uint32_t*)nullptr, (uint32_t*)nullptr, (size_t)npart, 0,
                                     bits, st);
     const size_t n4  = ((size_t)npart * 4 + 255) / 256 * 256;
-    cudaError_t  err = scratch.reserve(5 * n4 + tmp_bytes + 512);
+    cudaError_t  err = scratch.reserve(8 * n4 + tmp_bytes + 512);
     if (err != cudaSuccess) return err;
     char*     base  = (char*)scratch.ptr;
     uint32_t* k0    = (uint32_t*)(base);
@@ -88,20 +132,19 @@ namespace eb200 {
     uint32_t* i0    = (uint32_t*)(base + 2 * n4);
     uint32_t* perm  = (uint32_t*)(base + 3 * n4);
     void*     tmp   = (void*)(base + 4 * n4);
-    uint32_t* count = (uint32_t*)(base + 5 * n4);
-    void*     cubws = (void*)(base + 5 * n4 + 256);
+    uint32_t* count = (uint32_t*)(base + 8 * n4); // tmp holds four arrays: 4 * n4 .. 8 * n4
+    void*     cubws = (void*)(base + 8 * n4 + 256);
 
-    cudaMemsetAsync(count, 0, sizeof(uint32_t), st);
     const unsigned nb = (npart + 255) / 256;
     switch (g.dim) {
       case 1:
-        sort_keys_kernel<1><<<nb, 256, 0, st>>>(S, npart, n1, n2, n3, ncells, k0, i0, count);
+        sort_keys_kernel<1><<<nb, 256, 0, st>>>(S, npart, n1, n2, n3, ncells, k0, i0);
         break;
       case 2:
-        sort_keys_kernel<2><<<nb, 256, 0, st>>>(S, npart, n1, n2, n3, ncells, k0, i0, count);
+        sort_keys_kernel<2><<<nb, 256, 0, st>>>(S, npart, n1, n2, n3, ncells, k0, i0);
         break;
       case 3:
-        sort_keys_kernel<3><<<nb, 256, 0, st>>>(S, npart, n1, n2, n3, ncells, k0, i0, count);
+        sort_keys_kernel<3><<<nb, 256, 0, st>>>(S, npart, n1, n2, n3, ncells, k0, i0);
         break;
       default: return cudaErrorInvalidValue;
     }
@@ -110,29 +153,25 @@ namespace eb200 {
                                           bits, st);
     if (err != cudaSuccess) return err;
     count_launch();
+    if (remove_dead && n_alive_out) {
+      count_alive_kernel<<<1, 1, 0, st>>>(k1, npart, ncells, count);
+      count_launch();
+    }
 
-    permute(S.i1, perm, npart, tmp, st);
-    permute(S.dx1, perm, npart, tmp, st);
-    permute(S.i1_prev, perm, npart, tmp, st);
-    permute(S.dx1_prev, perm, npart, tmp, st);
-    if (g.dim > 1) {
-      permute(S.i2, perm, npart, tmp, st);
-      permute(S.dx2, perm, npart, tmp, st);
-      permute(S.i2_prev, perm, npart, tmp, st);
-      permute(S.dx2_prev, perm, npart, tmp, st);
+    {
+      uint32_t* w[20];
+      int       nw = 0;
+      auto      add = [&](void* q) {
+        if (q) w[nw++] = (uint32_t*)q;
+      };
+      add(S.i1), add(S.dx1), add(S.i1_prev), add(S.dx1_prev);
+      if (g.dim > 1) add(S.i2), add(S.dx2), add(S.i2_prev), add(S.dx2_prev);
+      if (g.dim > 2) add(S.i3), add(S.dx3), add(S.i3_prev), add(S.dx3_prev);
+      add(S.ux1), add(S.ux2), add(S.ux3), add(S.weight);
+      add(S.phi);
+      permute_words(w, nw, perm, npart, (char*)tmp, n4, st);
     }
-    if (g.dim > 2) {
-      permute(S.i3, perm, npart, tmp, st);
-      permute(S.dx3, perm, npart, tmp, st);
-      permute(S.i3_prev, perm, npart, tmp, st);
-      permute(S.dx3_prev, perm, npart, tmp, st);
-    }
-    permute(S.ux1, perm, npart, tmp, st);
-    permute(S.ux2, perm, npart, tmp, st);
-    permute(S.ux3, perm, npart, tmp, st);
-    permute(S.weight, perm, npart, tmp, st);
     permute(S.tag, perm, npart, tmp, st);
-    if (S.phi) permute(S.phi, perm, npart, tmp, st);
 
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;

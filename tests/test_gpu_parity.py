@@ -297,3 +297,31 @@ def test_fused_kernels_wide_mesh(eb, orc_mod, which, strict, order_kind):
         scale = np.abs(j_ref).max()
         assert np.abs(host(d_j) - j_ref).max() <= 2e-4 * scale, f"kernel {which} step {step}"
     assert ctx.launch_count - launches0 >= 2
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("nfilter", [1, 2, 4, 5, 8, 9])
+@pytest.mark.parametrize("n_cells", [(150, 37), (64, 16), (5, 3)])
+def test_fused_filter_passes(eb, orc_mod, n_cells, nfilter, strict):
+    """The fused multi-pass filter (temporal blocking, doubly periodic 2D domains) against
+    nfilter x (copy, DigitalFilter_kernel, periodic ghost fill) of the oracle: the strict build
+    must give identical bits, ghosts included; the fast build within FMA-contraction tolerance.
+    Meshes: not a multiple of the tile, exactly one tile, and smaller than the halo (the
+    periodic image wraps more than once)."""
+    orc = orc_mod.oracle()
+    g = orc_mod.Grid.make(n_cells, 2)
+    ctx = eb.Context(n_cells, order=0, strict=strict)
+    bc = [orc_mod.FBC_PERIODIC] * 6
+    cur = random_fields(g, 3, 9)
+    orc.comm_fields(g, cur, 0, 3, bc)
+    d_cur, d_buff = dev(cur), dev(np.zeros_like(cur))
+    buff = np.zeros_like(cur)
+    for _ in range(nfilter):
+        buff[...] = cur
+        orc.filter_pass(g, cur, buff, bc)
+        orc.comm_fields(g, cur, 0, 3, bc)
+    ctx.filter(d_cur, d_buff, nfilter, bc)
+    if strict:
+        assert_values_equal(host(d_cur), cur, f"fused filter x{nfilter}")
+    else:
+        np.testing.assert_allclose(host(d_cur), cur, rtol=RTOL_FAST, atol=ATOL_FAST)
