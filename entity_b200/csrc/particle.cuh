@@ -655,7 +655,16 @@ namespace eb200 {
       dx      += static_cast<float>(dx < ZERO);
       P.d[a]   = dx;
     }
-    // particle boundaries, then the migration tag
+    // particle boundaries, then the migration tag. Nearly every particle stays inside the
+    // domain: one unsigned compare per axis skips the whole block for those.
+    bool inside = true;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      inside = inside && (static_cast<unsigned>(P.i[a]) < static_cast<unsigned>(A.ni[a]));
+    }
+    if (inside) {
+      return;
+    }
     int lin = 0, centre = 0;
 #pragma unroll
     for (int a = 0; a < D; ++a) {

@@ -93,3 +93,54 @@ def test_step_fast_tolerance(mods, fused, agg):
     en = float((e[sl].astype(np.float64) ** 2).sum())
     eno = float((eo[sl].astype(np.float64) ** 2).sum())
     assert abs(en - eno) <= 1e-3 * eno
+
+
+def _energies(em, grid, species):
+    """(field, particle) energy in code units: sum over active cells of (E^2 + B^2) / 2 and
+    sum over alive particles of w (gamma - 1), both accumulated in float64."""
+    g = grid
+    sl = (slice(None),) + tuple(slice(g.ng, g.ng + g.n[a]) for a in range(g.dim))[::-1]
+    fld = 0.5 * float((em[sl].astype(np.float64) ** 2).sum())
+    kin = 0.0
+    for ux, uy, uz, w, tag in species:
+        alive = tag == 1
+        u2 = (ux[alive].astype(np.float64) ** 2 + uy[alive].astype(np.float64) ** 2 +
+              uz[alive].astype(np.float64) ** 2)
+        kin += float((w[alive].astype(np.float64) * (np.sqrt(1.0 + u2) - 1.0)).sum())
+    return fld, kin
+
+
+@pytest.mark.parametrize("which", [0, 2])
+def test_total_energy_window(mods, which):
+    """north_star: 'fields, currents and total energy stay within a stated fp32 tolerance over a
+    fixed step window'. Production path (fast build, fused push+deposit, warp-aggregated deposit,
+    periodic re-sorting) on the reconnection workload, 20 steps, against the serial oracle on the
+    imported state. Stated tolerances: field energy 1e-3, particle kinetic energy 1e-5, total
+    energy 1e-4 (relative); particle counts identical at every step."""
+    eb, wl, orc, pic = mods
+    sim = wl.reconnection((128, 64), ppc0=8, nfilter=4, fused=True, sort_interval=5,
+                          deposit_mode=eb.DEPOSIT_AGGREGATED)
+    sim.ctx.set_pd_kernel(which)
+    osim = pic.from_device_sim(sim)
+
+    def dev_energy():
+        sp = [tuple(s.arrays[k][:s.npart].cpu().numpy() for k in ("ux1", "ux2", "ux3", "weight", "tag"))
+              for s in sim.species]
+        return _energies(sim.em.cpu().numpy(), osim.grid, sp)
+
+    def orc_energy():
+        sp = [tuple(getattr(s["prtls"], k)[:s["npart"]] for k in ("ux1", "ux2", "ux3", "weight", "tag"))
+              for s in osim.species]
+        return _energies(osim.em, osim.grid, sp)
+
+    f0, k0 = orc_energy()
+    for step in range(20):
+        sim.step()
+        osim.step()
+        assert sim.n_pushed() == osim.n_pushed(), f"particle count differs at step {step}"
+    (fd, kd), (fo, ko) = dev_energy(), orc_energy()
+    assert abs(fd - fo) <= 1e-3 * fo
+    assert abs(kd - ko) <= 1e-5 * ko
+    assert abs((fd + kd) - (fo + ko)) <= 1e-4 * (fo + ko)
+    # and the window did something: energy moved between fields and particles
+    assert abs(ko - k0) > 1e-6 * k0 or abs(fo - f0) > 1e-6 * f0
