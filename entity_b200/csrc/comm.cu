@@ -374,19 +374,43 @@ namespace eb200 {
 
   __device__ __forceinline__ int class_of(short tag) { return tag == 0 ? 0 : (int)tag - 1; }
 
+  // eight consecutive tags per thread: one 16-byte load where the array allows it. Nearly all
+  // tags are 1 (alive, staying): the packed compare skips them eight at a time.
+  constexpr int SPLIT_VEC = 8;
+
+  __device__ __forceinline__ void load_tags8(const short* __restrict__ tag, uint32_t p8, uint32_t hi,
+                                             bool aligned, short (&t)[SPLIT_VEC]) {
+    if (aligned && p8 + SPLIT_VEC <= hi) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(tag + p8));
+      const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t[2 * k]     = (short)(w[k] & 0xffffu);
+        t[2 * k + 1] = (short)(w[k] >> 16);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < SPLIT_VEC; ++k) t[k] = (p8 + k < hi) ? tag[p8 + k] : (short)1;
+    }
+  }
+
   __global__ void __launch_bounds__(SPLIT_THREADS)
     split_count_kernel(const short* __restrict__ tag, uint32_t npart, uint32_t per_block,
-                       int nclass, uint32_t* __restrict__ counts /* [nclass][gridDim.x] */) {
+                       int nclass, bool aligned, uint32_t* __restrict__ counts /* [nclass][gridDim.x] */) {
     __shared__ uint32_t hist[MAXTAG];
     if (threadIdx.x < MAXTAG) hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t lo = blockIdx.x * per_block;
     const uint32_t hi = min(npart, lo + per_block);
-    for (uint32_t p = lo + threadIdx.x; p < hi; p += SPLIT_THREADS) {
-      const short t = tag[p];
-      if (t != 1) {
-        const int c = class_of(t);
-        if (c >= 0 && c < nclass) atomicAdd(&hist[c], 1u);
+    for (uint32_t p8 = lo + threadIdx.x * SPLIT_VEC; p8 < hi; p8 += SPLIT_THREADS * SPLIT_VEC) {
+      short t[SPLIT_VEC];
+      load_tags8(tag, p8, hi, aligned, t);
+#pragma unroll
+      for (int k = 0; k < SPLIT_VEC; ++k) {
+        if (t[k] != 1) {
+          const int c = class_of(t[k]);
+          if (c >= 0 && c < nclass) atomicAdd(&hist[c], 1u);
+        }
       }
     }
     __syncthreads();
@@ -436,45 +460,60 @@ namespace eb200 {
 
   __global__ void __launch_bounds__(SPLIT_THREADS)
     split_scatter_kernel(const short* __restrict__ tag, uint32_t npart, uint32_t per_block,
-                         int nclass, const uint32_t* __restrict__ offsets /* scanned counts */,
+                         int nclass, bool aligned,
+                         const uint32_t* __restrict__ offsets /* scanned counts */,
                          uint32_t* __restrict__ out_idx) {
     __shared__ uint32_t cursor[MAXTAG];
     __shared__ uint32_t wcount[SPLIT_THREADS / 32][MAXTAG];
+    __shared__ short    stag[SPLIT_THREADS * SPLIT_VEC];
     if ((int)threadIdx.x < nclass) cursor[threadIdx.x] = offsets[threadIdx.x * gridDim.x + blockIdx.x];
     __syncthreads();
     const uint32_t lo   = blockIdx.x * per_block;
     const uint32_t hi   = min(npart, lo + per_block);
     const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (uint32_t base = lo; base < hi; base += SPLIT_THREADS) {
-      const uint32_t p = base + threadIdx.x;
-      int            c = -1;
-      if (p < hi) {
-        const short t = tag[p];
-        if (t != 1) {
-          c = class_of(t);
-          if (c < 0 || c >= nclass) c = -1;
+    for (uint32_t chunk = lo; chunk < hi; chunk += SPLIT_THREADS * SPLIT_VEC) {
+      // fast path: 2048 tags per block iteration, all alive -> one barrier and on
+      short t8[SPLIT_VEC];
+      load_tags8(tag, chunk + threadIdx.x * SPLIT_VEC, hi, aligned, t8);
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < SPLIT_VEC; ++k) any = any || (t8[k] != 1);
+      if (!__syncthreads_or(any)) continue;
+      // slow path: hand the tags round in index order, 256 at a time (the stable split)
+#pragma unroll
+      for (int k = 0; k < SPLIT_VEC; ++k) stag[threadIdx.x * SPLIT_VEC + k] = t8[k];
+      __syncthreads();
+      for (int r = 0; r < SPLIT_VEC; ++r) {
+        const uint32_t p = chunk + r * SPLIT_THREADS + threadIdx.x;
+        int            c = -1;
+        if (p < hi) {
+          const short t = stag[r * SPLIT_THREADS + threadIdx.x];
+          if (t != 1) {
+            c = class_of(t);
+            if (c < 0 || c >= nclass) c = -1;
+          }
         }
+        if (!__syncthreads_or(c >= 0)) continue;
+        // rank inside the warp among lanes of the same class
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        const unsigned below = peers & ((1u << lane) - 1u);
+        for (int k = lane; k < MAXTAG; k += 32) wcount[warp][k] = 0;
+        __syncwarp();
+        if (c >= 0 && below == 0) wcount[warp][c] = __popc(peers);
+        __syncthreads();
+        if (c >= 0) {
+          uint32_t before = 0;
+          for (int w = 0; w < warp; ++w) before += wcount[w][c];
+          out_idx[cursor[c] + before + __popc(below)] = p;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nclass) {
+          uint32_t tot = 0;
+          for (int w = 0; w < SPLIT_THREADS / 32; ++w) tot += wcount[w][threadIdx.x];
+          cursor[threadIdx.x] += tot;
+        }
+        __syncthreads();
       }
-      if (!__syncthreads_or(c >= 0)) continue;
-      // rank inside the warp among lanes of the same class
-      const unsigned peers = __match_any_sync(0xffffffffu, c);
-      const unsigned below = peers & ((1u << lane) - 1u);
-      for (int k = lane; k < MAXTAG; k += 32) wcount[warp][k] = 0;
-      __syncwarp();
-      if (c >= 0 && below == 0) wcount[warp][c] = __popc(peers);
-      __syncthreads();
-      if (c >= 0) {
-        uint32_t before = 0;
-        for (int w = 0; w < warp; ++w) before += wcount[w][c];
-        out_idx[cursor[c] + before + __popc(below)] = p;
-      }
-      __syncthreads();
-      if ((int)threadIdx.x < nclass) {
-        uint32_t tot = 0;
-        for (int w = 0; w < SPLIT_THREADS / 32; ++w) tot += wcount[w][threadIdx.x];
-        cursor[threadIdx.x] += tot;
-      }
-      __syncthreads();
     }
   }
 
@@ -832,7 +871,7 @@ namespace eb200 {
       if (d != ctr) dirs.push_back(d);
     }
     // ---- 1. classify: per species out_idx + class totals on the device
-    const int      nblk = 148 * 4;
+    const int      nblk = 148 * 16;
     size_t         work_bytes = 0;
     std::vector<size_t> off_idx(nspecies), off_cnt(nspecies), off_tot(nspecies);
     for (int s = 0; s < nspecies; ++s) {
@@ -860,11 +899,14 @@ namespace eb200 {
         CU(C, cudaMemsetAsync(tot, 0, sizeof(uint32_t) * (2 * MAXTAG + 2), st));
         continue;
       }
-      const uint32_t per_block = ((sp.npart + nblk - 1) / nblk + SPLIT_THREADS - 1) / SPLIT_THREADS * SPLIT_THREADS;
-      split_count_kernel<<<nblk, SPLIT_THREADS, 0, st>>>(sp.arrays.tag, sp.npart, per_block, nclass, cnt);
+      constexpr uint32_t CH = SPLIT_THREADS * SPLIT_VEC; // tags per block iteration
+      const uint32_t per_block = ((sp.npart + nblk - 1) / nblk + CH - 1) / CH * CH;
+      const bool     aligned   = (reinterpret_cast<uintptr_t>(sp.arrays.tag) & 15u) == 0;
+      split_count_kernel<<<nblk, SPLIT_THREADS, 0, st>>>(sp.arrays.tag, sp.npart, per_block, nclass,
+                                                         aligned, cnt);
       split_scan_kernel<<<1, 1024, 0, st>>>(cnt, nclass, nblk, tot, tot + MAXTAG);
-      split_scatter_kernel<<<nblk, SPLIT_THREADS, 0, st>>>(sp.arrays.tag, sp.npart, per_block, nclass, cnt,
-                                                           (uint32_t*)(W + off_idx[s]));
+      split_scatter_kernel<<<nblk, SPLIT_THREADS, 0, st>>>(sp.arrays.tag, sp.npart, per_block, nclass,
+                                                           aligned, cnt, (uint32_t*)(W + off_idx[s]));
       count_launch();
       count_launch();
       count_launch();

@@ -270,7 +270,7 @@ namespace eb200 {
       // CommunicateParticles (srpic.hpp:130-132): a single self-periodic domain has no
       // neighbour to migrate to; species without a pusher never carry a send tag
       if (eb200_ctx_has_comm(dom.ctx)) {
-        PHASE(dom, EB200_PHASE_COMM);
+        PHASE(dom, EB200_PHASE_MIGRATION);
         TRY(eb200_comm_particles(dom.ctx, dom.species, dom.nspecies, dom.stream));
       }
       if (p.fieldsolver_enabled) {

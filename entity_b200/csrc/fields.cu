@@ -580,15 +580,22 @@ namespace eb200 {
       return cudaGetLastError();
     }
 
+    // `extend` > 0: the pass also covers that many ghost layers (they must hold exchanged
+    // data `extend` + 1 deep). Lets two passes share one halo exchange: the ghost-layer values
+    // computed here are what the neighbour computes for its own edge cells.
     cudaError_t filter_pass(const eb200_grid_t& g, float* cur, const float* buff, const int* fbc,
-                            cudaStream_t st) {
-      const Box box = make_box(g);
+                            int extend, cudaStream_t st) {
+      Box box = make_box(g);
+      if (extend > 0) {
+        for (int a = 0; a < g.dim; ++a) box.n[a] += 2 * extend;
+        box.G -= extend;
+      }
       FilterBC  bc;
       for (int a = 0; a < 3; ++a) {
         bc.cmin[a] = (a < g.dim) && fbc[2 * a] == EB200_FBC_CONDUCTOR;
         bc.cmax[a] = (a < g.dim) && fbc[2 * a + 1] == EB200_FBC_CONDUCTOR;
       }
-      const long n = n_active(g);
+      const long n = (long)box.n[0] * box.n[1] * box.n[2];
 #define CALL(D)                                                                                \
   filter_kernel<D><<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, cur),                   \
                                                   FieldView<D>(g, const_cast<float*>(buff)), bc);

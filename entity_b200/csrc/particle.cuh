@@ -282,6 +282,17 @@ namespace eb200 {
     }
   }
 
+  // field-node load that asks L1 to keep the line (the particle stream does not allocate there)
+  __device__ __forceinline__ float ld_keep(const float* p) {
+#ifdef EB200_X_LDG
+    return __ldg(p);
+#else
+    float v;
+    asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#endif
+  }
+
   // Zig-zag (O = 0) gather straight from a FieldView: one 32-bit element index per particle,
   // the primal/dual choice is an element offset, the 2^D nodes of a component are immediate or
   // row-stride offsets from one pointer. Same weights and summation order as gather_fields().
@@ -312,12 +323,12 @@ namespace eb200 {
       const float* wx = sx ? wd[0] : wp[0];
       const float* q  = bc + o;
       if constexpr (D == 1) {
-        return __ldg(q) * wx[0] + __ldg(q + 1) * wx[1];
+        return ld_keep(q) * wx[0] + ld_keep(q + 1) * wx[1];
       } else if constexpr (D == 2) {
         const float* wy  = wy_dual ? wd[1] : wp[1];
         const float* r   = bc + (o + st[1]);
-        const float  c00 = __ldg(q) * wx[0] + __ldg(q + 1) * wx[1];
-        const float  c10 = __ldg(r) * wx[0] + __ldg(r + 1) * wx[1];
+        const float  c00 = ld_keep(q) * wx[0] + ld_keep(q + 1) * wx[1];
+        const float  c10 = ld_keep(r) * wx[0] + ld_keep(r + 1) * wx[1];
         return c00 * wy[0] + c10 * wy[1];
       } else {
         const float* wy  = wy_dual ? wd[1] : wp[1];
@@ -325,11 +336,11 @@ namespace eb200 {
         const float* r   = bc + (o + st[1]);
         const float* q2  = bc + (o + st[2]);
         const float* r2  = bc + (o + st[1] + st[2]);
-        const float  c00 = __ldg(q) * wx[0] + __ldg(q + 1) * wx[1];
-        const float  c10 = __ldg(r) * wx[0] + __ldg(r + 1) * wx[1];
+        const float  c00 = ld_keep(q) * wx[0] + ld_keep(q + 1) * wx[1];
+        const float  c10 = ld_keep(r) * wx[0] + ld_keep(r + 1) * wx[1];
         const float  c0  = c00 * wy[0] + c10 * wy[1];
-        const float  c01 = __ldg(q2) * wx[0] + __ldg(q2 + 1) * wx[1];
-        const float  c11 = __ldg(r2) * wx[0] + __ldg(r2 + 1) * wx[1];
+        const float  c01 = ld_keep(q2) * wx[0] + ld_keep(q2 + 1) * wx[1];
+        const float  c11 = ld_keep(r2) * wx[0] + ld_keep(r2 + 1) * wx[1];
         const float  c1  = c01 * wy[0] + c11 * wy[1];
         return c0 * wz[0] + c1 * wz[1];
       }
@@ -601,7 +612,9 @@ namespace eb200 {
   }
 
   template <int D, int O, class EM, bool LEAN = false>
-  __device__ __forceinline__ void push_particle(const PushArgs& A, const EM& F, Prtl<D>& P) {
+  // returns true when the particle left [0, ni) along some axis, i.e. when the boundary block
+  // ran (only then can tag, i_prev or u have been touched by a boundary condition)
+  __device__ __forceinline__ bool push_particle(const PushArgs& A, const EM& F, Prtl<D>& P) {
     const eb200_pusher_t& c  = A.c;
     const float           dt = c.dt;
     bool                  massive = true;
@@ -663,7 +676,7 @@ namespace eb200 {
       inside = inside && (static_cast<unsigned>(P.i[a]) < static_cast<unsigned>(A.ni[a]));
     }
     if (inside) {
-      return;
+      return false;
     }
     int lin = 0, centre = 0;
 #pragma unroll
@@ -706,6 +719,7 @@ namespace eb200 {
       // mpi::SendTag: 2 + lexicographic index of the direction, null direction skipped
       P.tag = static_cast<short>((2 + lin - (lin > centre ? 1 : 0)) * P.tag);
     }
+    return true;
   }
 
   /* ------------------------------------------------------------------ deposit */

@@ -415,9 +415,26 @@ namespace eb200 {
     // the warp's segmented shuffle reduction once per FOUR particles.
     constexpr int VEC = 4;
 
+    // streaming 128-bit load that does not allocate in L1 (the field nodes live there)
+    __device__ __forceinline__ int4 ld_stream(const int4* p) {
+      int4 t;
+      asm volatile("ld.global.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+                   : "l"(p));
+      return t;
+    }
+    __device__ __forceinline__ float4 ld_stream(const float4* p) {
+      float4 t;
+      asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                   : "l"(p));
+      return t;
+    }
+    __device__ __forceinline__ short4 ld_stream(const short4* p) { return __ldcs(p); }
+
     template <class T4, class T>
     __device__ __forceinline__ void ld4(const T* p, T (&v)[VEC]) {
-      const T4 t = __ldcs(reinterpret_cast<const T4*>(p));
+      const T4 t = ld_stream(reinterpret_cast<const T4*>(p));
       v[0]       = t.x;
       v[1]       = t.y;
       v[2]       = t.z;

@@ -13,7 +13,8 @@ PBC_NONE, PBC_PERIODIC, PBC_ABSORB, PBC_REFLECT, PBC_AXIS = 0, 1, 2, 3, 4
 FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC = 0, 1, 2, 3, 4
 DEPOSIT_ATOMIC, DEPOSIT_ORDERED, DEPOSIT_AGGREGATED = 0, 1, 2
 
-PHASES = ["FieldSolver", "PushDeposit", "CurrentFiltering", "Communications", "ParticleSort"]
+PHASES = ["FieldSolver", "PushDeposit", "CurrentFiltering", "Communications", "ParticleSort",
+          "ParticleMigration"]
 
 PRTL_FIELDS = ["i1", "i2", "i3", "dx1", "dx2", "dx3", "ux1", "ux2", "ux3", "weight",
                "i1_prev", "i2_prev", "i3_prev", "dx1_prev", "dx2_prev", "dx3_prev",

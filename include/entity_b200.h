@@ -309,9 +309,10 @@ enum {
   EB200_PHASE_FIELDSOLVER = 0, /* Faraday x2 + Ampere + CurrentsAmpere */
   EB200_PHASE_PUSH_DEPOSIT = 1, /* ParticlePusher + CurrentDeposit (incl. zeroing J) */
   EB200_PHASE_FILTER = 2,       /* CurrentFiltering */
-  EB200_PHASE_COMM = 3,         /* Communications (ghost fill, J sync, migration) */
+  EB200_PHASE_COMM = 3,         /* Communications: field ghost fill, J sync */
   EB200_PHASE_SORT = 4,         /* ParticleSort */
-  EB200_NPHASES = 5
+  EB200_PHASE_MIGRATION = 5,    /* Communications: particle migration (multi-domain only) */
+  EB200_NPHASES = 6
 };
 int eb200_profile_enable(eb200_ctx_t* ctx, int on);
 /* synchronises the recorded events; ms_host[EB200_NPHASES], calls_host[EB200_NPHASES]
