@@ -243,6 +243,8 @@ def run_ours(args):
         from entity_b200 import lib as L
         from entity_b200.metadomain import Metadomain, bootstrap_unique_id
         dec = [-1, 2] if world % 2 == 0 else [-1, 1]
+        if args.decomp:
+            dec = list(args.decomp)
         nd = [len(e) for e in L.decompose(world, [size[0] * world, size[1] * world], dec)]
         mdm = Metadomain((size[0] * nd[0], size[1] * nd[1]), world, rank, dec)
         assert mdm.local_n == size
@@ -379,6 +381,8 @@ def main():
     ap.add_argument("--sort-interval", type=int, default=40)
     ap.add_argument("--deposit", default="aggregated", choices=["atomic", "aggregated", "ordered"])
     ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--decomp", type=int, nargs=2, default=None,
+                    help="override the block decomposition request (default -1 2, as reconnection.toml)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")

@@ -32,6 +32,9 @@
 #include <nccl.h> // types only; the library is resolved at run time (no link dependency)
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -752,8 +755,8 @@ namespace eb200 {
     snd.total      = spos;
     rcv_flat.total = rpos;
     if (spos == 0 && rpos == 0) return EB200_OK;
-    CU(C, C.sendbuf.reserve((size_t)std::max(spos, 1L) * sizeof(float)));
-    CU(C, C.recvbuf.reserve((size_t)std::max(rpos, 1L) * sizeof(float)));
+    CU(C, C.sendbuf.reserve_grow((size_t)std::max(spos, 1L) * sizeof(float)));
+    CU(C, C.recvbuf.reserve_grow((size_t)std::max(rpos, 1L) * sizeof(float)));
     auto nblocks = [](long n) { return (unsigned)std::min<long>((n + 255) / 256, 148L * 16); };
     if (spos > 0) {
       switch (g.dim) {
@@ -855,6 +858,31 @@ namespace eb200 {
     return halo_round(C, cur, 0, 3, true, st);
   }
 
+  // EB200_COMM_TRACE=1: stage times of the migration (stream-synchronised; diagnosis only)
+  struct MigTrace {
+    bool         on;
+    cudaStream_t st;
+    int          rank;
+    double       t[8];
+    int          k = 0;
+    std::chrono::steady_clock::time_point last;
+    MigTrace(cudaStream_t s, int r) : st(s), rank(r) {
+      static const bool env = getenv("EB200_COMM_TRACE") != nullptr;
+      on = env;
+      if (on) {
+        cudaStreamSynchronize(st);
+        last = std::chrono::steady_clock::now();
+      }
+    }
+    void mark() {
+      if (!on || k >= 8) return;
+      cudaStreamSynchronize(st);
+      const auto now = std::chrono::steady_clock::now();
+      t[k++] = std::chrono::duration<double, std::milli>(now - last).count();
+      last   = now;
+    }
+  };
+
   // Particles::Communicate for every species in one round
   int comm_particles(Comm& C, eb200_species_t* species, int nspecies, cudaStream_t st) {
     const Metadomain& M   = C.M;
@@ -863,6 +891,7 @@ namespace eb200 {
     const int         nclass = M.ndir; // dead + (ndir - 1) send tags
     if (nspecies <= 0) return EB200_OK;
     if (nspecies * (2 * MAXTAG + 2) > 4096) return fail(C, EB200_ERR_ARG, "too many species");
+    MigTrace trace(st, M.rank);
     // directions in which particles travel: enabled and the particle boundary lets them out
     // (a periodic single-domain dimension wraps inside the pusher and never tags)
     auto tag_of = [&](int d) { return 2 + d - (d > ctr ? 1 : 0); };
@@ -881,10 +910,14 @@ namespace eb200 {
       work_bytes += sizeof(uint32_t) * (2 * MAXTAG + 2);
       work_bytes  = (work_bytes + 255) / 256 * 256;
     }
-    // out_idx can hold every particle in the worst case; bound it by npart
+    // out_idx can hold every particle in the worst case: sized by the species' capacity, which
+    // does not change from step to step (npart does: sizing by it reallocated ~1 GB whenever a
+    // domain gained a particle, 16 ms per occurrence on the 3.3e8-particle block)
     for (int s = 0; s < nspecies; ++s) {
       off_idx[s]  = work_bytes;
-      work_bytes += sizeof(uint32_t) * (size_t)std::max<uint32_t>(species[s].npart, 1);
+      const uint32_t np  = species[s].npart;
+      const uint32_t cap = std::max<uint32_t>(species[s].maxnpart >= np ? species[s].maxnpart : np + np / 8, 1);
+      work_bytes += sizeof(uint32_t) * (size_t)cap;
       work_bytes  = (work_bytes + 255) / 256 * 256;
     }
     const size_t off_sendcnt = work_bytes; // counts to peers / from peers (uint32)
@@ -911,6 +944,7 @@ namespace eb200 {
       count_launch();
       count_launch();
     }
+    trace.mark(); // classify
     // ---- 2. counts to the peers (device to device), then one read-back
     // message to peer p: for s, for d ascending with neighbour(d) == p: total of class tag(d)-1
     uint32_t* d_sendcnt = (uint32_t*)(W + off_sendcnt);
@@ -942,8 +976,8 @@ namespace eb200 {
         rcnt[k] = rpos - roff[k];
       }
       // gather the class totals into the count message with tiny D2D copies
-      CU(C, C.sendbuf.reserve(std::max<size_t>((size_t)spos * 4, 256)));
-      CU(C, C.recvbuf.reserve(std::max<size_t>((size_t)rpos * 4, 256)));
+      CU(C, C.sendbuf.reserve_grow(std::max<size_t>((size_t)spos * 4, 256)));
+      CU(C, C.recvbuf.reserve_grow(std::max<size_t>((size_t)rpos * 4, 256)));
       long pos = 0;
       for (size_t k = 0; k < C.peers.size(); ++k) {
         for (const Slot& sl : sslots[k]) {
@@ -969,6 +1003,7 @@ namespace eb200 {
       (void)d_sendcnt;
       (void)d_recvcnt;
     }
+    trace.mark(); // counts
     const uint32_t* hbase = C.pinned;
     const uint32_t* hrecv = C.pinned + (size_t)nspecies * (MAXTAG + 1);
     // ---- 3. plans
@@ -1045,8 +1080,8 @@ namespace eb200 {
           return fail(C, EB200_ERR_CAPACITY, "Too many particles to receive (cannot fit into maxptl)");
         }
       }
-      CU(C, C.sendbuf.reserve(std::max<size_t>((size_t)spos * 4, 256)));
-      CU(C, C.recvbuf.reserve(std::max<size_t>((size_t)rpos * 4, 256)));
+      CU(C, C.sendbuf.reserve_grow(std::max<size_t>((size_t)spos * 4, 256)));
+      CU(C, C.recvbuf.reserve_grow(std::max<size_t>((size_t)rpos * 4, 256)));
     }
     // ---- 4. pack, exchange, unpack
     for (int s = 0; s < nspecies; ++s) {
@@ -1063,8 +1098,10 @@ namespace eb200 {
       }
       count_launch();
     }
+    trace.mark(); // pack
     int rc = exchange(C, soff, scnt, roff, rcnt, 4, st);
     if (rc != EB200_OK) return rc;
+    trace.mark(); // exchange
     for (int s = 0; s < nspecies; ++s) {
       eb200_species_t& sp = species[s];
       if (nrecv[s] == 0) continue;
@@ -1080,6 +1117,19 @@ namespace eb200 {
       if (nrecv[s] > nholes[s]) sp.npart += nrecv[s] - nholes[s]; // particles_comm.cpp:384-387
     }
     CU(C, cudaGetLastError());
+    if (trace.on) {
+      trace.mark(); // unpack
+      static int calls = 0;
+      if (++calls % 10 == 0) {
+        fprintf(stderr, "[migrate r%d #%d] classify %.3f counts %.3f pack %.3f exchange %.3f unpack %.3f ms;",
+                M.rank, calls, trace.t[0], trace.t[1], trace.t[2], trace.t[3], trace.t[4]);
+        for (int s = 0; s < nspecies; ++s) {
+          fprintf(stderr, " s%d: dead %u out %u recv %u npart %u", s, splan[s].class_base[1],
+                  nholes[s] - splan[s].class_base[1], nrecv[s], species[s].npart);
+        }
+        fprintf(stderr, "\n");
+      }
+    }
     return EB200_OK;
   }
 

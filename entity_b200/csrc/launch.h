@@ -27,6 +27,21 @@ namespace eb200 {
       return e;
     }
 
+    // for buffers whose size follows the data (particle counts): grow with headroom so that a
+    // slowly rising count does not free and reallocate every step (each cudaFree is a device
+    // synchronisation, and with peer mappings it costs milliseconds)
+    cudaError_t reserve_grow(size_t n, size_t floor_bytes = size_t(1) << 20) {
+      if (n <= bytes) return cudaSuccess;
+      size_t want = n + n / 2;
+      if (want < floor_bytes) want = floor_bytes;
+      cudaError_t e = reserve(want);
+      if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        e = reserve(n);
+      }
+      return e;
+    }
+
     void release() {
       if (ptr) cudaFree(ptr);
       ptr   = nullptr;
