@@ -384,7 +384,7 @@ def main():
     ap.add_argument("--decomp", type=int, nargs=2, default=None,
                     help="override the block decomposition request (default -1 2, as reconnection.toml)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()

@@ -5,7 +5,9 @@
 // the C ABI instead of Kokkos::parallel_for. No arithmetic on field or particle data happens here.
 #include "launch.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -36,6 +38,38 @@ namespace eb200 {
   struct HostMirror {
     std::vector<void*>  ptrs;
     std::vector<size_t> sizes;
+    // streamed host step: copy streams (non-blocking) and a pool of timing-free events
+    cudaStream_t             main = nullptr, up = nullptr, down = nullptr;
+    std::vector<cudaEvent_t> events;
+    size_t                   next_event = 0;
+
+    bool streams() {
+      if (main) return true;
+      if (cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking) != cudaSuccess) return false;
+      if (cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking) != cudaSuccess) return false;
+      if (cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking) != cudaSuccess) return false;
+      return true;
+    }
+    cudaEvent_t event() {
+      if (next_event == events.size()) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        events.push_back(e);
+      }
+      return events[next_event++];
+    }
+  };
+
+  // One step over HOST particle arrays, streamed: while the fused push+deposit works on chunk k
+  // of a species, chunk k+1 is on its way up and chunk k-1 on its way down (PCIe is full
+  // duplex). Only what the step reads goes up (tag, i, dx, u, weight: i_prev/dx_prev are
+  // overwritten by the pusher before anything reads them, sr.hpp:137-153) and only what it
+  // writes comes down (i, dx, u, i_prev, dx_prev, tag: weight is not modified).
+  struct HostStreamer {
+    HostMirror*      m;
+    eb200_species_t* host; // host pointers, same order as the device species of the Domain
+    size_t           chunk;
+    uint64_t         up_bytes = 0, down_bytes = 0;
   };
 
   struct EngineState {
@@ -82,6 +116,7 @@ namespace eb200 {
       int                         nspecies;
       eb200_stream_t              stream;
       Profiler*                   prof;
+      HostStreamer*               host = nullptr; // non-null: particle arrays stream from/to the host
     };
 
 #define PHASE(dom, which) PhaseScope phase_scope_((dom).prof, (which), (cudaStream_t)(dom).stream)
@@ -192,8 +227,62 @@ namespace eb200 {
 
     // ParticlePush + CurrentsDeposit in one pass per species (same result up to the order of
     // the additions into J)
+    // ParticleArrays slots (eb200_prtls_t order) the SR step reads / writes
+    static const int    kSlotsIn[]   = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16 };
+    static const int    kSlotsOut[]  = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16 };
+    static const size_t kSlotElem[17] = { 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 2 };
+
+    static int StreamedPushAndDeposit(Domain& dom, double time) {
+      HostStreamer& H  = *dom.host;
+      cudaStream_t  st = (cudaStream_t)dom.stream;
+      const int     mode = dom.prm->deposit_mode == EB200_DEPOSIT_AGGREGATED ? EB200_DEPOSIT_AGGREGATED
+                                                                             : EB200_DEPOSIT_ATOMIC;
+      for (int s = 0; s < dom.nspecies; ++s) {
+        eb200_species_t& sp = dom.species[s];
+        if (sp.pusher_flags == EB200_PUSHER_NONE || sp.npart == 0) continue;
+        const eb200_pusher_t c  = pusher_context(dom, sp, time);
+        void**               hp = (void**)&H.host[s].arrays;
+        void**               dp = (void**)&sp.arrays;
+        for (size_t lo = 0; lo < sp.npart; lo += H.chunk) {
+          const size_t n = std::min<size_t>(H.chunk, sp.npart - lo);
+          for (int k : kSlotsIn) {
+            if (!hp[k]) continue;
+            const size_t e = kSlotElem[k];
+            if (cudaMemcpyAsync((char*)dp[k] + lo * e, (const char*)hp[k] + lo * e, n * e,
+                                cudaMemcpyHostToDevice, H.m->up) != cudaSuccess) return EB200_ERR_CUDA;
+            H.up_bytes += n * e;
+          }
+          cudaEvent_t arrived = H.m->event();
+          cudaEventRecord(arrived, H.m->up);
+          cudaStreamWaitEvent(st, arrived, 0);
+          eb200_prtls_t part = sp.arrays;
+          void**        pp   = (void**)&part;
+          for (int k = 0; k < 17; ++k) {
+            if (pp[k]) pp[k] = (char*)pp[k] + lo * kSlotElem[k];
+          }
+          if (almost_zero(sp.charge)) {
+            TRY(eb200_push_sr(dom.ctx, &c, &part, (uint32_t)n, dom.em, dom.stream));
+          } else {
+            TRY(eb200_push_deposit_sr(dom.ctx, &c, &part, (uint32_t)n, dom.em, dom.cur, mode, dom.stream));
+          }
+          cudaEvent_t pushed = H.m->event();
+          cudaEventRecord(pushed, st);
+          cudaStreamWaitEvent(H.m->down, pushed, 0);
+          for (int k : kSlotsOut) {
+            if (!hp[k]) continue;
+            const size_t e = kSlotElem[k];
+            if (cudaMemcpyAsync((char*)hp[k] + lo * e, (const char*)dp[k] + lo * e, n * e,
+                                cudaMemcpyDeviceToHost, H.m->down) != cudaSuccess) return EB200_ERR_CUDA;
+            H.down_bytes += n * e;
+          }
+        }
+      }
+      return EB200_OK;
+    }
+
     int ParticlePushAndDeposit(Domain& dom, double time) {
       TRY(eb200_zero_currents(dom.ctx, dom.cur, dom.stream));
+      if (dom.host) return StreamedPushAndDeposit(dom, time);
       for (int s = 0; s < dom.nspecies; ++s) {
         eb200_species_t& sp = dom.species[s];
         if (sp.pusher_flags == EB200_PUSHER_NONE || sp.npart == 0) continue;
@@ -413,6 +502,59 @@ extern "C" int eb200_srpic_step_host(eb200_ctx_t* ctx, const eb200_srpic_params_
   float*       d_cur  = (float*)mirror_get(m, 1, b3);
   float*       d_buff = (float*)mirror_get(m, 2, b3);
   if (!d_em || !d_cur || !d_buff) return EB200_ERR_CUDA;
+  // Streamed variant: the fused Minkowski step of a single domain, on steps that neither sort
+  // nor compact (those permute every array, weight included: they take the plain path below)
+  {
+    const int  ci = prm->clear_interval, si = prm->sort_interval;
+    const bool reorders = ((ci > 0) && (step % (uint32_t)ci == 0u) && (step > 0u)) ||
+                          ((si > 0) && (step % (uint32_t)si == 0u));
+    static const bool disabled = getenv("EB200_HOST_STEP_PLAIN") != nullptr;
+    if (!disabled && !reorders && prm->fuse_push_deposit && prm->deposit_enabled &&
+        !eb200_ctx_has_comm(ctx) && m.streams()) {
+      m.next_event = 0;
+      std::vector<eb200_species_t> dev(species_host, species_host + nspecies);
+      for (int s = 0; s < nspecies; ++s) {
+        void** hp = (void**)&species_host[s].arrays;
+        void** dp = (void**)&dev[s].arrays;
+        for (int k = 0; k < 20; ++k) dp[k] = nullptr;
+        for (int k = 0; k < 17; ++k) {
+          if (!hp[k]) continue;
+          dp[k] = mirror_get(m, 3 + (size_t)s * 17 + k, (size_t)species_host[s].maxnpart * eb200::srpic::kSlotElem[k]);
+          if (!dp[k]) return EB200_ERR_CUDA;
+        }
+      }
+      eb200::HostStreamer H { &m, species_host, size_t(8) << 20 };
+      if (const char* e = getenv("EB200_HOST_CHUNK")) H.chunk = std::max<size_t>(1024, (size_t)atol(e) / 1024 * 1024);
+      cudaMemcpyAsync(d_em, em_host, b6, cudaMemcpyHostToDevice, m.main);
+      up += b6; // J is zeroed by the deposit before anything reads it: not uploaded
+      eb200::srpic::Domain dom;
+      dom.ctx = ctx;
+      dom.prm = prm;
+      if (eb200_ctx_grid(ctx, &dom.grid, &dom.dx, dom.xmin) != EB200_OK) return EB200_ERR_ARG;
+      dom.em       = d_em;
+      dom.cur      = d_cur;
+      dom.buff     = d_buff;
+      dom.species  = dev.data();
+      dom.nspecies = nspecies;
+      dom.stream   = m.main;
+      dom.prof     = &eb200_ctx_engine_state(ctx)->prof;
+      dom.host     = &H;
+      int rc = eb200::srpic::step_forward(dom, step, time);
+      if (rc == EB200_OK) {
+        cudaMemcpyAsync(em_host, d_em, b6, cudaMemcpyDeviceToHost, m.main);
+        cudaMemcpyAsync(cur_host, d_cur, b3, cudaMemcpyDeviceToHost, m.main);
+        down += b6 + b3;
+      }
+      cudaError_t e1 = cudaStreamSynchronize(m.up), e2 = cudaStreamSynchronize(m.main),
+                  e3 = cudaStreamSynchronize(m.down);
+      if (rc != EB200_OK) return rc;
+      if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return EB200_ERR_CUDA;
+      for (int s = 0; s < nspecies; ++s) species_host[s].npart = dev[s].npart;
+      if (bytes_h2d) *bytes_h2d = up + H.up_bytes;
+      if (bytes_d2h) *bytes_d2h = down + H.down_bytes;
+      return EB200_OK;
+    }
+  }
   cudaMemcpyAsync(d_em, em_host, b6, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_cur, cur_host, b3, cudaMemcpyHostToDevice, st);
   up += b6 + b3;

@@ -144,3 +144,47 @@ def test_total_energy_window(mods, which):
     assert abs((fd + kd) - (fo + ko)) <= 1e-4 * (fo + ko)
     # and the window did something: energy moved between fields and particles
     assert abs(ko - k0) > 1e-6 * k0 or abs(fo - f0) > 1e-6 * f0
+
+
+@pytest.mark.parametrize("chunk", ["1024", None])
+def test_step_host_streamed_matches_device(mods, chunk, monkeypatch):
+    """eb200_srpic_step_host (host buffers; particle chunks streamed up / pushed / streamed down
+    on three streams, plain whole-array path on sort steps) against eb200_srpic_step on device
+    arrays from the same state. The pusher is independent of the deposit order, so the first
+    step's particles are bit-identical; J differs by the order of fp32 atomic additions (5e-4
+    of max|J|), which feeds back into later steps (fp32 tolerance there)."""
+    eb, wl, orc, pic = mods
+    if chunk:
+        monkeypatch.setenv("EB200_HOST_CHUNK", chunk)
+    else:
+        monkeypatch.delenv("EB200_HOST_CHUNK", raising=False)
+    sim = wl.reconnection((64, 64), ppc0=8, nfilter=3, strict=True, fused=True, sort_interval=3,
+                          deposit_mode=eb.DEPOSIT_AGGREGATED)
+    hs = sim.host_state()
+    # poison what the streamed path promises not to read: stale i_prev / dx_prev on the host
+    for spec in hs["species"]:
+        for nm in ("i1_prev", "i2_prev", "dx1_prev", "dx2_prev"):
+            spec[nm].fill_(7)
+    names = ["i1", "i2", "dx1", "dx2", "ux1", "ux2", "ux3", "weight", "i1_prev", "i2_prev",
+             "dx1_prev", "dx2_prev", "tag"]
+    for step in range(6):
+        sim.step()
+        up, down = sim.step_host(hs)
+        assert up > 0 and down > 0
+        j, jh = sim.cur.cpu().numpy(), hs["cur"].numpy()
+        assert np.abs(j - jh).max() <= 5e-4 * np.abs(j).max(), f"J at step {step}"
+        e, eh = sim.em.cpu().numpy(), hs["em"].numpy()
+        assert np.abs(e - eh).max() <= 1e-4 * np.abs(e).max(), f"EM at step {step}"
+        for sp, spec, c in zip(sim.species, hs["species"], hs["c"]):
+            assert sp.npart == c.npart
+            n = sp.npart
+            if step == 0:
+                for nm in names:
+                    a, b = sp.arrays[nm][:n].cpu().numpy(), spec[nm][:n].numpy()
+                    assert np.array_equal(a, b), f"{nm}: {(a != b).sum()} of {n} differ"
+    # after the window (two sort steps inside): same multiset of particles within fp32 tolerance
+    for sp, spec in zip(sim.species, hs["species"]):
+        n = sp.npart
+        assert np.array_equal(np.sort(sp.arrays["weight"][:n].cpu().numpy()), np.sort(spec["weight"][:n].numpy()))
+        ua, ub = sp.arrays["ux1"][:n].cpu().numpy(), spec["ux1"][:n].numpy()
+        assert abs(float(ua.astype(np.float64).sum()) - float(ub.astype(np.float64).sum())) <= 1e-3 * np.abs(ua).sum()
