@@ -45,6 +45,8 @@ struct eb200_ctx {
   std::string    err;
   uint64_t       launches_at_init;
   int            pd_kernel = 0; // eb200_set_pd_kernel
+  eb200::Scratch packed;        // E/B repacked node by node for the fused 2D zig-zag kernel
+  const float*   packed_hold = nullptr; // em the packed copy is guaranteed current for
   bool           no_filter_fusion = false; // EB200_NO_FILTER_FUSION=1: pass-by-pass filter
   eb200::MetricParams metric {}; // curvilinear / GR contexts
 };
@@ -226,6 +228,7 @@ void eb200_finalize(eb200_ctx_t* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   ctx->scratch.release();
+  ctx->packed.release();
   if (ctx->comm) eb200::comm_delete(ctx->comm);
   eb200::engine_state_delete(ctx->engine);
   delete ctx;
@@ -454,6 +457,17 @@ int eb200_deposit(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, 
                     "deposit");
 }
 
+// the fused 2D zig-zag kernel that gathers from packed nodes (kernel 5)
+static bool uses_packed_nodes(const eb200_ctx* ctx, int mode) {
+  return (ctx->pd_kernel == 5 || ctx->pd_kernel == 6 || ctx->pd_kernel == 0) && ctx->cfg.metric == EB200_METRIC_MINKOWSKI && ctx->cfg.grid.dim == 2 &&
+         ctx->cfg.shape_order == 0 && mode == EB200_DEPOSIT_AGGREGATED;
+}
+
+static size_t packed_bytes(const eb200_ctx* ctx) {
+  const eb200_grid_t& g = ctx->cfg.grid;
+  return (size_t)(g.n[0] + 2 * g.ng) * (size_t)(g.n[1] + 2 * g.ng) * 24;
+}
+
 int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
                           const eb200_prtls_t* prtls, uint32_t npart, const float* em, float* cur,
                           int mode, eb200_stream_t stream) {
@@ -466,12 +480,40 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
   rc = check_prtls(ctx, prtls, npart);
   if (rc) return rc;
   REQUIRE(ctx, em != nullptr && cur != nullptr, "null field");
+  float* packed  = nullptr;
+  bool   do_pack = false;
+  if (uses_packed_nodes(ctx, mode)) {
+    // the packed copy is rebuilt on every call unless the engine holds it for this em
+    // (eb200_pack_fields_hold: nothing touches em between the species of one step)
+    if (check_cuda(ctx, ctx->packed.reserve(packed_bytes(ctx)), "packed E/B") == EB200_OK) {
+      packed  = (float*)ctx->packed.ptr;
+      do_pack = ctx->packed_hold != em;
+    }
+  }
   return check_cuda(ctx,
                     VARIANT_CALL(ctx, push_deposit_sr(ctx->cfg.grid, ctx->cfg.shape_order,
                                                       *pusher, *prtls, npart, em, cur,
-                                                      mode | (ctx->pd_kernel << 8),
-                                                      (cudaStream_t)stream)),
+                                                      mode | (ctx->pd_kernel << 8), packed,
+                                                      do_pack, (cudaStream_t)stream)),
                     "push_deposit_sr");
+}
+
+int eb200_pack_fields_hold(eb200_ctx_t* ctx, const float* em, eb200_stream_t stream) {
+  ENTER(ctx);
+  ctx->packed_hold = nullptr;
+  if (em == nullptr || !uses_packed_nodes(ctx, EB200_DEPOSIT_AGGREGATED)) return EB200_OK;
+  int rc = check_cuda(ctx, ctx->packed.reserve(packed_bytes(ctx)), "packed E/B");
+  if (rc) return rc;
+  rc = check_cuda(ctx, VARIANT_CALL(ctx, pack_em2d(ctx->cfg.grid, em, (float*)ctx->packed.ptr,
+                                                   (cudaStream_t)stream)), "pack_em2d");
+  if (rc) return rc;
+  ctx->packed_hold = em;
+  return EB200_OK;
+}
+
+int eb200_pack_fields_release(eb200_ctx_t* ctx) {
+  if (ctx) ctx->packed_hold = nullptr;
+  return EB200_OK;
 }
 
 /* ------------------------------------------------------ curvilinear SR field solvers */
@@ -611,8 +653,8 @@ int eb200_metric_eval(int metric, const int* n_active, const float* metric_param
 
 int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which) {
   ENTER(ctx);
-  REQUIRE(ctx, which >= 0 && which <= 4,
-          "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4, 4 shared-memory tiles");
+  REQUIRE(ctx, which >= 0 && which <= 6,
+          "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4, 4 shared-memory tiles, 5 vec4 + packed nodes, 6 pipelined");
   ctx->pd_kernel = which;
   return EB200_OK;
 }

@@ -280,9 +280,17 @@ namespace eb200 {
       return EB200_OK;
     }
 
+    static int PushAndDepositSpecies(Domain& dom, double time);
+
     int ParticlePushAndDeposit(Domain& dom, double time) {
       TRY(eb200_zero_currents(dom.ctx, dom.cur, dom.stream));
-      if (dom.host) return StreamedPushAndDeposit(dom, time);
+      TRY(eb200_pack_fields_hold(dom.ctx, dom.em, dom.stream));
+      const int rc = dom.host ? StreamedPushAndDeposit(dom, time) : PushAndDepositSpecies(dom, time);
+      eb200_pack_fields_release(dom.ctx);
+      return rc;
+    }
+
+    static int PushAndDepositSpecies(Domain& dom, double time) {
       for (int s = 0; s < dom.nspecies; ++s) {
         eb200_species_t& sp = dom.species[s];
         if (sp.pusher_flags == EB200_PUSHER_NONE || sp.npart == 0) continue;

@@ -59,7 +59,10 @@ namespace eb200 {
                         int mode, Scratch& scratch, cudaStream_t st);                          \
     cudaError_t push_deposit_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,    \
                                 const eb200_prtls_t& S, uint32_t npart, const float* em,       \
-                                float* cur, int mode, cudaStream_t st);                              \
+                                float* cur, int mode, float* packed, bool do_pack,             \
+                                cudaStream_t st);                                              \
+    cudaError_t pack_em2d(const eb200_grid_t& g, const float* em, float* packed,              \
+                          cudaStream_t st);                                                    \
     cudaError_t faraday(const eb200_grid_t& g, float* em, float c1, float c2,                 \
                         const float* stencil9, cudaStream_t st);                               \
     cudaError_t ampere(const eb200_grid_t& g, float* em, float c1, float c2, cudaStream_t st); \

@@ -353,6 +353,87 @@ namespace eb200 {
     b0[2] = lerp(bx3, true, true, false, D != 3);
   }
 
+  // E/B of a 2D mesh repacked node by node (24 bytes: {Ex, By | Ey, Bx | Ez, Bz}, i.e. the
+  // components grouped by staggering): the 2 x 2 patch of a staggering group is four loads off
+  // two row pointers (64-bit loads for the two-component groups), and every address is the
+  // uniform base + an unsigned 32-bit byte offset -- 16 loads and ~25 integer instructions per
+  // particle instead of 24 loads behind ~70 instructions of 64-bit index arithmetic on the
+  // component planes. The copy is made once per step by pack_em2d_kernel (0.4 GB of traffic).
+  struct PackedEM2 {
+    const char* p;
+    unsigned    rowb; // bytes per mesh row: 24 * N1
+  };
+
+  __device__ __forceinline__ float2 ld_keep2(const char* p) {
+    float2 v;
+    asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+  }
+
+  __device__ __forceinline__ float ld_keep1(const char* p) {
+    float v;
+    asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+  }
+
+  // same weights, nodes and summation order as gather_fields_direct<2>()
+  __device__ __forceinline__ void gather_packed(const PackedEM2& F, int ng, const Prtl<2>& P,
+                                                float* e0, float* b0) {
+    float          wp[2][2], wd[2][2];
+    unsigned       back[2]; // how far the dual (staggered) patch starts before the primal one
+    const unsigned st[2] = { 24u, F.rowb };
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ind = static_cast<int>(P.d[a] + HALF);
+      back[a]       = ind ? 0u : st[a];
+      wp[a][0]      = ONE - P.d[a];
+      wp[a][1]      = P.d[a];
+      wd[a][0]      = static_cast<float>(ind + 1) - (P.d[a] + HALF);
+      wd[a][1]      = ONE - wd[a][0];
+    }
+    const unsigned b00 = static_cast<unsigned>(P.i[0] + ng) * 24u +
+                         static_cast<unsigned>(P.i[1] + ng) * F.rowb;
+    const unsigned b10 = b00 - back[0], b01 = b00 - back[1], b11 = b10 - back[1];
+    {
+      // staggered in x1: Ex (.x), By (.y); wx dual, wy primal
+      const char*  q  = F.p + b10;
+      const char*  r  = F.p + (b10 + F.rowb);
+      const float2 q0 = ld_keep2(q), q1 = ld_keep2(q + 24), r0 = ld_keep2(r), r1 = ld_keep2(r + 24);
+      const float* wx = wd[0];
+      const float* wy = wp[1];
+      e0[0] = (q0.x * wx[0] + q1.x * wx[1]) * wy[0] + (r0.x * wx[0] + r1.x * wx[1]) * wy[1];
+      b0[1] = (q0.y * wx[0] + q1.y * wx[1]) * wy[0] + (r0.y * wx[0] + r1.y * wx[1]) * wy[1];
+    }
+    {
+      // staggered in x2: Ey (.x), Bx (.y); wx primal, wy dual
+      const char*  q  = F.p + (b01 + 8u);
+      const char*  r  = F.p + (b01 + 8u + F.rowb);
+      const float2 q0 = ld_keep2(q), q1 = ld_keep2(q + 24), r0 = ld_keep2(r), r1 = ld_keep2(r + 24);
+      const float* wx = wp[0];
+      const float* wy = wd[1];
+      e0[1] = (q0.x * wx[0] + q1.x * wx[1]) * wy[0] + (r0.x * wx[0] + r1.x * wx[1]) * wy[1];
+      b0[0] = (q0.y * wx[0] + q1.y * wx[1]) * wy[0] + (r0.y * wx[0] + r1.y * wx[1]) * wy[1];
+    }
+    {
+      // Ez on the nodes
+      const char*  q  = F.p + (b00 + 16u);
+      const char*  r  = F.p + (b00 + 16u + F.rowb);
+      const float* wx = wp[0];
+      const float* wy = wp[1];
+      e0[2] = (ld_keep1(q) * wx[0] + ld_keep1(q + 24) * wx[1]) * wy[0] +
+              (ld_keep1(r) * wx[0] + ld_keep1(r + 24) * wx[1]) * wy[1];
+    }
+    {
+      // Bz staggered in both
+      const char*  q  = F.p + (b11 + 20u);
+      const char*  r  = F.p + (b11 + 20u + F.rowb);
+      const float* wx = wd[0];
+      const float* wy = wd[1];
+      b0[2] = (ld_keep1(q) * wx[0] + ld_keep1(q + 24) * wx[1]) * wy[0] +
+              (ld_keep1(r) * wx[0] + ld_keep1(r + 24) * wx[1]) * wy[1];
+    }
+  }
+
   // A CTA's shared-memory copy of the E/B nodes around its (cell-sorted) particles: TR rows of
   // TC columns per component, origin (c0, r0) in ghost-inclusive node indices. Particles whose
   // 3 x 3 gather neighbourhood lies inside read shared memory (immediate offsets from one
@@ -416,6 +497,9 @@ namespace eb200 {
     if constexpr (is_tile_em<EM>::value) {
       static_assert(D == 2 && O == 0, "field tiles: 2D zig-zag only");
       gather_tile(F, ng, P, e0, b0);
+    } else if constexpr (std::is_same<EM, PackedEM2>::value) {
+      static_assert(D == 2 && O == 0, "packed nodes: 2D zig-zag only");
+      gather_packed(F, ng, P, e0, b0);
     } else if constexpr (std::is_same<EM, FieldView<D>>::value) {
       if constexpr (O == 0) {
         gather_fields_direct<D>(F, ng, P, e0, b0);

@@ -2,6 +2,7 @@
 //
 // Compiled twice (EB200_STRICT=0/1, see common.cuh). Launch helpers at the bottom are
 // what capi.cu calls.
+#include <cstdlib>
 #include "particle.cuh"
 #include "launch.h"
 
@@ -458,10 +459,23 @@ namespace eb200 {
     // without spilling (80 registers), the 3D body (12 nodes per segment) needs 128
     constexpr int vec_minblocks(int D) { return (D == 3) ? 2 : EB200_VEC_MINBLOCKS; }
 
-    template <int D, bool LEAN>
+    // E/B component planes -> 24-byte nodes {Ex, By | Ey, Bx | Ez, Bz} (PackedEM2)
+    __global__ void __launch_bounds__(256)
+      pack_em2d_kernel(const float* __restrict__ em, long plane, float2* __restrict__ out) {
+      const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+      if (n >= plane) return;
+      const float e1 = __ldcs(em + n), e2 = __ldcs(em + plane + n), e3 = __ldcs(em + 2 * plane + n);
+      const float b1 = __ldcs(em + 3 * plane + n), b2 = __ldcs(em + 4 * plane + n),
+                  b3 = __ldcs(em + 5 * plane + n);
+      out[3 * n]     = make_float2(e1, b2);
+      out[3 * n + 1] = make_float2(e2, b1);
+      out[3 * n + 2] = make_float2(e3, b3);
+    }
+
+    template <int D, bool LEAN, class EM = FieldView<D>>
     __global__ void __launch_bounds__(256, vec_minblocks(D))
       push_deposit_vec_kernel(PushArgs A, eb200_prtls_t S, uint32_t ngroups, uint32_t ahead,
-                              FieldView<D> EB, float charge, float inv_dt, FieldView<D> J) {
+                              EM EB, float charge, float inv_dt, FieldView<D> J) {
       constexpr int  NV       = ZigZag<D>::NV;
       const uint32_t g        = blockIdx.x * blockDim.x + threadIdx.x;
       const bool     in_range = g < ngroups;
@@ -546,7 +560,7 @@ namespace eb200 {
         }
         P.w   = wv[k];
         P.tag = tag;
-        push_particle<D, 0, FieldView<D>, LEAN>(A, EB, P);
+        push_particle<D, 0, EM, LEAN>(A, EB, P);
         if (P.tag != tag) {
           S.tag[p0 + k] = P.tag;
         }
@@ -616,6 +630,230 @@ namespace eb200 {
         if (run.head && cur >= 0) {
 #endif
           atomicAdd(J.p + cur + zigzag_offset<D>(n, J.N1, N12, J.plane), s);
+        }
+      }
+    }
+
+    /* ------------- pipelined push + deposit (2D zig-zag, packed nodes, persistent CTAs) */
+    // The vectorised kernel spends its stall cycles in two dependent waits per thread: the
+    // particle slices (DRAM/L2 latency) and then the first particle's E/B nodes (an L1 miss:
+    // every CTA works on cells nobody on the SM has touched). Here each CTA owns a CONTIGUOUS
+    // range of 1024-particle tiles and walks it: the slices of the next tile are copied
+    // global -> shared with per-thread cp.async (16 bytes per array and thread, thread-private
+    // slots: no barrier, no register cost) while the current tile is computed, and the E/B
+    // lines the next tile will gather from (one tile further along the mesh row for
+    // cell-sorted particles) are pulled into L1 with prefetch instructions. Arithmetic, stores
+    // and the deposit are those of push_deposit_vec_kernel.
+    __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tma::saddr(smem)), "l"(g)
+                   : "memory");
+    }
+    __device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tma::saddr(smem)), "l"(g)
+                   : "memory");
+    }
+    __device__ __forceinline__ void cp_async_commit() {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void cp_async_wait_all() {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __device__ __forceinline__ void prefetch_l1(const void* p) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
+
+#ifndef EB200_PIPE_MINBLOCKS
+  #define EB200_PIPE_MINBLOCKS 3
+#endif
+    constexpr int PIPE_THREADS = 256;
+
+    template <bool LEAN>
+    __global__ void __launch_bounds__(PIPE_THREADS, EB200_PIPE_MINBLOCKS)
+      push_deposit_pipe_kernel(PushArgs A, eb200_prtls_t S, uint32_t ngroups,
+                               uint32_t tiles_per_cta, uint32_t tile_stride, unsigned ahead_bytes,
+                               unsigned em_bytes,
+                               PackedEM2 EB, float charge, float inv_dt, FieldView<2> J) {
+      constexpr int D  = 2;
+      constexpr int NV = ZigZag<D>::NV;
+      __shared__ __align__(16) int4   s_i[D][PIPE_THREADS];
+      __shared__ __align__(16) float4 s_d[D][PIPE_THREADS];
+      __shared__ __align__(16) float4 s_u[3][PIPE_THREADS];
+      __shared__ __align__(16) float4 s_w[PIPE_THREADS];
+      __shared__ __align__(8) short4  s_t[PIPE_THREADS];
+      const int      tid     = threadIdx.x;
+      const uint32_t ntiles  = (ngroups + PIPE_THREADS - 1) / PIPE_THREADS;
+      // tile_stride == 1: this CTA owns tiles [b * per, (b + 1) * per); otherwise tiles b,
+      // b + stride, ... (all resident CTAs then sweep one contiguous window of the arrays)
+      const uint32_t t_begin = (tile_stride == 1) ? blockIdx.x * tiles_per_cta : blockIdx.x;
+      const uint32_t t_end   = (tile_stride == 1) ? min(ntiles, t_begin + tiles_per_cta) : ntiles;
+      if (t_begin >= t_end) return;
+      int*   ii[3]  = { S.i1, S.i2, S.i3 };
+      float* dd[3]  = { S.dx1, S.dx2, S.dx3 };
+      int*   iip[3] = { S.i1_prev, S.i2_prev, S.i3_prev };
+      float* ddp[3] = { S.dx1_prev, S.dx2_prev, S.dx3_prev };
+      auto issue = [&](uint32_t tile) {
+        const uint32_t gn = tile * PIPE_THREADS + tid;
+        if (gn < ngroups) {
+          const size_t q0 = (size_t)gn * VEC;
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            cp_async16(&s_i[a][tid], ii[a] + q0);
+            cp_async16(&s_d[a][tid], dd[a] + q0);
+          }
+          cp_async16(&s_u[0][tid], S.ux1 + q0);
+          cp_async16(&s_u[1][tid], S.ux2 + q0);
+          cp_async16(&s_u[2][tid], S.ux3 + q0);
+          cp_async16(&s_w[tid], S.weight + q0);
+          cp_async8(&s_t[tid], S.tag + q0);
+        }
+        cp_async_commit();
+      };
+      issue(t_begin);
+      const long N12 = (long)J.N1 * J.N2;
+      auto       red = [&](int key, const float (&a)[NV]) {
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+          atomicAdd(J.p + key + zigzag_offset<D>(n, J.N1, N12, J.plane), a[n]);
+        }
+      };
+      for (uint32_t tile = t_begin; tile < t_end; tile += tile_stride) {
+        const uint32_t g        = tile * PIPE_THREADS + tid;
+        const bool     in_range = g < ngroups;
+        const size_t   p0       = (size_t)g * VEC;
+        int            iv[D][VEC];
+        float          dv[D][VEC], uv[3][VEC], wv[VEC];
+        short          tv[VEC]    = { 0, 0, 0, 0 };
+        bool           all_pushed = false;
+        cp_async_wait_all();
+        if (in_range) {
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            const int4   t4 = s_i[a][tid];
+            const float4 f4 = s_d[a][tid];
+            iv[a][0] = t4.x, iv[a][1] = t4.y, iv[a][2] = t4.z, iv[a][3] = t4.w;
+            dv[a][0] = f4.x, dv[a][1] = f4.y, dv[a][2] = f4.z, dv[a][3] = f4.w;
+          }
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const float4 f4 = s_u[a][tid];
+            uv[a][0] = f4.x, uv[a][1] = f4.y, uv[a][2] = f4.z, uv[a][3] = f4.w;
+          }
+          {
+            const float4 f4 = s_w[tid];
+            wv[0] = f4.x, wv[1] = f4.y, wv[2] = f4.z, wv[3] = f4.w;
+            const short4 h4 = s_t[tid];
+            tv[0] = h4.x, tv[1] = h4.y, tv[2] = h4.z, tv[3] = h4.w;
+          }
+          // every staged vector has been read (one element of each is consumed here) before
+          // the slots are handed to the next tile's copies
+          float chk = uv[0][0] + uv[1][0] + uv[2][0] + wv[0] + dv[0][0] + dv[1][0];
+          int   chi = iv[0][0] + iv[1][0] + tv[0];
+          asm volatile("" ::"f"(chk), "r"(chi) : "memory");
+        }
+        if (tile + tile_stride < t_end) {
+          issue(tile + tile_stride);
+          if (in_range && ahead_bytes) {
+            // E/B lines of the next tile: the rows around this thread's first particle, one
+            // tile further along the row
+            const unsigned b = static_cast<unsigned>(iv[0][0] + A.ng) * 24u +
+                               static_cast<unsigned>(iv[1][0] + A.ng) * EB.rowb + ahead_bytes;
+            if (b + EB.rowb + 128u < em_bytes && b >= EB.rowb) {
+              prefetch_l1(EB.p + (b - EB.rowb));
+              prefetch_l1(EB.p + b);
+              prefetch_l1(EB.p + (b + EB.rowb));
+            }
+          }
+        }
+        if (in_range) {
+          all_pushed = (tv[0] == 1) && (tv[1] == 1) && (tv[2] == 1) && (tv[3] == 1);
+          if (all_pushed) {
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+              st4<int4>(iip[a] + p0, iv[a]);
+              st4<float4>(ddp[a] + p0, dv[a]);
+            }
+          }
+        }
+        float acc[NV];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) acc[n] = ZERO;
+        int cur = -1;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const short tag = tv[k];
+          if (tag != 1) {
+            continue;
+          }
+          Prtl<D> P;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            P.i[a] = P.ip[a] = (a < D) ? iv[a][k] : 0;
+            P.d[a] = P.dp[a] = (a < D) ? dv[a][k] : ZERO;
+            P.u[a]           = uv[a][k];
+          }
+          P.w   = wv[k];
+          P.tag = tag;
+          push_particle<D, 0, PackedEM2, LEAN>(A, EB, P);
+          if (P.tag != tag) {
+            S.tag[p0 + k] = P.tag;
+          }
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            if (!all_pushed || P.ip[a] != iv[a][k]) {
+              iip[a][p0 + k] = P.ip[a];
+            }
+            if (!all_pushed) {
+              ddp[a][p0 + k] = P.dp[a];
+            }
+            iv[a][k] = P.i[a];
+            dv[a][k] = P.d[a];
+          }
+#pragma unroll
+          for (int a = 0; a < 3; ++a) uv[a][k] = P.u[a];
+          if (P.tag == 0) {
+            continue;
+          }
+          float v[2][NV];
+          zigzag_values<D>(P, charge, inv_dt, A.c.dx, v);
+          const int  G     = A.ng;
+          const int  key0  = (int)J.idx(P.ip[0] + G, P.ip[1] + G, 0);
+          const int  key1  = (int)J.idx(P.i[0] + G, P.i[1] + G, 0);
+          const bool cross = key0 != key1;
+          if (cross) {
+            red(key1, v[1]);
+          } else {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) v[0][n] += v[1][n];
+          }
+          if (key0 != cur) {
+            if (cur >= 0) {
+              red(cur, acc);
+            }
+            cur = key0;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) acc[n] = v[0][n];
+          } else {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) acc[n] += v[0][n];
+          }
+        }
+        if (in_range) {
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            st4<int4>(ii[a] + p0, iv[a]);
+            st4<float4>(dd[a] + p0, dv[a]);
+          }
+          st4<float4>(S.ux1 + p0, uv[0]);
+          st4<float4>(S.ux2 + p0, uv[1]);
+          st4<float4>(S.ux3 + p0, uv[2]);
+        }
+        const WarpRun run = warp_runs(cur);
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+          const float sm = run_sum(acc[n], run);
+          if (run.head && cur >= 0) {
+            atomicAdd(J.p + cur + zigzag_offset<D>(n, J.N1, N12, J.plane), sm);
+          }
         }
       }
     }
@@ -935,17 +1173,90 @@ namespace eb200 {
     template <int D, int O>
     cudaError_t launch_push_deposit(const PushArgs& A, const eb200_prtls_t& S, uint32_t npart,
                                     const eb200_grid_t& g, const float* em, float* cur,
-                                    int mode, cudaStream_t st) {
+                                    int mode, float* packed, bool do_pack, cudaStream_t st) {
       if (npart == 0) return cudaSuccess;
       FieldView<D> EB(g, const_cast<float*>(em));
       FieldView<D> J(g, cur);
       const float inv_dt = ONE / A.c.dt;
       uint32_t    p_begin = 0;
       // which fused kernel (eb200_set_pd_kernel): 0 auto, 1 one particle per thread,
-      // 2 TMA-staged persistent, 3 four particles per thread (zig-zag only)
+      // 2 TMA-staged persistent, 3 four particles per thread (zig-zag only), 4 shared-memory
+      // field tile, 5 four particles per thread gathering from packed nodes (2D zig-zag)
       const int which = (mode >> 8) & 0xff;
       mode &= 0xff;
       const bool want_vec = (O == 0) && (which == 0 || which == 3);
+      if constexpr (O == 0 && D == 2) {
+        if (which == 6 && packed != nullptr && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) &&
+            npart >= VEC && J.plane < 0x7fffffffL && EB.plane * 24 < 0xffffffffL) {
+          if (do_pack) {
+            pack_em2d_kernel<<<(unsigned)((EB.plane + 255) / 256), 256, 0, st>>>(
+              em, EB.plane, reinterpret_cast<float2*>(packed));
+            count_launch();
+          }
+          PackedEM2 PK;
+          PK.p    = reinterpret_cast<const char*>(packed);
+          PK.rowb = 24u * (unsigned)EB.N1;
+          const uint32_t ngroups = npart / VEC;
+          const bool     lean    = lean_pusher(A.c);
+          auto           kern    = lean ? push_deposit_pipe_kernel<true> : push_deposit_pipe_kernel<false>;
+          static int     slots[2] = { 0, 0 };
+          if (slots[lean] == 0) {
+            int dev = 0, nsm = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PIPE_THREADS, 0);
+            slots[lean] = nsm * (per_sm > 0 ? per_sm : 1);
+          }
+          const uint32_t ntiles = (ngroups + PIPE_THREADS - 1) / PIPE_THREADS;
+          const uint32_t grid   = ntiles < (uint32_t)slots[lean] ? ntiles : (uint32_t)slots[lean];
+          const uint32_t per    = (ntiles + grid - 1) / grid;
+          // one tile of cell-sorted particles spans about 1024 / (particles per cell) cells
+          const double   per_cell = (double)npart / ((double)g.n[0] * g.n[1]);
+          static const int ahead_env = getenv("EB200_PIPE_AHEAD") ? atoi(getenv("EB200_PIPE_AHEAD")) : -1;
+          unsigned       ahead  = ahead_env >= 0 ? (unsigned)ahead_env * 24u
+                                                 : (unsigned)((PIPE_THREADS * VEC) / (per_cell > 1.0 ? per_cell : 1.0)) * 24u;
+          static const bool blocked = getenv("EB200_PIPE_BLOCKED") != nullptr;
+          if (blocked) {
+            kern<<<(ntiles + per - 1) / per, PIPE_THREADS, 0, st>>>(
+              A, S, ngroups, per, 1u, ahead, (unsigned)(EB.plane * 24), PK, A.c.charge, inv_dt, J);
+          } else {
+            if (ahead_env < 0) ahead *= grid;
+            kern<<<grid, PIPE_THREADS, 0, st>>>(
+              A, S, ngroups, per, grid, ahead, (unsigned)(EB.plane * 24), PK, A.c.charge, inv_dt, J);
+          }
+          count_launch();
+          p_begin = ngroups * VEC;
+          if (p_begin == npart) return cudaGetLastError();
+        }
+        if ((which == 5 || which == 0) && p_begin == 0 && packed != nullptr && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) &&
+            npart >= VEC && J.plane < 0x7fffffffL && EB.plane * 24 < 0xffffffffL) {
+          if (do_pack) {
+            pack_em2d_kernel<<<(unsigned)((EB.plane + 255) / 256), 256, 0, st>>>(
+              em, EB.plane, reinterpret_cast<float2*>(packed));
+            count_launch();
+          }
+          PackedEM2 PK;
+          PK.p    = reinterpret_cast<const char*>(packed);
+          PK.rowb = 24u * (unsigned)EB.N1;
+          const uint32_t ngroups = npart / VEC;
+          const bool     lean    = lean_pusher(A.c);
+          auto           kern    = lean ? push_deposit_vec_kernel<2, true, PackedEM2>
+                                        : push_deposit_vec_kernel<2, false, PackedEM2>;
+          static int     wave[2] = { 0, 0 };
+          if (wave[lean] == 0) {
+            int dev = 0, nsm = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+            wave[lean] = nsm * (per_sm > 0 ? per_sm : 1);
+          }
+          kern<<<(ngroups + 255) / 256, 256, 0, st>>>(A, S, ngroups, (uint32_t)wave[lean], PK,
+                                                       A.c.charge, inv_dt, J);
+          count_launch();
+          p_begin = ngroups * VEC;
+          if (p_begin == npart) return cudaGetLastError();
+        }
+      }
       if constexpr (O == 0 && D == 2) {
         // 4: shared-memory field tile (needs 16-byte aligned rows and a mesh at least one
         // tile wide)
@@ -1073,16 +1384,25 @@ namespace eb200 {
 
     cudaError_t push_deposit_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,
                                 const eb200_prtls_t& S, uint32_t npart, const float* em,
-                                float* cur, int mode, cudaStream_t st) {
+                                float* cur, int mode, float* packed, bool do_pack,
+                                cudaStream_t st) {
       PushArgs A;
       A.c   = c;
       A.ndh = HALF * (c.charge / c.mass) * c.omegaB0 * c.dt;
       A.ng  = g.ng;
       A.inv_dx = ONE / c.dx;
       for (int a = 0; a < 3; ++a) A.ni[a] = g.n[a];
-#define CALL(D, O) launch_push_deposit<D, O>(A, S, npart, g, em, cur, mode, st)
+#define CALL(D, O) launch_push_deposit<D, O>(A, S, npart, g, em, cur, mode, packed, do_pack, st)
       EB200_DISPATCH_DO(g.dim, order, CALL)
 #undef CALL
+    }
+
+    cudaError_t pack_em2d(const eb200_grid_t& g, const float* em, float* packed, cudaStream_t st) {
+      FieldView<2> EB(g, const_cast<float*>(em));
+      pack_em2d_kernel<<<(unsigned)((EB.plane + 255) / 256), 256, 0, st>>>(
+        em, EB.plane, reinterpret_cast<float2*>(packed));
+      count_launch();
+      return cudaGetLastError();
     }
 
   } // namespace EB200_VARIANT

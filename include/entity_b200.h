@@ -182,6 +182,13 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
                           const eb200_prtls_t* prtls, uint32_t npart, const float* em, float* cur,
                           int mode, eb200_stream_t stream);
 int eb200_zero_currents(eb200_ctx_t* ctx, float* cur, eb200_stream_t stream);
+/* Fused kernel 5 gathers E/B from a context-owned copy of em repacked node by node. A call of
+ * eb200_push_deposit_sr rebuilds that copy unless the caller holds it: hold(em) packs once and
+ * promises that em is not modified until release (eb200_srpic_step does this around the species
+ * loop of srpic::ParticlePush, where the reference does not touch em either). No-ops for the
+ * other kernels. */
+int eb200_pack_fields_hold(eb200_ctx_t* ctx, const float* em, eb200_stream_t stream);
+int eb200_pack_fields_release(eb200_ctx_t* ctx);
 /* which fused kernel eb200_push_deposit_sr / eb200_srpic_step launch in AGGREGATED mode:
  * 0 = automatic (default), 1 = one particle per thread, 2 = TMA-staged persistent chunks,
  * 3 = four particles per thread with 128-bit accesses (zig-zag only). A tuning knob for
