@@ -349,15 +349,18 @@ int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const i
     pair_ok = pair_ok && (fbc[a] == EB200_FBC_PERIODIC || fbc[a] == EB200_FBC_SYNC);
   }
   for (int pass = 0; pass < nfilter; ++pass) {
-    // buff <- cur (currents.h:108), filter into cur (:109-116), ghost exchange (:117)
-    cudaError_t e = cudaMemcpyAsync(buff, cur, bytes, cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) return check_cuda(ctx, e, "filter copy");
+    cudaError_t e;
     if (pair_ok && pass + 1 < nfilter) {
-      e = VARIANT_CALL(ctx, filter_pass(ctx->cfg.grid, cur, buff, fbc, 1, st));
+      // a pair ping-pongs between the two arrays: cur -> buff over the active cells + one ghost
+      // layer, then buff -> cur over the active cells; no copy (each filter pass writes every
+      // cell the next one reads)
+      e = VARIANT_CALL(ctx, filter_pass(ctx->cfg.grid, buff, cur, fbc, 1, st));
       if (e != cudaSuccess) return check_cuda(ctx, e, "filter pass (extended)");
+      ++pass;
+    } else {
+      // buff <- cur (currents.h:108), filter into cur (:109-116), ghost exchange (:117)
       e = cudaMemcpyAsync(buff, cur, bytes, cudaMemcpyDeviceToDevice, st);
       if (e != cudaSuccess) return check_cuda(ctx, e, "filter copy");
-      ++pass;
     }
     e = VARIANT_CALL(ctx, filter_pass(ctx->cfg.grid, cur, buff, fbc, 0, st));
     if (e != cudaSuccess) return check_cuda(ctx, e, "filter pass");

@@ -109,7 +109,6 @@ namespace eb200 {
   cudaError_t sort_particles(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
                              uint32_t maxnpart, int remove_dead, uint32_t* n_alive_out,
                              Scratch& scratch, cudaStream_t st) {
-    (void)maxnpart;
     if (n_alive_out) *n_alive_out = npart;
     if (npart == 0) return cudaSuccess;
     const int      n1 = g.n[0], n2 = g.dim > 1 ? g.n[1] : 1, n3 = g.dim > 2 ? g.n[2] : 1;
@@ -123,7 +122,17 @@ namespace eb200 {
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                     (uint32_t*)nullptr, (uint32_t*)nullptr, (size_t)npart, 0,
                                     bits, st);
-    const size_t n4  = ((size_t)npart * 4 + 255) / 256 * 256;
+    // the scratch layout is sized by the arrays' capacity, not by npart: npart moves from call to
+    // call (migration, species of different size) and every growth of a 5 GB buffer is a
+    // cudaFree + cudaMalloc (tens of milliseconds)
+    const size_t ncap = (maxnpart >= npart) ? (size_t)maxnpart : (size_t)npart + npart / 8;
+    const size_t n4   = (ncap * 4 + 255) / 256 * 256;
+    {
+      size_t cap_tmp = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, cap_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                      (uint32_t*)nullptr, (uint32_t*)nullptr, ncap, 0, bits, st);
+      if (cap_tmp > tmp_bytes) tmp_bytes = cap_tmp;
+    }
     cudaError_t  err = scratch.reserve(8 * n4 + tmp_bytes + 512);
     if (err != cudaSuccess) return err;
     char*     base  = (char*)scratch.ptr;
