@@ -327,7 +327,7 @@ int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const i
     int    left = nfilter;
     for (int s = 0; s < sweeps; ++s) {
       const int   p = (left + (sweeps - s) - 1) / (sweeps - s);
-      cudaError_t e = VARIANT_CALL(ctx, filter_fused(ctx->cfg.grid, a, b, p, st));
+      cudaError_t e = VARIANT_CALL(ctx, filter_fused(ctx->cfg.grid, a, b, p, 0, st));
       if (e != cudaSuccess) return check_cuda(ctx, e, "fused filter");
       left -= p;
       float* t = a;
@@ -348,6 +348,38 @@ int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const i
   for (int a = 0; a < 2 * ctx->cfg.grid.dim; ++a) {
     pair_ok = pair_ok && (fbc[a] == EB200_FBC_PERIODIC || fbc[a] == EB200_FBC_SYNC);
   }
+  auto exchange = [&](float* fld) -> int {
+    if (ctx->comm) {
+      int rc = eb200::comm_fields(*ctx->comm, fld, 0, 3, st);
+      return rc == EB200_OK ? rc : fail(ctx, rc, eb200::comm_error(ctx->comm));
+    }
+    return check_cuda(ctx, VARIANT_CALL(ctx, comm_fields_self(ctx->cfg.grid, fld, 0, 3, fbc, st)),
+                      "filter ghost exchange");
+  };
+  if (pair_ok && ctx->cfg.grid.dim == 2 && nfilter > 0) {
+    // 2D: each pair is ONE sweep of the temporally blocked kernel reading the exchanged ghost
+    // cells as its halo (two passes in shared memory), ping-ponging between the two arrays;
+    // the exchange follows the array that holds the result
+    float* a    = cur;
+    float* b    = buff;
+    int    left = nfilter;
+    while (left > 0) {
+      const int   p = left >= 2 ? 2 : 1;
+      cudaError_t e = VARIANT_CALL(ctx, filter_fused(ctx->cfg.grid, a, b, p, 1, st));
+      if (e != cudaSuccess) return check_cuda(ctx, e, "fused filter (ghost halo)");
+      int rc = exchange(b);
+      if (rc != EB200_OK) return rc;
+      left -= p;
+      float* t = a;
+      a        = b;
+      b        = t;
+    }
+    if (a != cur) {
+      cudaError_t e = cudaMemcpyAsync(cur, a, bytes, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return check_cuda(ctx, e, "filter copy");
+    }
+    return EB200_OK;
+  }
   for (int pass = 0; pass < nfilter; ++pass) {
     cudaError_t e;
     if (pair_ok && pass + 1 < nfilter) {
@@ -364,13 +396,8 @@ int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const i
     }
     e = VARIANT_CALL(ctx, filter_pass(ctx->cfg.grid, cur, buff, fbc, 0, st));
     if (e != cudaSuccess) return check_cuda(ctx, e, "filter pass");
-    if (ctx->comm) {
-      int rc = eb200::comm_fields(*ctx->comm, cur, 0, 3, st);
-      if (rc != EB200_OK) return fail(ctx, rc, eb200::comm_error(ctx->comm));
-    } else {
-      e = VARIANT_CALL(ctx, comm_fields_self(ctx->cfg.grid, cur, 0, 3, fbc, st));
-      if (e != cudaSuccess) return check_cuda(ctx, e, "filter ghost exchange");
-    }
+    int rc = exchange(cur);
+    if (rc != EB200_OK) return rc;
   }
   return EB200_OK;
 }

@@ -454,7 +454,9 @@ namespace eb200 {
     // instead of P x (copy + stencil + ghost fill).
     constexpr int FT_X = 64, FT_Y = 16, FT_PMAX = 4;
 
-    template <int P>
+    // GHOSTS: the halo of a tile is read from the ghost cells as they are (they hold the
+    // neighbour domains' exchanged values, P <= G) instead of the periodic image
+    template <int P, bool GHOSTS = false>
     __global__ void __launch_bounds__(256)
       filter_fused2d_kernel(FieldView<2> src, FieldView<2> dst, int n1, int n2, int G) {
       constexpr int W = FT_X + 2 * P, H = FT_Y + 2 * P;
@@ -474,7 +476,13 @@ namespace eb200 {
       };
       for (int e = threadIdx.x; e < W * H; e += 256) {
         const int ly = e / W, lx = e - ly * W;
-        buf[0][e] = src.ld(wrap(x0 + lx, n1) + G, wrap(y0 + ly, n2) + G, 0, c);
+        if constexpr (GHOSTS) {
+          // tiles past the active edge (partial tiles) clamp: those cells are never stored
+          const int gx = min(x0 + lx, n1 + G - 1), gy = min(y0 + ly, n2 + G - 1);
+          buf[0][e] = src.ld(gx + G, gy + G, 0, c);
+        } else {
+          buf[0][e] = src.ld(wrap(x0 + lx, n1) + G, wrap(y0 + ly, n2) + G, 0, c);
+        }
       }
       __syncthreads();
       int cur = 0;
@@ -606,10 +614,20 @@ namespace eb200 {
     }
 
     cudaError_t filter_fused(const eb200_grid_t& g, const float* src, float* dst, int passes,
-                             cudaStream_t st) {
+                             int ghosts, cudaStream_t st) {
       if (g.dim != 2 || passes < 1 || passes > FT_PMAX) return cudaErrorInvalidValue;
       const dim3 grid((g.n[0] + FT_X - 1) / FT_X, (g.n[1] + FT_Y - 1) / FT_Y, 3);
       const FieldView<2> S(g, const_cast<float*>(src)), Dd(g, dst);
+      if (ghosts) {
+        if (passes > 2 || passes > g.ng) return cudaErrorInvalidValue;
+        if (passes == 1) {
+          filter_fused2d_kernel<1, true><<<grid, 256, 0, st>>>(S, Dd, g.n[0], g.n[1], g.ng);
+        } else {
+          filter_fused2d_kernel<2, true><<<grid, 256, 0, st>>>(S, Dd, g.n[0], g.n[1], g.ng);
+        }
+        count_launch();
+        return cudaGetLastError();
+      }
       switch (passes) {
         case 1: filter_fused2d_kernel<1><<<grid, 256, 0, st>>>(S, Dd, g.n[0], g.n[1], g.ng); break;
         case 2: filter_fused2d_kernel<2><<<grid, 256, 0, st>>>(S, Dd, g.n[0], g.n[1], g.ng); break;

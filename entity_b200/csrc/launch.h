@@ -71,7 +71,7 @@ namespace eb200 {
     cudaError_t filter_pass(const eb200_grid_t& g, float* cur, const float* buff,             \
                             const int* fbc, int extend, cudaStream_t st);                      \
     cudaError_t filter_fused(const eb200_grid_t& g, const float* src, float* dst, int passes, \
-                             cudaStream_t st);                                                 \
+                             int ghosts, cudaStream_t st);                                     \
     cudaError_t comm_fields_self(const eb200_grid_t& g, float* fld, int c0, int c1,           \
                                  const int* fbc, cudaStream_t st);                             \
     cudaError_t sync_currents_self(const eb200_grid_t& g, float* cur, float* buff,            \
