@@ -858,6 +858,202 @@ namespace eb200 {
       }
     }
 
+    /* ------------- shared-memory resident push + deposit (2D zig-zag, packed nodes) */
+    // The vectorised kernel holds the four particles of a thread in registers (44 of its 80),
+    // which caps the SM at 24 warps; it is latency bound (1.1 eligible warps per scheduler).
+    // Here the slices are parked in shared memory, transposed to [k][thread] so that the
+    // per-particle 32-bit accesses are conflict free, the particle loop is NOT unrolled (one
+    // copy of the push/deposit body: a quarter of the code) and the registers only hold one
+    // particle + the cell accumulators: more resident warps for the same work. Global accesses
+    // stay 128-bit and coalesced; arithmetic and deposit are those of push_deposit_vec_kernel.
+#ifndef EB200_SMEM_MINBLOCKS
+  #define EB200_SMEM_MINBLOCKS 4
+#endif
+    template <bool LEAN>
+    __global__ void __launch_bounds__(256, EB200_SMEM_MINBLOCKS)
+      push_deposit_smem_kernel(PushArgs A, eb200_prtls_t S, uint32_t ngroups, uint32_t ahead,
+                               PackedEM2 EB, float charge, float inv_dt, FieldView<2> J) {
+      constexpr int D  = 2;
+      constexpr int NV = ZigZag<D>::NV;
+      __shared__ int   s_i[D][VEC][256];
+      __shared__ float s_d[D][VEC][256];
+      __shared__ float s_u[3][VEC][256];
+      __shared__ float s_w[VEC][256];
+      __shared__ short s_t[VEC][256];
+      const int      tid      = threadIdx.x;
+      const uint32_t g        = blockIdx.x * blockDim.x + tid;
+      const bool     in_range = g < ngroups;
+      const size_t   p0       = (size_t)g * VEC;
+      int*           ii[3]    = { S.i1, S.i2, S.i3 };
+      float*         dd[3]    = { S.dx1, S.dx2, S.dx3 };
+      int*           iip[3]   = { S.i1_prev, S.i2_prev, S.i3_prev };
+      float*         ddp[3]   = { S.dx1_prev, S.dx2_prev, S.dx3_prev };
+      if (tid == 0) {
+        const size_t q0 = ((size_t)blockIdx.x + ahead) * blockDim.x * VEC;
+        if (q0 + (size_t)blockDim.x * VEC <= (size_t)ngroups * VEC) {
+          const unsigned b4 = blockDim.x * VEC * 4, b2 = blockDim.x * VEC * 2;
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            tma::prefetch_l2(ii[a] + q0, b4);
+            tma::prefetch_l2(dd[a] + q0, b4);
+          }
+          tma::prefetch_l2(S.ux1 + q0, b4);
+          tma::prefetch_l2(S.ux2 + q0, b4);
+          tma::prefetch_l2(S.ux3 + q0, b4);
+          tma::prefetch_l2(S.weight + q0, b4);
+          tma::prefetch_l2(S.tag + q0, b2);
+        }
+      }
+      bool all_pushed = false;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) s_t[k][tid] = 0;
+      if (in_range) {
+        short tv[VEC];
+        ld4<short4>(S.tag + p0, tv);
+        all_pushed = (tv[0] == 1) && (tv[1] == 1) && (tv[2] == 1) && (tv[3] == 1);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s_t[k][tid] = tv[k];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          int   iv[VEC];
+          float dv[VEC];
+          ld4<int4>(ii[a] + p0, iv);
+          ld4<float4>(dd[a] + p0, dv);
+          if (all_pushed) {
+            st4<int4>(iip[a] + p0, iv);
+            st4<float4>(ddp[a] + p0, dv);
+          }
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            s_i[a][k][tid] = iv[k];
+            s_d[a][k][tid] = dv[k];
+          }
+        }
+        {
+          float v[VEC];
+          ld4<float4>(S.ux1 + p0, v);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) s_u[0][k][tid] = v[k];
+          ld4<float4>(S.ux2 + p0, v);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) s_u[1][k][tid] = v[k];
+          ld4<float4>(S.ux3 + p0, v);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) s_u[2][k][tid] = v[k];
+          ld4<float4>(S.weight + p0, v);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) s_w[k][tid] = v[k];
+        }
+      }
+      const long N12 = (long)J.N1 * J.N2;
+      auto       red = [&](int key, const float (&a)[NV]) {
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+          atomicAdd(J.p + key + zigzag_offset<D>(n, J.N1, N12, J.plane), a[n]);
+        }
+      };
+      float acc[NV];
+#pragma unroll
+      for (int n = 0; n < NV; ++n) acc[n] = ZERO;
+      int cur = -1;
+#pragma unroll 1
+      for (int k = 0; k < VEC; ++k) {
+        const short tag = s_t[k][tid];
+        if (tag != 1) {
+          continue;
+        }
+        Prtl<D> P;
+        int     i_old[D];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (a < D) {
+            i_old[a] = s_i[a][k][tid];
+            P.i[a] = P.ip[a] = i_old[a];
+            P.d[a] = P.dp[a] = s_d[a][k][tid];
+          } else {
+            P.i[a] = P.ip[a] = 0;
+            P.d[a] = P.dp[a] = ZERO;
+          }
+          P.u[a] = s_u[a][k][tid];
+        }
+        P.w   = s_w[k][tid];
+        P.tag = tag;
+        push_particle<D, 0, PackedEM2, LEAN>(A, EB, P);
+        if (P.tag != tag) {
+          S.tag[p0 + k] = P.tag;
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          if (!all_pushed || P.ip[a] != i_old[a]) {
+            iip[a][p0 + k] = P.ip[a];
+          }
+          if (!all_pushed) {
+            ddp[a][p0 + k] = P.dp[a];
+          }
+          s_i[a][k][tid] = P.i[a];
+          s_d[a][k][tid] = P.d[a];
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) s_u[a][k][tid] = P.u[a];
+        if (P.tag == 0) {
+          continue;
+        }
+        float v[2][NV];
+        zigzag_values<D>(P, charge, inv_dt, A.c.dx, v);
+        const int  G     = A.ng;
+        const int  key0  = (int)J.idx(P.ip[0] + G, P.ip[1] + G, 0);
+        const int  key1  = (int)J.idx(P.i[0] + G, P.i[1] + G, 0);
+        const bool cross = key0 != key1;
+        if (cross) {
+          red(key1, v[1]);
+        } else {
+#pragma unroll
+          for (int n = 0; n < NV; ++n) v[0][n] += v[1][n];
+        }
+        if (key0 != cur) {
+          if (cur >= 0) {
+            red(cur, acc);
+          }
+          cur = key0;
+#pragma unroll
+          for (int n = 0; n < NV; ++n) acc[n] = v[0][n];
+        } else {
+#pragma unroll
+          for (int n = 0; n < NV; ++n) acc[n] += v[0][n];
+        }
+      }
+      if (in_range) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          int   iv[VEC];
+          float dv[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            iv[k] = s_i[a][k][tid];
+            dv[k] = s_d[a][k][tid];
+          }
+          st4<int4>(ii[a] + p0, iv);
+          st4<float4>(dd[a] + p0, dv);
+        }
+        float* uu[3] = { S.ux1, S.ux2, S.ux3 };
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          float v[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) v[k] = s_u[a][k][tid];
+          st4<float4>(uu[a] + p0, v);
+        }
+      }
+      const WarpRun run = warp_runs(cur);
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        const float sm = run_sum(acc[n], run);
+        if (run.head && cur >= 0) {
+          atomicAdd(J.p + cur + zigzag_offset<D>(n, J.N1, N12, J.plane), sm);
+        }
+      }
+    }
+
     /* ----------------------- tiled push + deposit (2D zig-zag, cell-sorted particles) */
     // The vectorised kernel above with the field gather moved to shared memory: the CTA's 1024
     // consecutive particles sit (when sorted) in ~1024/ppc consecutive cells of one row; the
@@ -1186,6 +1382,34 @@ namespace eb200 {
       mode &= 0xff;
       const bool want_vec = (O == 0) && (which == 0 || which == 3);
       if constexpr (O == 0 && D == 2) {
+        if (which == 7 && packed != nullptr && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) &&
+            npart >= VEC && J.plane < 0x7fffffffL && EB.plane * 24 < 0xffffffffL) {
+          if (do_pack) {
+            pack_em2d_kernel<<<(unsigned)((EB.plane + 255) / 256), 256, 0, st>>>(
+              em, EB.plane, reinterpret_cast<float2*>(packed));
+            count_launch();
+          }
+          PackedEM2 PK;
+          PK.p    = reinterpret_cast<const char*>(packed);
+          PK.rowb = 24u * (unsigned)EB.N1;
+          const uint32_t ngroups = npart / VEC;
+          const bool     lean    = lean_pusher(A.c);
+          auto           kern    = lean ? push_deposit_smem_kernel<true> : push_deposit_smem_kernel<false>;
+          static int     wave[2] = { 0, 0 };
+          if (wave[lean] == 0) {
+            int dev = 0, nsm = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 75);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+            wave[lean] = nsm * (per_sm > 0 ? per_sm : 1);
+          }
+          kern<<<(ngroups + 255) / 256, 256, 0, st>>>(A, S, ngroups, (uint32_t)wave[lean], PK,
+                                                       A.c.charge, inv_dt, J);
+          count_launch();
+          p_begin = ngroups * VEC;
+          if (p_begin == npart) return cudaGetLastError();
+        }
         if (which == 6 && packed != nullptr && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) &&
             npart >= VEC && J.plane < 0x7fffffffL && EB.plane * 24 < 0xffffffffL) {
           if (do_pack) {

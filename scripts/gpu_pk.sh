@@ -1,6 +1,6 @@
 #!/bin/bash
 OUT=gpurun_out; mkdir -p $OUT
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "wide_mesh" > $OUT/pytest_pk.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_step.py -m gpu -x -q -k "wide_mesh or energy" > $OUT/pytest_pk.log 2>&1
 echo "pytest rc=$?" >> $OUT/pytest_pk.log; tail -n 3 $OUT/pytest_pk.log
 run() { # tag env...
   TAG=$1; shift
@@ -8,5 +8,4 @@ run() { # tag env...
   python -c "import json; d=json.load(open('$OUT/bench_pk_$TAG.json')); print('$TAG', round(d['ms_per_step'],3), round(d['roofline']['phase_ms_per_step']['PushDeposit'],3), round(d['roofline']['frac'],3))" || tail -n 3 $OUT/bench_pk_$TAG.err
 }
 run k5 EB200_PD_KERNEL=5
-run k6_stride EB200_PD_KERNEL=6
-run k6_stride_noahead EB200_PD_KERNEL=6 EB200_PIPE_AHEAD=0
+run k7 EB200_PD_KERNEL=7

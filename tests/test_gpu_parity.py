@@ -235,7 +235,7 @@ def test_errors(eb):
         ctx.push(ctx.make_pusher(dt=0.1, pusher_flags=0), {}, 0, None)
 
 
-@pytest.mark.parametrize("which", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("which", [1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("strict", [False, True])
 @pytest.mark.parametrize("order_kind", ["sorted", "stale", "random"])
 def test_fused_kernels_wide_mesh(eb, orc_mod, which, strict, order_kind):

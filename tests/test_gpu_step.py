@@ -110,7 +110,7 @@ def _energies(em, grid, species):
     return fld, kin
 
 
-@pytest.mark.parametrize("which", [0, 2, 5, 6])
+@pytest.mark.parametrize("which", [0, 2, 5, 6, 7])
 def test_total_energy_window(mods, which):
     """north_star: 'fields, currents and total energy stay within a stated fp32 tolerance over a
     fixed step window'. Production path (fast build, fused push+deposit, warp-aggregated deposit,
