@@ -77,14 +77,32 @@ namespace eb200 {
     uint32_t* p[4];
   };
 
+  // four consecutive destinations per thread: one 128-bit index load, up to sixteen gathers in
+  // flight, 128-bit streaming stores (dst is 16-byte aligned scratch)
   __global__ void __launch_bounds__(256)
     gather4_kernel(Quad src, Quad dst, int na, const uint32_t* __restrict__ perm, uint32_t n) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n) {
-      const uint32_t s = perm[q];
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (q + 3 < n) {
+      const uint4 s = __ldcs(reinterpret_cast<const uint4*>(perm + q));
+      uint4       v[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        if (a < na) dst.p[a][q] = src.p[a][s];
+        if (a < na) {
+          const uint32_t* sp = src.p[a];
+          v[a] = make_uint4(__ldg(sp + s.x), __ldg(sp + s.y), __ldg(sp + s.z), __ldg(sp + s.w));
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (a < na) __stcs(reinterpret_cast<uint4*>(dst.p[a] + q), v[a]);
+      }
+    } else {
+      for (uint32_t r = q; r < n; ++r) {
+        const uint32_t s = perm[r];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          if (a < na) dst.p[a][r] = src.p[a][s];
+        }
       }
     }
   }
@@ -98,7 +116,7 @@ namespace eb200 {
         src.p[a] = arrs[a0 + a];
         dst.p[a] = (uint32_t*)(tmp + (size_t)a * stride);
       }
-      gather4_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, m, perm, n);
+      gather4_kernel<<<(n / 4 + 1 + 255) / 256, 256, 0, st>>>(src, dst, m, perm, n);
       count_launch();
       for (int a = 0; a < m; ++a) {
         cudaMemcpyAsync(src.p[a], dst.p[a], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
