@@ -30,6 +30,7 @@ UNITS = [
     ("fields.cu", "fast", ["-DEB200_STRICT=0"]),
     ("curv.cu", "one", ["--fmad=false"]),
     ("sort.cu", "one", []),
+    ("stats.cu", "one", ["--fmad=false"]),
     ("comm.cu", "one", []),
     ("engine.cu", "one", []),
     ("capi.cu", "one", []),

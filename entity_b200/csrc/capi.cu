@@ -46,6 +46,7 @@ struct eb200_ctx {
   uint64_t       launches_at_init;
   int            pd_kernel = 0; // eb200_set_pd_kernel
   eb200::Scratch packed;        // E/B repacked node by node for the fused 2D zig-zag kernel
+  eb200::Scratch stats;         // one double: the device-side accumulator of the reductions
   const float*   packed_hold = nullptr; // em the packed copy is guaranteed current for
   bool           no_filter_fusion = false; // EB200_NO_FILTER_FUSION=1: pass-by-pass filter
   eb200::MetricParams metric {}; // curvilinear / GR contexts
@@ -229,6 +230,7 @@ void eb200_finalize(eb200_ctx_t* ctx) {
   cudaSetDevice(ctx->cfg.device);
   ctx->scratch.release();
   ctx->packed.release();
+  ctx->stats.release();
   if (ctx->comm) eb200::comm_delete(ctx->comm);
   eb200::engine_state_delete(ctx->engine);
   delete ctx;
@@ -539,6 +541,57 @@ int eb200_pack_fields_hold(eb200_ctx_t* ctx, const float* em, eb200_stream_t str
   if (rc) return rc;
   ctx->packed_hold = em;
   return EB200_OK;
+}
+
+static int stats_finish(eb200_ctx_t* ctx, cudaError_t e, double* out_host, cudaStream_t st,
+                        const char* what) {
+  if (e != cudaSuccess) return check_cuda(ctx, e, what);
+  e = cudaMemcpyAsync(out_host, ctx->stats.ptr, sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return check_cuda(ctx, e, what);
+  return check_cuda(ctx, cudaStreamSynchronize(st), what);
+}
+
+int eb200_stats_fields(eb200_ctx_t* ctx, const float* em, const float* cur, int what, int comp,
+                       double* out_host, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE_MINK(ctx, "eb200_stats_fields");
+  REQUIRE(ctx, em != nullptr && out_host != nullptr, "null argument");
+  REQUIRE(ctx, what >= EB200_STATS_B2 && what <= EB200_STATS_JDOTE, "unknown field statistic");
+  REQUIRE(ctx, what == EB200_STATS_JDOTE || (comp >= 1 && comp <= 3), "component must be 1..3");
+  REQUIRE(ctx, what != EB200_STATS_JDOTE || cur != nullptr, "J.E needs cur");
+  const float dx = ctx->cfg.metric_params[0];
+  REQUIRE(ctx, dx > 0.0f, "metric_params[0] (dx) must be positive");
+  int rc = check_cuda(ctx, ctx->stats.reserve(256), "stats scratch");
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  return stats_finish(ctx, eb200::stats_fields(ctx->cfg.grid, em, cur, dx, what, comp,
+                                               (double*)ctx->stats.ptr, st),
+                      out_host, st, "stats_fields");
+}
+
+int eb200_stats_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, float mass,
+                          float charge, int use_weights, int what, int c1, int c2,
+                          double* out_host, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE_MINK(ctx, "eb200_stats_particles");
+  REQUIRE(ctx, out_host != nullptr, "null argument");
+  REQUIRE(ctx, what >= EB200_STATS_NPART && what <= EB200_STATS_T, "unknown particle statistic");
+  REQUIRE(ctx, what != EB200_STATS_T || (c1 >= 0 && c1 <= 3 && c2 >= 0 && c2 <= 3),
+          "stress-energy components must be 0..3");
+  // reduced_stats.hpp:428-431
+  REQUIRE(ctx, !((what == EB200_STATS_RHO || what == EB200_STATS_CHARGE) && mass == 0.0f),
+          "Rho & Charge for massless particles not defined");
+  int rc = check_prtls(ctx, prtls, npart);
+  if (rc) return rc;
+  const float dx = ctx->cfg.metric_params[0];
+  REQUIRE(ctx, dx > 0.0f, "metric_params[0] (dx) must be positive");
+  rc = check_cuda(ctx, ctx->stats.reserve(256), "stats scratch");
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  return stats_finish(ctx, eb200::stats_particles(ctx->cfg.grid, *prtls, npart, mass, charge,
+                                                  use_weights, dx, what, c1, c2,
+                                                  (double*)ctx->stats.ptr, st),
+                      out_host, st, "stats_particles");
 }
 
 int eb200_pack_fields_release(eb200_ctx_t* ctx) {

@@ -49,6 +49,13 @@ namespace eb200 {
     }
   };
 
+  // stats.cu (compiled once): reduced statistics of a Minkowski domain
+  cudaError_t stats_fields(const eb200_grid_t& g, const float* em, const float* cur, float dx,
+                           int what, int comp, double* out_dev, cudaStream_t st);
+  cudaError_t stats_particles(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
+                              float mass, float charge, int use_weights, float dx, int what, int c1,
+                              int c2, double* out_dev, cudaStream_t st);
+
 #define EB200_DECLARE_VARIANT(NS)                                                              \
   namespace NS {                                                                               \
     cudaError_t push_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,            \

@@ -12,6 +12,8 @@ DRAG_NONE, DRAG_SYNCHROTRON, DRAG_COMPTON = 0, 1, 2
 PBC_NONE, PBC_PERIODIC, PBC_ABSORB, PBC_REFLECT, PBC_AXIS = 0, 1, 2, 3, 4
 FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC = 0, 1, 2, 3, 4
 DEPOSIT_ATOMIC, DEPOSIT_ORDERED, DEPOSIT_AGGREGATED = 0, 1, 2
+STATS_B2, STATS_E2, STATS_EXB, STATS_JDOTE = 0, 1, 2, 3
+STATS_NPART, STATS_N, STATS_RHO, STATS_CHARGE, STATS_T = 0, 1, 2, 3, 4
 
 PHASES = ["FieldSolver", "PushDeposit", "CurrentFiltering", "Communications", "ParticleSort",
           "ParticleMigration"]
@@ -185,6 +187,16 @@ def load():
                                           C.c_int, C.c_uint32, C.c_double,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.eb200_srpic_step_host.restype = C.c_int
+    lib.eb200_stats_fields.argtypes = [ctxp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_double), vp]
+    lib.eb200_stats_fields.restype = C.c_int
+    lib.eb200_stats_particles.argtypes = [ctxp, C.POINTER(Prtls), C.c_uint32, C.c_float, C.c_float,
+                                          C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_double), vp]
+    lib.eb200_stats_particles.restype = C.c_int
+    lib.eb200_pack_fields_hold.argtypes = [ctxp, vp, vp]
+    lib.eb200_pack_fields_hold.restype = C.c_int
+    lib.eb200_pack_fields_release.argtypes = [ctxp]
+    lib.eb200_pack_fields_release.restype = C.c_int
     lib.eb200_decompose.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p]
     lib.eb200_domain_info.argtypes = [C.POINTER(MetadomainC), C.POINTER(DomainInfoC)]
     lib.eb200_comm_unique_id.argtypes = [C.c_char_p]
@@ -463,6 +475,23 @@ class Context:
         self._check(self.lib.eb200_push_deposit_sr(self.handle, C.byref(pusher), C.byref(s),
                                                    npart, _ptr(em), _ptr(cur), mode,
                                                    self._stream(stream)))
+
+    # -- reduced statistics (reduced_stats.hpp): local sums, host values
+    def stats_fields(self, em, cur, what, comp=1, stream=None) -> float:
+        out = C.c_double(0.0)
+        self._check(self.lib.eb200_stats_fields(self.handle, _ptr(em),
+                                                _ptr(cur) if cur is not None else None, what, comp,
+                                                C.byref(out), self._stream(stream)))
+        return out.value
+
+    def stats_particles(self, arrays, npart, mass, charge, what, c1=0, c2=0, use_weights=False,
+                        stream=None) -> float:
+        out = C.c_double(0.0)
+        s = self.prtls_struct(arrays)
+        self._check(self.lib.eb200_stats_particles(self.handle, C.byref(s), npart, mass, charge,
+                                                   1 if use_weights else 0, what, c1, c2,
+                                                   C.byref(out), self._stream(stream)))
+        return out.value
 
     def zero_currents(self, cur, stream=None):
         self._check(self.lib.eb200_zero_currents(self.handle, _ptr(cur), self._stream(stream)))

@@ -260,6 +260,29 @@ int eb200_comm_init(eb200_ctx_t* ctx, const eb200_metadomain_t* md, const char* 
 int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls,
                          uint32_t* npart_inout_host, int remove_dead, eb200_stream_t stream);
 
+/* ------------------------------------------------------------- reduced statistics */
+/* kernel::ReducedFields_kernel (src/kernels/reduced_stats.hpp:25-386) through ReduceFields
+ * (src/framework/domain/metadomain_stats.cpp:128-183), Minkowski 1D/2D/3D: the sum over the
+ * active cells of this domain of B_I^2, E_I^2, (E x B)_I (I = comp, 1..3) or J.E, each term
+ * evaluated as the reference does (cell-centred averages, tetrad components, sqrt(det h)).
+ * Returns the LOCAL sum (before the MPI reduction and the division by totVolume the reference's
+ * stats writer applies). Synchronises the stream: the result is a host value, as the
+ * reference's parallel_reduce. cur may be NULL unless what == EB200_STATS_JDOTE. */
+enum { EB200_STATS_B2 = 0, EB200_STATS_E2 = 1, EB200_STATS_EXB = 2, EB200_STATS_JDOTE = 3 };
+int eb200_stats_fields(eb200_ctx_t* ctx, const float* em, const float* cur, int what, int comp,
+                       double* out_host, eb200_stream_t stream);
+/* kernel::ReducedParticleMoments_kernel (reduced_stats.hpp:400-536) through ComputeMoments
+ * (metadomain_stats.cpp:72-126) for ONE species of a Minkowski domain: Npart (alive count), N,
+ * Rho, Charge (sum of dV * (use_weights ? weight : 1 | mass | charge)) or the stress-energy
+ * component T^{c1 c2} (c = 0: energy, 1..3: u_c; sum of dV * coeff / energy -- the reference
+ * applies no weight there). LOCAL sum of one species; the caller adds species and normalises by
+ * totVolume * ppc0 as ComputeMoments does. Synchronises the stream. */
+enum { EB200_STATS_NPART = 0, EB200_STATS_N = 1, EB200_STATS_RHO = 2, EB200_STATS_CHARGE = 3,
+       EB200_STATS_T = 4 };
+int eb200_stats_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, float mass,
+                          float charge, int use_weights, int what, int c1, int c2,
+                          double* out_host, eb200_stream_t stream);
+
 /* ------------------------------------------------------------- whole SRPIC step */
 /* One species as the engine sees it: ntt::ParticleSpecies (src/framework/containers/species.h)
  * + the SoA arrays + the live particle count. */
