@@ -31,6 +31,7 @@ UNITS = [
     ("curv.cu", "one", ["--fmad=false"]),
     ("sort.cu", "one", []),
     ("stats.cu", "one", ["--fmad=false"]),
+    ("bcs.cu", "one", ["--fmad=false"]),
     ("comm.cu", "one", []),
     ("engine.cu", "one", []),
     ("capi.cu", "one", []),

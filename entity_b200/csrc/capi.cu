@@ -543,6 +543,30 @@ int eb200_pack_fields_hold(eb200_ctx_t* ctx, const float* em, eb200_stream_t str
   return EB200_OK;
 }
 
+int eb200_match_fields(eb200_ctx_t* ctx, float* em, const float* target, int o, float xg_edge,
+                       float ds, int tags, int components_mask, const int* range_min,
+                       const int* range_max, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE_MINK(ctx, "eb200_match_fields");
+  REQUIRE(ctx, em != nullptr && target != nullptr && range_min != nullptr && range_max != nullptr,
+          "null argument");
+  const eb200_grid_t& g = ctx->cfg.grid;
+  REQUIRE(ctx, o >= 0 && o < g.dim, "matching direction outside the simulated dimensions");
+  REQUIRE(ctx, ds > 0.0f, "match: ds must be positive");
+  REQUIRE(ctx, (tags & ~(EB200_BC_E | EB200_BC_B)) == 0, "match: tags = EB200_BC_E | EB200_BC_B");
+  for (int a = 0; a < g.dim; ++a) {
+    REQUIRE(ctx, range_min[a] >= 0 && range_max[a] <= g.n[a] + 2 * g.ng,
+            "match: range outside the array");
+  }
+  const float dx = ctx->cfg.metric_params[0];
+  REQUIRE(ctx, dx > 0.0f, "metric_params[0] (dx) must be positive");
+  return check_cuda(ctx,
+                    eb200::match_fields(g, em, target, o, dx, ctx->cfg.metric_params[1 + o], xg_edge,
+                                        ds, tags, components_mask & 63, range_min, range_max,
+                                        (cudaStream_t)stream),
+                    "match_fields");
+}
+
 static int stats_finish(eb200_ctx_t* ctx, cudaError_t e, double* out_host, cudaStream_t st,
                         const char* what) {
   if (e != cudaSuccess) return check_cuda(ctx, e, what);

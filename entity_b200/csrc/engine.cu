@@ -75,6 +75,10 @@ namespace eb200 {
   struct EngineState {
     Profiler   prof;
     HostMirror mirror;
+    // MATCH faces applied by srpic::FieldBoundaries inside the step (eb200_srpic_set_match)
+    std::vector<eb200_match_face_t> match;
+    const float*                    match_target = nullptr;
+    int                             match_mask   = 0;
   };
 
   struct PhaseScope {
@@ -117,6 +121,7 @@ namespace eb200 {
       eb200_stream_t              stream;
       Profiler*                   prof;
       HostStreamer*               host = nullptr; // non-null: particle arrays stream from/to the host
+      const EngineState*          eng  = nullptr; // MATCH faces, if any
     };
 
 #define PHASE(dom, which) PhaseScope phase_scope_((dom).prof, (which), (cudaStream_t)(dom).stream)
@@ -329,20 +334,39 @@ namespace eb200 {
       return EB200_OK;
     }
 
+    // srpic::FieldBoundaries (fields_bcs.h:600-672) for the MATCH faces registered with the
+    // context; the other kinds (CONDUCTOR inside the filter / field kernels, PERIODIC and SYNC
+    // inside the exchanges) are handled where the data moves
+    int FieldBoundaries(Domain& dom, int tags) {
+      if (!dom.eng || dom.eng->match.empty()) return EB200_OK;
+      PHASE(dom, EB200_PHASE_FIELDSOLVER);
+      for (const eb200_match_face_t& f : dom.eng->match) {
+        TRY(eb200_match_fields(dom.ctx, dom.em, dom.eng->match_target, f.o, f.xg_edge, f.ds, tags,
+                               dom.eng->match_mask, f.range_min, f.range_max, dom.stream));
+      }
+      return EB200_OK;
+    }
+
     // SRPICEngine::step_forward, srpic.hpp:65-188
     int step_forward(Domain& dom, uint32_t step, double time) {
       const eb200_srpic_params_t& p = *dom.prm;
       if (step == 0) {
-        PHASE(dom, EB200_PHASE_COMM);
-        TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 0, 6, p.fbc, dom.stream));
+        {
+          PHASE(dom, EB200_PHASE_COMM);
+          TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 0, 6, p.fbc, dom.stream));
+        }
+        TRY(FieldBoundaries(dom, EB200_BC_B | EB200_BC_E));
       }
       if (p.fieldsolver_enabled) {
         {
           PHASE(dom, EB200_PHASE_FIELDSOLVER);
           TRY(Faraday(dom, 0.5f));
         }
-        PHASE(dom, EB200_PHASE_COMM);
-        TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 3, 6, p.fbc, dom.stream));
+        {
+          PHASE(dom, EB200_PHASE_COMM);
+          TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 3, 6, p.fbc, dom.stream));
+        }
+        TRY(FieldBoundaries(dom, EB200_BC_B));
       }
       {
         PHASE(dom, EB200_PHASE_PUSH_DEPOSIT);
@@ -379,6 +403,7 @@ namespace eb200 {
           PHASE(dom, EB200_PHASE_COMM);
           TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 3, 6, p.fbc, dom.stream));
         }
+        TRY(FieldBoundaries(dom, EB200_BC_B));
         {
           PHASE(dom, EB200_PHASE_FIELDSOLVER);
           TRY(Ampere(dom, 1.0f));
@@ -386,9 +411,12 @@ namespace eb200 {
             TRY(CurrentsAmpere(dom));
           }
         }
-        PHASE(dom, EB200_PHASE_COMM);
-        TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 0, 3, p.fbc, dom.stream));
-        TRY(eb200_comm_fields(dom.ctx, dom.cur, 3, 0, 3, p.fbc, dom.stream));
+        {
+          PHASE(dom, EB200_PHASE_COMM);
+          TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 0, 3, p.fbc, dom.stream));
+          TRY(eb200_comm_fields(dom.ctx, dom.cur, 3, 0, 3, p.fbc, dom.stream));
+        }
+        TRY(FieldBoundaries(dom, EB200_BC_E));
       }
       {
         PHASE(dom, EB200_PHASE_SORT);
@@ -418,6 +446,7 @@ extern "C" int eb200_srpic_step(eb200_ctx_t* ctx, const eb200_srpic_params_t* pr
   dom.nspecies = nspecies;
   dom.stream   = stream;
   dom.prof     = &eb200_ctx_engine_state(ctx)->prof;
+  dom.eng      = eb200_ctx_engine_state(ctx);
   return eb200::srpic::step_forward(dom, step, time);
 }
 
@@ -436,6 +465,16 @@ namespace eb200 {
     delete e;
   }
 } // namespace eb200
+
+extern "C" int eb200_srpic_set_match(eb200_ctx_t* ctx, const eb200_match_face_t* faces, int nfaces,
+                                     const float* target, int components_mask) {
+  if (!ctx || nfaces < 0 || (nfaces > 0 && (!faces || !target))) return EB200_ERR_ARG;
+  eb200::EngineState* e = eb200_ctx_engine_state(ctx);
+  e->match.assign(faces, faces + nfaces);
+  e->match_target = nfaces > 0 ? target : nullptr;
+  e->match_mask   = components_mask;
+  return EB200_OK;
+}
 
 extern "C" int eb200_profile_enable(eb200_ctx_t* ctx, int on) {
   if (!ctx) return EB200_ERR_ARG;
@@ -546,6 +585,7 @@ extern "C" int eb200_srpic_step_host(eb200_ctx_t* ctx, const eb200_srpic_params_
       dom.nspecies = nspecies;
       dom.stream   = m.main;
       dom.prof     = &eb200_ctx_engine_state(ctx)->prof;
+      dom.eng      = eb200_ctx_engine_state(ctx);
       dom.host     = &H;
       int rc = eb200::srpic::step_forward(dom, step, time);
       if (rc == EB200_OK) {

@@ -49,6 +49,10 @@ namespace eb200 {
     }
   };
 
+  // bcs.cu (compiled once, --fmad=false): matching field boundaries
+  cudaError_t match_fields(const eb200_grid_t& g, float* em, const float* target, int o, float dx,
+                           float xmin_o, float xg_edge, float ds, int tags, int mask,
+                           const int* rmin, const int* rmax, cudaStream_t st);
   // stats.cu (compiled once): reduced statistics of a Minkowski domain
   cudaError_t stats_fields(const eb200_grid_t& g, const float* em, const float* cur, float dx,
                            int what, int comp, double* out_dev, cudaStream_t st);

@@ -13,6 +13,7 @@ PBC_NONE, PBC_PERIODIC, PBC_ABSORB, PBC_REFLECT, PBC_AXIS = 0, 1, 2, 3, 4
 FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC = 0, 1, 2, 3, 4
 DEPOSIT_ATOMIC, DEPOSIT_ORDERED, DEPOSIT_AGGREGATED = 0, 1, 2
 STATS_B2, STATS_E2, STATS_EXB, STATS_JDOTE = 0, 1, 2, 3
+BC_E, BC_B = 1, 2
 STATS_NPART, STATS_N, STATS_RHO, STATS_CHARGE, STATS_T = 0, 1, 2, 3, 4
 
 PHASES = ["FieldSolver", "PushDeposit", "CurrentFiltering", "Communications", "ParticleSort",
@@ -94,6 +95,11 @@ class SpeciesC(C.Structure):
     _fields_ = [("mass", C.c_float), ("charge", C.c_float), ("pusher_flags", C.c_int),
                 ("drag_flags", C.c_int), ("npart", C.c_uint32), ("maxnpart", C.c_uint32),
                 ("arrays", Prtls)]
+
+
+class MatchFaceC(C.Structure):
+    _fields_ = [("o", C.c_int), ("xg_edge", C.c_float), ("ds", C.c_float),
+                ("range_min", C.c_int * 3), ("range_max", C.c_int * 3)]
 
 
 class ParamsC(C.Structure):
@@ -187,6 +193,11 @@ def load():
                                           C.c_int, C.c_uint32, C.c_double,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.eb200_srpic_step_host.restype = C.c_int
+    lib.eb200_match_fields.argtypes = [ctxp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                       i32p, i32p, vp]
+    lib.eb200_match_fields.restype = C.c_int
+    lib.eb200_srpic_set_match.argtypes = [ctxp, C.POINTER(MatchFaceC), C.c_int, vp, C.c_int]
+    lib.eb200_srpic_set_match.restype = C.c_int
     lib.eb200_stats_fields.argtypes = [ctxp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_double), vp]
     lib.eb200_stats_fields.restype = C.c_int
     lib.eb200_stats_particles.argtypes = [ctxp, C.POINTER(Prtls), C.c_uint32, C.c_float, C.c_float,
@@ -475,6 +486,14 @@ class Context:
         self._check(self.lib.eb200_push_deposit_sr(self.handle, C.byref(pusher), C.byref(s),
                                                    npart, _ptr(em), _ptr(cur), mode,
                                                    self._stream(stream)))
+
+    # -- matching field boundaries (fields_bcs.hpp MatchBoundaries_kernel)
+    def match_fields(self, em, target, o, xg_edge, ds, tags, mask, range_min, range_max, stream=None):
+        d = len(range_min)
+        lo, hi = (C.c_int * 3)(*(list(range_min) + [0] * (3 - d))), \
+            (C.c_int * 3)(*(list(range_max) + [1] * (3 - d)))
+        self._check(self.lib.eb200_match_fields(self.handle, _ptr(em), _ptr(target), o, xg_edge, ds,
+                                                tags, mask, lo, hi, self._stream(stream)))
 
     # -- reduced statistics (reduced_stats.hpp): local sums, host values
     def stats_fields(self, em, cur, what, comp=1, stream=None) -> float:

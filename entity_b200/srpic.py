@@ -103,6 +103,20 @@ class Simulation:
     def dt(self):
         return self.scales["dt"]
 
+    def set_match(self, faces, target, mask=63):
+        """MATCH field boundaries inside the step (srpic::FieldBoundaries): faces = list of
+        (o, xg_edge, ds, range_min, range_max); target = device tensor in the layout of em with
+        the MatchFields values on every component's node. The tensors are kept alive here."""
+        arr = (L.MatchFaceC * max(1, len(faces)))()
+        d = self.dim
+        for k, (o, xg_edge, ds, rmin, rmax) in enumerate(faces):
+            arr[k].o, arr[k].xg_edge, arr[k].ds = o, xg_edge, ds
+            arr[k].range_min = (C.c_int * 3)(*(list(rmin) + [0] * (3 - d)))
+            arr[k].range_max = (C.c_int * 3)(*(list(rmax) + [1] * (3 - d)))
+        self._match = (arr, target, list(faces), mask)
+        self.ctx._check(self.ctx.lib.eb200_srpic_set_match(
+            self.ctx.handle, arr, len(faces), target.data_ptr() if len(faces) else None, mask))
+
     def add_species(self, mass, charge, arrays: dict, npart: int, pusher=L.PUSHER_BORIS,
                     maxnpart=None):
         """arrays: name -> torch tensor on this device (capacity = maxnpart)."""

@@ -260,6 +260,22 @@ int eb200_comm_init(eb200_ctx_t* ctx, const eb200_metadomain_t* md, const char* 
 int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls,
                          uint32_t* npart_inout_host, int remove_dead, eb200_stream_t stream);
 
+/* ------------------------------------------------------------- field boundaries */
+/* kernel::bc::MatchBoundaries_kernel<SRPIC, Minkowski<D>, FS, o> (src/kernels/fields_bcs.hpp:
+ * 42-560) as launched by srpic::MatchFieldsIn (src/engines/srpic/fields_bcs.h:38-215) over the
+ * ghost-inclusive index range [range_min, range_max) that Mesh::ExtentToRange gives it:
+ *   F = s F + (1 - s) transform<T->U>(target),  s = tanh(|x_o - xg_edge| 4 / ds)
+ * per component, at that component's staggered node. `target` (6 component planes, layout of em)
+ * holds the values of the problem generator's MatchFields functor at those nodes (tetrad basis):
+ * the functor itself cannot cross a C ABI, the host evaluates it (once, or per step when it
+ * depends on time). components_mask: bit c set = the functor defines component c (ex1, ex2, ex3,
+ * bx1, bx2, bx3): the reference skips what the functor lacks. tags: EB200_BC_E | EB200_BC_B
+ * (BC::E / BC::B, src/global/enums.h). o = matching direction (0, 1, 2). */
+enum { EB200_BC_E = 1, EB200_BC_B = 2 };
+int eb200_match_fields(eb200_ctx_t* ctx, float* em, const float* target, int o, float xg_edge,
+                       float ds, int tags, int components_mask, const int* range_min,
+                       const int* range_max, eb200_stream_t stream);
+
 /* ------------------------------------------------------------- reduced statistics */
 /* kernel::ReducedFields_kernel (src/kernels/reduced_stats.hpp:25-386) through ReduceFields
  * (src/framework/domain/metadomain_stats.cpp:128-183), Minkowski 1D/2D/3D: the sum over the
@@ -323,6 +339,20 @@ typedef struct {
 int eb200_srpic_step(eb200_ctx_t* ctx, const eb200_srpic_params_t* prm, float* em, float* cur,
                      float* buff, eb200_species_t* species, int nspecies, uint32_t step,
                      double time, eb200_stream_t stream);
+
+/* srpic::FieldBoundaries with MATCH faces inside eb200_srpic_step (src/engines/srpic/srpic.hpp:
+ * 74-80, 93-101, 144-152, 168-176; src/engines/srpic/fields_bcs.h:38-215): the faces registered
+ * here are matched (eb200_match_fields, in the order given) for B after each Faraday half-step's
+ * exchange, for E after the Ampere / CurrentsAmpere exchange, and for both at step 0. `target`
+ * and the face table are borrowed until the next call (nfaces = 0 clears them); faces of a
+ * matched dimension carry EB200_FBC_NONE in eb200_srpic_params_t.fbc. */
+typedef struct {
+  int   o;                          /* matching direction */
+  float xg_edge, ds;                /* edge of the global box on that side, layer thickness */
+  int   range_min[3], range_max[3]; /* ghost-inclusive cell range of the layer in this domain */
+} eb200_match_face_t;
+int eb200_srpic_set_match(eb200_ctx_t* ctx, const eb200_match_face_t* faces, int nfaces,
+                          const float* target, int components_mask);
 
 /* Metadomain::CommunicateParticles + Particles::Communicate for all species in one round
  * (metadomain_comm.cpp:565-653, particles_comm.cpp:180-389, kernels/comm.hpp): particles

@@ -32,6 +32,17 @@ class OracleSim:
         self.species = []  # dicts: mass, charge, pusher, prtls(ParticleSet), npart
         self.step_index = 0
         self.time = 0.0
+        self.match = None  # (faces, target, mask): MATCH field boundaries (oracle/bcs.py)
+
+    # srpic::FieldBoundaries for MATCH faces (src/engines/srpic/fields_bcs.h:38-215, 600-672)
+    def _field_boundaries(self, tags):
+        if not self.match:
+            return
+        from . import bcs
+        faces, target, mask = self.match
+        for o, xg_edge, ds, rmin, rmax in faces:
+            bcs.match_fields(self.grid, self.em, target, o, self.dx, self.xmin[o], xg_edge, ds,
+                             tags, mask, rmin, rmax)
 
     def add_species(self, mass, charge, prtls: orc.ParticleSet, npart, pusher=orc.PUSHER_BORIS):
         self.species.append(dict(mass=mass, charge=charge, pusher=pusher, prtls=prtls, npart=npart))
@@ -49,9 +60,11 @@ class OracleSim:
         dt = f32(s["dt"])
         if self.step_index == 0:
             im.comm_fields(g, self.em, 0, 6, self.fbc)
+            self._field_boundaries(3)
         c1, c2 = self._coeffs(0.5)
         im.faraday(g, self.em, c1, c2, None)
         im.comm_fields(g, self.em, 3, 6, self.fbc)
+        self._field_boundaries(2)  # BC::B (srpic.hpp:93-101)
         for sp in self.species:
             if sp["pusher"] == orc.PUSHER_NONE or sp["npart"] == 0:
                 continue
@@ -73,12 +86,14 @@ class OracleSim:
             im.comm_fields(g, self.cur, 0, 3, self.fbc)
         im.faraday(g, self.em, c1, c2, None)
         im.comm_fields(g, self.em, 3, 6, self.fbc)
+        self._field_boundaries(2)  # BC::B (srpic.hpp:144-152)
         c1, c2 = self._coeffs(1.0)
         im.ampere(g, self.em, c1, c2)
         coeff = -dt * f32(s["q0"]) / (f32(s["B0"]) * f32(s["V0"]))
         im.currents_ampere(g, self.em, self.cur, coeff, f32(s["ppc0"]))
         im.comm_fields(g, self.em, 0, 3, self.fbc)
         im.comm_fields(g, self.cur, 0, 3, self.fbc)
+        self._field_boundaries(1)  # BC::E (srpic.hpp:168-176)
         self.step_index += 1
         self.time += float(dt)
 
@@ -96,6 +111,8 @@ def from_device_sim(sim, impl=None) -> OracleSim:
     o.em[...] = sim.em.cpu().numpy()
     o.cur[...] = sim.cur.cpu().numpy()
     o.step_index, o.time = sim.step_index, sim.time
+    if getattr(sim, "_match", None) and sim._match[2]:
+        o.match = (sim._match[2], sim._match[1].cpu().numpy(), sim._match[3])
     for sp in sim.species:
         cap = sp.maxnpart
         ps = orc.ParticleSet(cap)

@@ -188,3 +188,46 @@ def test_step_host_streamed_matches_device(mods, chunk, monkeypatch):
         assert np.array_equal(np.sort(sp.arrays["weight"][:n].cpu().numpy()), np.sort(spec["weight"][:n].numpy()))
         ua, ub = sp.arrays["ux1"][:n].cpu().numpy(), spec["ux1"][:n].numpy()
         assert abs(float(ua.astype(np.float64).sum()) - float(ub.astype(np.float64).sum())) <= 1e-3 * np.abs(ua).sum()
+
+
+def test_step_with_match_boundaries(mods):
+    """Whole steps with the reconnection configuration's boundaries in x2 (fields MATCH,
+    particles ABSORB; pgens/reconnection/reconnection.toml) against the oracle stepper with the
+    same MATCH layers (oracle/bcs.py, pinned to the reference's MatchBoundaries_kernel): strict
+    build + ordered deposit. Everything but tanh is the same fp32 operation sequence: fields and
+    currents within 2e-6 of their maxima, particle counts (absorption) identical every step."""
+    eb, wl, orc, pic = mods
+    import torch
+    from entity_b200.srpic import Scales, Simulation
+    n, G, dx = (48, 40), 2, 0.25
+    fbc = [eb.FBC_PERIODIC, eb.FBC_PERIODIC, eb.FBC_NONE, eb.FBC_NONE, 0, 0]
+    pbc = [eb.PBC_PERIODIC, eb.PBC_PERIODIC, eb.PBC_ABSORB, eb.PBC_ABSORB, 0, 0]
+    base = wl.two_stream(n, ppc0=8, strict=True, deposit_mode=eb.DEPOSIT_ORDERED)
+    sim = Simulation(n, 0, Scales(2, base.ctx.dx, 100.0, 10.0, 8), nfilter=2, strict=True,
+                     deposit_mode=eb.DEPOSIT_ORDERED, fbc=fbc, pbc=pbc, xmin=(0.0, -5.0, 0.0))
+    for sp in base.species:
+        sp.arrays["ux2"].mul_(30.0)  # fast enough along x2 for some to reach the absorbing walls
+        sim.add_species(sp.mass, sp.charge, sp.arrays, sp.npart, sp.pusher)
+    dx = sim.ctx.dx
+    # target: uniform guide field B_x1 = 0.2 (tetrad), nothing else; both x2 faces, 6 cells thick
+    target = torch.zeros_like(sim.em)
+    target[3] = 0.2
+    sim.em[3] = 0.2 / dx
+    nds, ext = 6, [n[0] + 2 * G, n[1] + 2 * G]
+    ymin, ymax = -5.0, float(np.float32(-5.0) + np.float32(dx) * np.float32(n[1]))
+    faces = [(1, ymin, nds * dx, [0, 0], [ext[0], G + nds]),
+             (1, ymax, nds * dx, [0, G + n[1] - nds], [ext[0], ext[1]])]
+    sim.set_match(faces, target, 63)
+    osim = pic.from_device_sim(sim)
+    n0 = sum(s.npart for s in sim.species)
+    for step in range(8):
+        sim.step()
+        osim.step()
+        alive = sum(int((s.arrays["tag"][:s.npart] == 1).sum()) for s in sim.species)
+        oalive = sum(int((s["prtls"].tag[:s["npart"]] == 1).sum()) for s in osim.species)
+        assert alive == oalive, f"alive particles differ at step {step}"
+        e, eo = sim.em.cpu().numpy(), osim.em
+        j, jo = sim.cur.cpu().numpy(), osim.cur
+        assert np.abs(e - eo).max() <= 2e-6 * np.abs(eo).max(), f"EM at step {step}"
+        assert np.abs(j - jo).max() <= 2e-6 * np.abs(jo).max() + 1e-12, f"J at step {step}"
+    assert alive < n0, "no particle reached the absorbing walls: the case does not test them"
