@@ -226,6 +226,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from entity_b200 import workloads
+    if args.walls and world > 1:
+        raise SystemExit("bench.py --walls: single-GPU variant (the multi-domain bench tiles a periodic box)")
 
     size = tuple(args.size)
     import entity_b200 as eb
@@ -233,7 +235,7 @@ def run_ours(args):
              "ordered": eb.DEPOSIT_ORDERED}[args.deposit]
     sim = workloads.reconnection(size, ppc0=args.ppc, nfilter=args.filters, fused=not args.unfused,
                                  sort_interval=args.sort_interval, device=local,
-                                 deposit_mode=dmode, seed=0x5678 + rank,
+                                 deposit_mode=dmode, seed=0x5678 + rank, walls=args.walls,
                                  capacity_factor=1.0 if world == 1 else 1.1)
     decomposition = [1, 1]
     if world > 1:
@@ -330,8 +332,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if size == (4096, 2048) and args.ppc == 32 else
-                       f"reconnection 2D {size[0]}x{size[1]} cells, {args.ppc} ppc (reduced)",
+            "config": {"workload": (WORKLOAD if size == (4096, 2048) and args.ppc == 32 else
+                                    f"reconnection 2D {size[0]}x{size[1]} cells, {args.ppc} ppc (reduced)")
+                       + (" [x2 walls: fields MATCH ds=20, particles ABSORB, no injector]"
+                          if args.walls else ""),
                        "cells_per_gpu": list(size), "ppc0": args.ppc, "shape_order": 0,
                        "current_filters": args.filters, "particles_per_gpu": n_pushed0,
                        "fused_push_deposit": not args.unfused, "sort_interval": args.sort_interval,
@@ -381,6 +385,9 @@ def main():
     ap.add_argument("--sort-interval", type=int, default=40)
     ap.add_argument("--deposit", default="aggregated", choices=["atomic", "aggregated", "ordered"])
     ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--walls", action="store_true",
+                    help="x2 boundaries of reconnection.toml (fields MATCH, particles ABSORB) instead "
+                         "of the periodic core; single GPU, no replenishing injector")
     ap.add_argument("--decomp", type=int, nargs=2, default=None,
                     help="override the block decomposition request (default -1 2, as reconnection.toml)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -102,7 +102,7 @@ def two_stream(n=(256, 256), ppc0=64, nfilter=4, seed=0x1234, **kw) -> Simulatio
 
 
 def reconnection(n=(4096, 2048), ppc0=32, nfilter=8, seed=0x5678, sheets=True,
-                 capacity_factor=1.0, **kw) -> Simulation:
+                 capacity_factor=1.0, walls=False, **kw) -> Simulation:
     """configs[1]: 2D pair-plasma Harris sheet(s), periodic-core variant. The box is doubly
     periodic, so a multi-domain run tiles it: every block of `n` cells holds the same two
     sheets (own seed) and the global plasma is an array of Harris sheets. `capacity_factor`
@@ -111,6 +111,11 @@ def reconnection(n=(4096, 2048), ppc0=32, nfilter=8, seed=0x5678, sheets=True,
     Lx = 1000.0 * (n[0] / 4096.0)
     dx = Lx / n[0]
     Ly = dx * n[1]
+    if walls:
+        # the x2 boundaries of pgens/reconnection/reconnection.toml:16-21: fields MATCH (to the
+        # initial profile, ds = 20), particles ABSORB; no replenishing injector
+        kw.setdefault("fbc", [L.FBC_PERIODIC, L.FBC_PERIODIC, L.FBC_NONE, L.FBC_NONE, 0, 0])
+        kw.setdefault("pbc", [L.PBC_PERIODIC, L.PBC_PERIODIC, L.PBC_ABSORB, L.PBC_ABSORB, 0, 0])
     sim = Simulation(n, 0, Scales(2, dx, larmor0=0.1, skindepth0=1.0, ppc0=ppc0), nfilter=nfilter,
                      xmin=(-0.5 * Lx, -0.5 * Ly, 0.0), **kw)
     torch = sim.torch
@@ -122,6 +127,17 @@ def reconnection(n=(4096, 2048), ppc0=32, nfilter=8, seed=0x5678, sheets=True,
     y = (jj + 0.5) * dx - 0.5 * Ly
     bx = torch.tanh((y - y1) / cs_width) - torch.tanh((y - y2) / cs_width) - 1.0
     sim.em[3] = (bx / dx)[:, None].expand(-1, g.n[0] + 2 * g.ng)
+    if walls:
+        import numpy as np
+        target = torch.zeros_like(sim.em)
+        target[3] = bx[:, None].expand(-1, g.n[0] + 2 * g.ng)  # tetrad components
+        ds = 20.0 * (n[0] / 4096.0)
+        nds = max(1, int(round(ds / dx)))
+        ext = [g.n[0] + 2 * g.ng, g.n[1] + 2 * g.ng]
+        ymin = float(np.float32(-0.5 * Ly))
+        ymax = float(np.float32(ymin) + np.float32(dx) * np.float32(n[1]))
+        sim.set_match([(1, ymin, ds, [0, 0], [ext[0], g.ng + nds]),
+                       (1, ymax, ds, [0, g.ng + n[1] - nds], [ext[0], ext[1]])], target, 63)
     gen = _gen(sim, seed)
     ncell = n[0] * n[1]
     n_bg = ncell * (ppc0 // 2)
