@@ -233,10 +233,23 @@ def run_ours(args):
     import entity_b200 as eb
     dmode = {"atomic": eb.DEPOSIT_ATOMIC, "aggregated": eb.DEPOSIT_AGGREGATED,
              "ordered": eb.DEPOSIT_ORDERED}[args.deposit]
-    sim = workloads.reconnection(size, ppc0=args.ppc, nfilter=args.filters, fused=not args.unfused,
-                                 sort_interval=args.sort_interval, device=local,
-                                 deposit_mode=dmode, seed=0x5678 + rank, walls=args.walls,
-                                 capacity_factor=1.0 if world == 1 else 1.1)
+    turb = args.turbulence is not None
+    if turb:
+        # configs[2]-shaped block (3D, T = 1 pair plasma, 3rd-order shapes, 4 filter passes) at the
+        # n^3 given: a second bench line for the Esirkepov path, single GPU, not the headline
+        if world > 1:
+            raise SystemExit("bench.py --turbulence: single-GPU line")
+        size = (args.turbulence,) * 3
+        if args.sort_interval == 40:
+            args.sort_interval = 5  # hot plasma, wide windows: the order decays within a few steps
+        sim = workloads.turbulence(size, ppc0=args.ppc if args.ppc != 32 else 16, order=3, nfilter=4,
+                                   fused=not args.unfused, sort_interval=args.sort_interval,
+                                   device=local, deposit_mode=dmode, seed=0x9abc)
+    else:
+        sim = workloads.reconnection(size, ppc0=args.ppc, nfilter=args.filters, fused=not args.unfused,
+                                     sort_interval=args.sort_interval, device=local,
+                                     deposit_mode=dmode, seed=0x5678 + rank, walls=args.walls,
+                                     capacity_factor=1.0 if world == 1 else 1.1)
     decomposition = [1, 1]
     if world > 1:
         # spatial block decomposition as the reference's reconnection.toml asks ([-1, 2]); every
@@ -293,7 +306,8 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     pd_ms, pd_calls = prof["PushDeposit"]
     per_launch_s = 1e-3 * pd_ms / max(args.steps, 1)  # one push+deposit phase per step
-    achieved = n_pushed * B_P_2D / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    b_p = 102.0 if turb else B_P_2D  # 78 B (2D), 102 B (3D) per particle-step
+    achieved = n_pushed * b_p / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
                 "kernel": "push_deposit (all species of one step)", "peak_source": peak_src,
@@ -332,12 +346,17 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (WORKLOAD if size == (4096, 2048) and args.ppc == 32 else
+            "config": {"workload": (f"turbulence-shaped 3D Cartesian SR pair plasma, {size[0]}^3 cells, "
+                                    f"{16 if args.ppc == 32 else args.ppc} ppc, 3rd-order shapes (reduced from 1024^3)"
+                                    if turb else
+                                    WORKLOAD if size == (4096, 2048) and args.ppc == 32 else
                                     f"reconnection 2D {size[0]}x{size[1]} cells, {args.ppc} ppc (reduced)")
                        + (" [x2 walls: fields MATCH ds=20, particles ABSORB, no injector]"
                           if args.walls else ""),
-                       "cells_per_gpu": list(size), "ppc0": args.ppc, "shape_order": 0,
-                       "current_filters": args.filters, "particles_per_gpu": n_pushed0,
+                       "cells_per_gpu": list(size),
+                       "ppc0": (16 if args.ppc == 32 else args.ppc) if turb else args.ppc,
+                       "shape_order": 3 if turb else 0,
+                       "current_filters": 4 if turb else args.filters, "particles_per_gpu": n_pushed0,
                        "fused_push_deposit": not args.unfused, "sort_interval": args.sort_interval,
                        "deposit": args.deposit,
                        "parallelism": (f"domain decomposition {decomposition[0]}x{decomposition[1]}, "
@@ -385,6 +404,8 @@ def main():
     ap.add_argument("--sort-interval", type=int, default=40)
     ap.add_argument("--deposit", default="aggregated", choices=["atomic", "aggregated", "ordered"])
     ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--turbulence", type=int, default=None, metavar="N",
+                    help="bench the turbulence-shaped 3D block (N^3 cells, 16 ppc, O=3) instead")
     ap.add_argument("--walls", action="store_true",
                     help="x2 boundaries of reconnection.toml (fields MATCH, particles ABSORB) instead "
                          "of the periodic core; single GPU, no replenishing injector")
