@@ -1317,13 +1317,15 @@ namespace eb200 {
       return cudaGetLastError();
     }
 
-    // Esirkepov windows of 64 nodes and more (3D, O >= 2): the segmented shuffle reduction of
+    // 3D Esirkepov windows (27 .. 125 nodes x 3 components): the segmented shuffle reduction of
     // the AGGREGATED mode costs ten instructions per node and lane, more than the atomics it
-    // saves (3D O=3, 160^3 x 16 ppc: 86 ms aggregated vs 57 ms per-lane atomics per step); the
-    // mode is a hint about the order of the additions, not about the result
+    // saves. Measured per step on 1.4e7 cell-sorted particles (scripts/deposit_modes.py), atomic
+    // vs aggregated: 3D O=1 1.82 / 2.65 ms, O=2 6.26 / 8.97, O=3 13.8 / 19.5; in 2D the
+    // aggregation wins (O=2 3.17 / 2.43, O=3 6.76 / 3.30) and stays. The mode is a hint about
+    // the order of the additions, not about the result.
     template <int D, int O>
     constexpr bool wide_window() {
-      return D == 3 && O >= 2;
+      return D == 3 && O >= 1;
     }
 
     template <int D, int O>
