@@ -1046,6 +1046,115 @@ namespace eb200 {
     }
   }
 
+  /* ----------------------- 3D third-order Esirkepov deposit, rows with paired reductions */
+  // The per-lane atomic deposit of a 5 x 5 x 5 window is bound by the number of reduction
+  // requests that reach L2, not by arithmetic. The five nodes of a window row along x1 are
+  // contiguous in memory: they go out as two 64-bit reductions (red.global.add.v2.f32, which
+  // needs an 8-byte aligned address: the pairing shifts by one element when the row starts on
+  // an odd element) and one scalar, branch free. Same window, guards and per-node weights as
+  // deposit_particle<3, 3>(), evaluated row by row (the running sums of jx2 / jx3 are kept per
+  // (i, k) / (i, j) while x2 / x3 advance), so the additions into a J element differ from the
+  // node-by-node form only in their order. Fast build only: the strict build keeps the
+  // reference's program order.
+  __device__ __forceinline__ void red_pair(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+  }
+
+  // v[0..4] -> J elements e .. e + 4 (zeros are not sent)
+  __device__ __forceinline__ void red_row5(float* e, const float (&v)[5]) {
+    const bool odd = (reinterpret_cast<uintptr_t>(e) >> 2) & 1u;
+    float*     a   = e + (odd ? 1 : 0);
+    const float p0 = odd ? v[1] : v[0], p1 = odd ? v[2] : v[1];
+    const float p2 = odd ? v[3] : v[2], p3 = odd ? v[4] : v[3];
+    const float s  = odd ? v[0] : v[4];
+    if (p0 != ZERO || p1 != ZERO) red_pair(a, p0, p1);
+    if (p2 != ZERO || p3 != ZERO) red_pair(a + 2, p2, p3);
+    if (s != ZERO) atomicAdd(odd ? e : e + 4, s);
+  }
+
+  __device__ __forceinline__ void deposit_esirkepov3_rows(const Prtl<3>& P, float charge,
+                                                          float inv_dt, float dxc, int G,
+                                                          const FieldView<3>& J) {
+    constexpr int N = 5;
+    (void)dxc; // 3D: every component comes from the density decomposition, no velocity term
+    const float coeff = P.w * charge;
+    const float Q     = coeff * inv_dt;
+    float       iS1[N], fS1[N], iS2[N], fS2[N], iS3[N], fS3[N];
+    int         min1, max1, min2, max2, min3, max3;
+    deposit_shapes<3>(P.ip[0], P.dp[0], P.i[0], P.d[0], min1, max1, iS1, fS1);
+    deposit_shapes<3>(P.ip[1], P.dp[1], P.i[1], P.d[1], min2, max2, iS2, fS2);
+    deposit_shapes<3>(P.ip[2], P.dp[2], P.i[2], P.d[2], min3, max3, iS3, fS3);
+    min1 += G, min2 += G, min3 += G;
+    max1 += G, max2 += G, max3 += G;
+    const int  d1 = max1 - min1, d2 = max2 - min2, d3 = max3 - min3;
+    const long N12 = (long)J.N1 * J.N2;
+    float*     base = J.p + J.idx(min1, min2, min3);
+    // jx1(i, j, k) = -Q sum_{i' <= i} THIRD DS1(i') F23(j, k): one row per (j, k)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        if (j > d2 || k > d3) continue;
+        const float f = (iS2[j] * iS3[k] + fS2[j] * fS3[k]) +
+                        HALF * (iS3[k] * fS2[j] + iS2[j] * fS3[k]);
+        float v[N];
+        float acc = ZERO;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          acc -= Q * (THIRD * (fS1[i] - iS1[i]) * f);
+          v[i] = (i < d1) ? acc : ZERO;
+        }
+        red_row5(base + (long)j * J.N1 + (long)k * N12, v);
+      }
+    }
+    // jx2(i, j, k) = -Q sum_{j' <= j} THIRD DS2(j') F13(i, k): running sums per (i, k) while
+    // x2 advances, one row per (j, k)
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      if (k > d3) continue;
+      float g[N], acc[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        g[i]   = iS1[i] * iS3[k] + fS1[i] * fS3[k] + HALF * (iS3[k] * fS1[i] + iS1[i] * fS3[k]);
+        acc[i] = ZERO;
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float ds = THIRD * (fS2[j] - iS2[j]);
+        float       v[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          acc[i] -= Q * (ds * g[i]);
+          v[i] = (i <= d1) ? acc[i] : ZERO;
+        }
+        if (j < d2) red_row5(base + J.plane + (long)j * J.N1 + (long)k * N12, v);
+      }
+    }
+    // jx3(i, j, k) = -Q sum_{k' <= k} THIRD DS3(k') F12(i, j): running sums per (i, j) while
+    // x3 advances
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      if (j > d2) continue;
+      float g[N], acc[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        g[i]   = iS1[i] * iS2[j] + fS1[i] * fS2[j] + HALF * (iS1[i] * fS2[j] + iS2[j] * fS1[i]);
+        acc[i] = ZERO;
+      }
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float ds = THIRD * (fS3[k] - iS3[k]);
+        float       v[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          acc[i] -= Q * (ds * g[i]);
+          v[i] = (i <= d1) ? acc[i] : ZERO;
+        }
+        if (k < d3) red_row5(base + 2 * J.plane + (long)j * J.N1 + (long)k * N12, v);
+      }
+    }
+  }
+
   /* ------------------------------------------------- warp-aggregated deposit */
   // Particles arrive (nearly) cell-sorted, so consecutive lanes of a warp mostly deposit
   // onto the same nodes. Instead of one atomic per lane and node, runs of lanes with the

@@ -99,10 +99,17 @@ namespace eb200 {
       if constexpr (AGG) {
         deposit_particle_aggregated<D, O>(P, active, charge, inv_dt, dxc, G, J);
       } else {
-        deposit_particle<D, O>(P, charge, inv_dt, dxc, G,
-                               [&](int i, int j, int k, int c, float v, bool guard = true) {
-                                 if (guard) atomicAdd(&J.at(i, j, k, c), v);
-                               });
+#if !EB200_STRICT
+        if constexpr (D == 3 && O == 3) {
+          deposit_esirkepov3_rows(P, charge, inv_dt, dxc, G, J);
+        } else
+#endif
+        {
+          deposit_particle<D, O>(P, charge, inv_dt, dxc, G,
+                                 [&](int i, int j, int k, int c, float v, bool guard = true) {
+                                   if (guard) atomicAdd(&J.at(i, j, k, c), v);
+                                 });
+        }
       }
     }
 
@@ -148,10 +155,17 @@ namespace eb200 {
         deposit_particle_aggregated<D, O>(P, active, charge, inv_dt, A.c.dx, A.ng, J);
       } else {
         if (active) {
-          deposit_particle<D, O>(P, charge, inv_dt, A.c.dx, A.ng,
-                                 [&](int i, int j, int k, int c, float v, bool guard = true) {
-                                   if (guard) atomicAdd(&J.at(i, j, k, c), v);
-                                 });
+#if !EB200_STRICT
+          if constexpr (D == 3 && O == 3) {
+            deposit_esirkepov3_rows(P, charge, inv_dt, A.c.dx, A.ng, J);
+          } else
+#endif
+          {
+            deposit_particle<D, O>(P, charge, inv_dt, A.c.dx, A.ng,
+                                   [&](int i, int j, int k, int c, float v, bool guard = true) {
+                                     if (guard) atomicAdd(&J.at(i, j, k, c), v);
+                                   });
+          }
         }
       }
     }
