@@ -1496,15 +1496,21 @@ namespace eb200 {
           auto           kern    = lean ? push_deposit_vec_kernel<2, true, PackedEM2>
                                         : push_deposit_vec_kernel<2, false, PackedEM2>;
           static int     wave[2] = { 0, 0 };
+          // CTA size of the packed-node kernel (EB200_VEC_THREADS = 64 / 128 / 256, experiment)
+          static const int nthr = [] {
+            const char* e = getenv("EB200_VEC_THREADS");
+            const int   v = e ? atoi(e) : 256;
+            return (v == 64 || v == 128) ? v : 256;
+          }();
           if (wave[lean] == 0) {
             int dev = 0, nsm = 0, per_sm = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthr, 0);
             wave[lean] = nsm * (per_sm > 0 ? per_sm : 1);
           }
-          kern<<<(ngroups + 255) / 256, 256, 0, st>>>(A, S, ngroups, (uint32_t)wave[lean], PK,
-                                                       A.c.charge, inv_dt, J);
+          kern<<<(ngroups + nthr - 1) / nthr, nthr, 0, st>>>(A, S, ngroups, (uint32_t)wave[lean], PK,
+                                                             A.c.charge, inv_dt, J);
           count_launch();
           p_begin = ngroups * VEC;
           if (p_begin == npart) return cudaGetLastError();
