@@ -318,9 +318,24 @@ int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const i
   }
   const size_t bytes = field_bytes(ctx->cfg.grid, 3);
   // single doubly periodic 2D domain: several passes per sweep (fields.cu, temporal blocking)
+  // ... or a 2D domain whose non-periodic dimensions carry EB200_FBC_NONE on both faces (MATCH /
+  // open boundaries: their ghost cells are static during the filter, as in the reference, which
+  // exchanges nothing there): the sweeps read those ghost cells and carry them
   bool fuse = ctx->cfg.grid.dim == 2 && ctx->comm == nullptr && nfilter > 0 && !ctx->no_filter_fusion;
-  for (int a = 0; a < 4; ++a) fuse = fuse && fbc[a] == EB200_FBC_PERIODIC;
+  int  static_dims = 0;
+  for (int a = 0; a < 2; ++a) {
+    const bool per = fbc[2 * a] == EB200_FBC_PERIODIC && fbc[2 * a + 1] == EB200_FBC_PERIODIC;
+    const bool non = fbc[2 * a] == EB200_FBC_NONE && fbc[2 * a + 1] == EB200_FBC_NONE;
+    fuse           = fuse && (per || non);
+    if (non) static_dims |= 2 << a;
+  }
+  if (static_dims && nfilter < 2) fuse = false; // an odd single sweep would land in buff
   if (fuse) {
+    if (static_dims) {
+      // the second array must show the same static ghost cells
+      cudaError_t e = cudaMemcpyAsync(buff, cur, bytes, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return check_cuda(ctx, e, "filter copy");
+    }
     // an even number of sweeps of <= 4 passes each, so that the result lands in `cur`
     int sweeps = (nfilter + 3) / 4;
     if (sweeps % 2 == 1 && nfilter >= 2) ++sweeps;
@@ -329,7 +344,7 @@ int eb200_filter(eb200_ctx_t* ctx, float* cur, float* buff, int nfilter, const i
     int    left = nfilter;
     for (int s = 0; s < sweeps; ++s) {
       const int   p = (left + (sweeps - s) - 1) / (sweeps - s);
-      cudaError_t e = VARIANT_CALL(ctx, filter_fused(ctx->cfg.grid, a, b, p, 0, st));
+      cudaError_t e = VARIANT_CALL(ctx, filter_fused(ctx->cfg.grid, a, b, p, static_dims, st));
       if (e != cudaSuccess) return check_cuda(ctx, e, "fused filter");
       left -= p;
       float* t = a;

@@ -456,9 +456,14 @@ namespace eb200 {
 
     // GHOSTS: the halo of a tile is read from the ghost cells as they are (they hold the
     // neighbour domains' exchanged values, P <= G) instead of the periodic image
-    template <int P, bool GHOSTS = false>
+    // st1 / st2 (GHOSTS = false): the dimension is not periodic and not exchanged -- its ghost
+    // cells hold values that no pass changes (the reference never refreshes them between
+    // passes either): the halo is read from them as they are and cells outside the active
+    // range are carried, not filtered
+    template <int P, bool GHOSTS = false, int ST = 0>
     __global__ void __launch_bounds__(256)
       filter_fused2d_kernel(FieldView<2> src, FieldView<2> dst, int n1, int n2, int G) {
+      constexpr bool st1 = (ST & 2) != 0, st2 = (ST & 4) != 0; // static dimension 1 / 2
       constexpr int W = FT_X + 2 * P, H = FT_Y + 2 * P;
       __shared__ float buf[2][H * W];
       const int c  = blockIdx.z;
@@ -481,7 +486,15 @@ namespace eb200 {
           const int gx = min(x0 + lx, n1 + G - 1), gy = min(y0 + ly, n2 + G - 1);
           buf[0][e] = src.ld(gx + G, gy + G, 0, c);
         } else {
-          buf[0][e] = src.ld(wrap(x0 + lx, n1) + G, wrap(y0 + ly, n2) + G, 0, c);
+          // only the first ghost layer of a static dimension is ever read by a carried cell's
+          // neighbours; anything further out is clamped (and never used)
+          // (the corner ghosts next to a static face are not periodic images either: the
+          // reference exchanges corners only where both dimensions communicate)
+          const int  x = x0 + lx, y = y0 + ly;
+          const bool out1 = st1 && (x < 0 || x >= n1), out2 = st2 && (y < 0 || y >= n2);
+          const int  gx = (st1 || out2) ? max(-1, min(x, n1)) : wrap(x, n1);
+          const int  gy = (st2 || out1) ? max(-1, min(y, n2)) : wrap(y, n2);
+          buf[0][e] = src.ld(gx + G, gy + G, 0, c);
         }
       }
       __syncthreads();
@@ -494,6 +507,31 @@ namespace eb200 {
         for (int e = threadIdx.x; e < w * h; e += 256) {
           const int    ly = e / w, lx = e - ly * w;
           const float* q  = b + (ly + p) * W + (lx + p);
+          if constexpr (!GHOSTS) {
+            if constexpr (st1 || st2) {
+              const int gx = x0 + lx + p, gy = y0 + ly + p;
+              if ((st1 && (gx < 0 || gx >= n1)) || (st2 && (gy < 0 || gy >= n2))) {
+                a[(ly + p) * W + (lx + p)] = q[0];
+                continue;
+              }
+              // next to a static face the neighbours in the static ghost layer are read from the
+              // array itself at their true place (corner ghosts included -- they are not
+              // periodic images), never from the tile; the cell this position stands for: a halo
+              // position of a periodic dimension is the image of a cell at the other end
+              if ((st1 && (gx == 0 || gx == n1 - 1)) || (st2 && (gy == 0 || gy == n2 - 1))) {
+                const int X = st1 ? gx : wrap(gx, n1), Y = st2 ? gy : wrap(gy, n2);
+                auto nb = [&](int dx, int dy) {
+                  const int  nx = X + dx, ny = Y + dy;
+                  const bool out = (st1 && (nx < 0 || nx >= n1)) || (st2 && (ny < 0 || ny >= n2));
+                  return out ? src.ld(nx + G, ny + G, 0, c) : q[dy * W + dx];
+                };
+                a[(ly + p) * W + (lx + p)] =
+                  INV_4 * q[0] + INV_8 * (nb(-1, 0) + nb(1, 0) + nb(0, -1) + nb(0, 1)) +
+                  INV_16 * (nb(-1, -1) + nb(1, 1) + nb(-1, 1) + nb(1, -1));
+                continue;
+              }
+            }
+          }
           a[(ly + p) * W + (lx + p)] =
             INV_4 * q[0] + INV_8 * (q[-1] + q[1] + q[-W] + q[W]) +
             INV_16 * (q[-W - 1] + q[W + 1] + q[W - 1] + q[-W + 1]);
@@ -613,11 +651,33 @@ namespace eb200 {
       return cudaGetLastError();
     }
 
+    // ghosts: 0 periodic images, 1 exchanged ghost cells (<= 2 passes), 2 | 4 = dimension 1 | 2
+    // is static (non-periodic, not exchanged), the other one periodic unless also static
     cudaError_t filter_fused(const eb200_grid_t& g, const float* src, float* dst, int passes,
                              int ghosts, cudaStream_t st) {
       if (g.dim != 2 || passes < 1 || passes > FT_PMAX) return cudaErrorInvalidValue;
       const dim3 grid((g.n[0] + FT_X - 1) / FT_X, (g.n[1] + FT_Y - 1) / FT_Y, 3);
       const FieldView<2> S(g, const_cast<float*>(src)), Dd(g, dst);
+      if (ghosts & 6) {
+#define FUSED_ST(PP, SS) \
+  filter_fused2d_kernel<PP, false, SS><<<grid, 256, 0, st>>>(S, Dd, g.n[0], g.n[1], g.ng)
+#define FUSED_ST_P(SS)                                                                         \
+  switch (passes) {                                                                            \
+    case 1: FUSED_ST(1, SS); break;                                                            \
+    case 2: FUSED_ST(2, SS); break;                                                            \
+    case 3: FUSED_ST(3, SS); break;                                                            \
+    default: FUSED_ST(4, SS); break;                                                           \
+  }
+        switch (ghosts & 6) {
+          case 2: FUSED_ST_P(2) break;
+          case 4: FUSED_ST_P(4) break;
+          default: FUSED_ST_P(6) break;
+        }
+#undef FUSED_ST_P
+#undef FUSED_ST
+        count_launch();
+        return cudaGetLastError();
+      }
       if (ghosts) {
         if (passes > 2 || passes > g.ng) return cudaErrorInvalidValue;
         if (passes == 1) {

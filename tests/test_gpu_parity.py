@@ -300,6 +300,37 @@ def test_fused_kernels_wide_mesh(eb, orc_mod, which, strict, order_kind):
 
 
 @pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("nfilter", [1, 2, 3, 8, 9])
+@pytest.mark.parametrize("open_dims", [(1,), (0,), (0, 1)])
+@pytest.mark.parametrize("n_cells", [(150, 37), (64, 16), (7, 5)])
+def test_fused_filter_open_faces(eb, orc_mod, n_cells, open_dims, nfilter, strict):
+    """The fused sweeps on a 2D domain with non-periodic, non-exchanged dimensions (FBC_NONE on
+    both faces: the MATCH walls of the reconnection configuration): their ghost cells are static
+    during the filter and enter every pass as they are, exactly as in nfilter x (copy,
+    DigitalFilter_kernel, ghost fill of the periodic dimensions only). Strict build: identical
+    bits, ghost cells included."""
+    orc = orc_mod.oracle()
+    g = orc_mod.Grid.make(n_cells, 2)
+    ctx = eb.Context(n_cells, order=0, strict=strict)
+    bc = [orc_mod.FBC_PERIODIC] * 6
+    for a in open_dims:
+        bc[2 * a] = bc[2 * a + 1] = orc_mod.FBC_NONE
+    cur = random_fields(g, 3, 19)  # ghost cells random too: they are the static boundary data
+    orc.comm_fields(g, cur, 0, 3, bc)
+    d_cur, d_buff = dev(cur), dev(random_fields(g, 3, 23))
+    buff = np.zeros_like(cur)
+    for _ in range(nfilter):
+        buff[...] = cur
+        orc.filter_pass(g, cur, buff, bc)
+        orc.comm_fields(g, cur, 0, 3, bc)
+    ctx.filter(d_cur, d_buff, nfilter, bc)
+    if strict:
+        assert_values_equal(host(d_cur), cur, f"fused filter, open faces, x{nfilter}")
+    else:
+        np.testing.assert_allclose(host(d_cur), cur, rtol=RTOL_FAST, atol=ATOL_FAST)
+
+
+@pytest.mark.parametrize("strict", [True, False])
 @pytest.mark.parametrize("nfilter", [1, 2, 4, 5, 8, 9])
 @pytest.mark.parametrize("n_cells", [(150, 37), (64, 16), (5, 3)])
 def test_fused_filter_passes(eb, orc_mod, n_cells, nfilter, strict):
