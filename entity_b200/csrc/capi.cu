@@ -9,6 +9,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <limits>
+#include <cmath>
+#include <algorithm>
 #include <string>
 
 namespace eb200 {
@@ -580,6 +583,56 @@ int eb200_match_fields(eb200_ctx_t* ctx, float* em, const float* target, int o, 
                                         ds, tags, components_mask & 63, range_min, range_max,
                                         (cudaStream_t)stream),
                     "match_fields");
+}
+
+// Mesh::Intersects + Mesh::ExtentToRange for the one box srpic::MatchFieldsIn builds
+int eb200_match_layer(const eb200_grid_t* g, float dx, const float* xmin, const float* xmax,
+                      float gx_lo, float gx_hi, int o, int sign, float ds,
+                      eb200_match_face_t* face) {
+  if (!g || !xmin || !xmax || !face || g->dim < 1 || g->dim > 3 || o < 0 || o >= g->dim ||
+      sign == 0 || !(dx > 0.0f) || !(ds > 0.0f)) {
+    return -EB200_ERR_ARG;
+  }
+  float bmin, bmax, edge;
+  if (sign > 0) { // fields_bcs.h:78-88
+    bmax = gx_hi;
+    bmin = bmax - ds;
+    edge = bmax;
+  } else {
+    bmin = gx_lo;
+    bmax = bmin + ds;
+    edge = bmin;
+  }
+  const float lo = xmin[o], hi = xmax[o];
+  // Mesh::Intersection, mesh.h:84-98 (both bounds finite here)
+  const float x_min = std::min(hi, std::max(lo, bmin));
+  const float x_max = std::max(lo, std::min(hi, bmax));
+  const float eps   = std::numeric_limits<float>::epsilon();
+  if (x_min > x_max || x_min == x_max ||
+      std::fabs(x_min - x_max) <= std::min(std::fabs(x_min), std::fabs(x_max)) * eps) {
+    return 0; // mesh.h:112-120
+  }
+  const int  G = g->ng;
+  const bool incl_lo = sign < 0, incl_hi = sign > 0; // fields_bcs.h:93-98
+  face->o       = o;
+  face->xg_edge = edge;
+  face->ds      = ds;
+  for (int d = 0; d < 3; ++d) {
+    face->range_min[d] = 0;
+    face->range_max[d] = (d < g->dim) ? g->n[d] + 2 * G : 1; // Range::All with ghosts, mesh.h:149-153
+  }
+  // mesh.h:155-197; metric.convert<Ph, Cd>(x) = (x - x_min) * dx_inv (minkowski.h:175-181) with
+  // the domain metric's own dx = (x1_max - x1_min) / nx1, dx_inv = 1 / dx (minkowski.h:54-55)
+  const float dx_m   = (xmax[0] - xmin[0]) / (float)g->n[0];
+  const float dx_inv = 1.0f / dx_m;
+  (void)dx;
+  float       c_min  = std::floor((x_min - lo) * dx_inv);
+  float       c_max  = std::ceil((x_max - lo) * dx_inv);
+  if (!incl_lo) c_min = std::max(c_min, 0.0f);
+  if (!incl_hi) c_max = std::min(c_max, (float)g->n[o]);
+  face->range_min[o] = (int)c_min + (incl_lo ? 0 : G);
+  face->range_max[o] = (int)c_max + (incl_hi ? 2 * G : G);
+  return 1;
 }
 
 static int stats_finish(eb200_ctx_t* ctx, cudaError_t e, double* out_host, cudaStream_t st,

@@ -196,6 +196,10 @@ def load():
     lib.eb200_match_fields.argtypes = [ctxp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                        i32p, i32p, vp]
     lib.eb200_match_fields.restype = C.c_int
+    lib.eb200_match_layer.argtypes = [C.POINTER(Grid), C.c_float, C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_int,
+                                      C.c_float, C.POINTER(MatchFaceC)]
+    lib.eb200_match_layer.restype = C.c_int
     lib.eb200_srpic_set_match.argtypes = [ctxp, C.POINTER(MatchFaceC), C.c_int, vp, C.c_int]
     lib.eb200_srpic_set_match.restype = C.c_int
     lib.eb200_stats_fields.argtypes = [ctxp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_double), vp]
@@ -229,6 +233,24 @@ def exported_symbols():
     hdr = os.path.join(os.path.dirname(HERE), "include", "entity_b200.h")
     txt = open(hdr).read()
     return sorted(set(re.findall(r"\b(eb200_[a-z_0-9]+)\s*\(", txt)))
+
+
+def match_layer(grid, dx, local_xmin, local_xmax, global_xmin_o, global_xmax_o, o, sign, ds):
+    """srpic::MatchFieldsIn geometry for one face of the global box (pure host code): returns
+    (o, xg_edge, ds, range_min, range_max) for Simulation.set_match / Context.match_fields, or
+    None when the layer does not reach this domain."""
+    lib = load()
+    d = grid.dim
+    lo = (C.c_float * 3)(*(list(local_xmin)[:d] + [0.0] * (3 - d)))
+    hi = (C.c_float * 3)(*(list(local_xmax)[:d] + [0.0] * (3 - d)))
+    f = MatchFaceC()
+    rc = lib.eb200_match_layer(C.byref(grid), dx, lo, hi, global_xmin_o, global_xmax_o, o, sign, ds,
+                               C.byref(f))
+    if rc < 0:
+        raise EB200Error(f"eb200_match_layer: bad argument (rc={rc})")
+    if rc == 0:
+        return None
+    return (f.o, f.xg_edge, f.ds, list(f.range_min)[:d], list(f.range_max)[:d])
 
 
 def decompose(ndomains, ncells, decomposition=None):

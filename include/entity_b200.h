@@ -351,6 +351,17 @@ typedef struct {
   float xg_edge, ds;                /* edge of the global box on that side, layer thickness */
   int   range_min[3], range_max[3]; /* ghost-inclusive cell range of the layer in this domain */
 } eb200_match_face_t;
+/* The geometry srpic::MatchFieldsIn hands to the kernel (src/engines/srpic/fields_bcs.h:72-114
+ * with Mesh::Intersects / Mesh::ExtentToRange, src/framework/domain/mesh.h:69-203) for the
+ * face (o, sign) of the GLOBAL box and a Minkowski domain with the given local extent: the
+ * layer [edge - ds, edge] (sign > 0) or [edge, edge + ds] (sign < 0), ghosts included on the
+ * outer side and over the whole transverse extent. Returns 1 and fills *face when the layer
+ * intersects the domain, 0 when it does not (MatchFieldsIn then returns without a launch),
+ * < 0 on a bad argument. Pure host code, fp32 like the reference (the cell size used for the
+ * index range is the domain metric's own, (local_xmax[0] - local_xmin[0]) / n[0]). */
+int eb200_match_layer(const eb200_grid_t* local_grid, float dx, const float* local_xmin,
+                      const float* local_xmax, float global_xmin_o, float global_xmax_o, int o,
+                      int sign, float ds, eb200_match_face_t* face);
 int eb200_srpic_set_match(eb200_ctx_t* ctx, const eb200_match_face_t* faces, int nfaces,
                           const float* target, int components_mask);
 
