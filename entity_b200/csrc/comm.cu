@@ -528,8 +528,14 @@ namespace eb200 {
     int      shift[MAXTAG][3];       // index shift applied on the way out
   };
 
+  // payload words of a record (pld_r then pld_i; kernels/comm.hpp:75-105 sends them too)
+  __host__ __device__ inline int npld_words(const eb200_prtls_t& S) {
+    return (S.pld_r ? S.npld_r : 0) + (S.pld_i ? S.npld_i : 0);
+  }
+
   // PopulatePrtlSendBuffer (+ the index shifts of PrepareOutgoingPrtls): one record of NW
   // 32-bit words per particle: [i, i_prev] x D, [dx, dx_prev] x D, ux1..3, weight (, phi)
+  // (, payloads)
   template <int D>
   __global__ void __launch_bounds__(256)
     prtl_pack_kernel(const __grid_constant__ SendPlan P, eb200_prtls_t S,
@@ -541,7 +547,8 @@ namespace eb200 {
     while (c + 1 < P.nclass && q >= P.class_base[c + 1]) ++c;
     const uint32_t p = out_idx[q];
     if (P.seg_off[c] >= 0) {
-      const int      NW  = 4 * D + 4 + (has_phi ? 1 : 0);
+      const int      NB  = 4 * D + 4 + (has_phi ? 1 : 0);
+      const int      NW  = NB + npld_words(S);
       uint32_t*      rec = buf + P.seg_off[c] + (long)(q - P.class_base[c]) * NW;
       const int*     ii[3]  = { S.i1, S.i2, S.i3 };
       const int*     iip[3] = { S.i1_prev, S.i2_prev, S.i3_prev };
@@ -559,6 +566,13 @@ namespace eb200 {
       rec[4 * D + 2] = __float_as_uint(S.ux3[p]);
       rec[4 * D + 3] = __float_as_uint(S.weight[p]);
       if (has_phi) rec[4 * D + 4] = __float_as_uint(S.phi[p]);
+      int w = NB;
+      if (S.pld_r) {
+        for (int k = 0; k < S.npld_r; ++k) rec[w++] = __float_as_uint(S.pld_r[p + (size_t)k * S.pld_stride]);
+      }
+      if (S.pld_i) {
+        for (int k = 0; k < S.npld_i; ++k) rec[w++] = S.pld_i[p + (size_t)k * S.pld_stride];
+      }
     }
     // sent (or unsendable) particles leave the domain
     S.tag[p] = 0;
@@ -580,7 +594,8 @@ namespace eb200 {
     if (r >= nrecv) return;
     int k = 0;
     while (k + 1 < R.nseg && r >= R.first[k + 1]) ++k;
-    const int       NW  = 4 * D + 4 + (has_phi ? 1 : 0);
+    const int       NB  = 4 * D + 4 + (has_phi ? 1 : 0);
+    const int       NW  = NB + npld_words(S);
     const uint32_t* rec = buf + R.seg_off[k] + (long)(r - R.first[k]) * NW;
     const uint32_t  p   = (r < nholes) ? out_idx[r] : (npart + r - nholes);
     int*            ii[3]  = { S.i1, S.i2, S.i3 };
@@ -599,6 +614,13 @@ namespace eb200 {
     S.ux3[p]    = __uint_as_float(rec[4 * D + 2]);
     S.weight[p] = __uint_as_float(rec[4 * D + 3]);
     if (has_phi) S.phi[p] = __uint_as_float(rec[4 * D + 4]);
+    int w = NB;
+    if (S.pld_r) {
+      for (int k = 0; k < S.npld_r; ++k) S.pld_r[p + (size_t)k * S.pld_stride] = __uint_as_float(rec[w++]);
+    }
+    if (S.pld_i) {
+      for (int k = 0; k < S.npld_i; ++k) S.pld_i[p + (size_t)k * S.pld_stride] = rec[w++];
+    }
     S.tag[p] = 1;
   }
 
@@ -1022,7 +1044,7 @@ namespace eb200 {
         P.seg_off[c] = -1;
         P.shift[c][0] = P.shift[c][1] = P.shift[c][2] = 0;
       }
-      NW[s] = 4 * D + 4 + (species[s].arrays.phi ? 1 : 0);
+      NW[s] = 4 * D + 4 + (species[s].arrays.phi ? 1 : 0) + npld_words(species[s].arrays);
       rplan[s].nseg = 0;
     }
     // data message layout: per peer, per species, per direction ascending

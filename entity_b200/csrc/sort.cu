@@ -129,6 +129,9 @@ namespace eb200 {
                              Scratch& scratch, cudaStream_t st) {
     if (n_alive_out) *n_alive_out = npart;
     if (npart == 0) return cudaSuccess;
+    if (S.npld_r < 0 || S.npld_i < 0 || S.npld_r > EB200_MAX_PLD || S.npld_i > EB200_MAX_PLD) {
+      return cudaErrorInvalidValue;
+    }
     const int      n1 = g.n[0], n2 = g.dim > 1 ? g.n[1] : 1, n3 = g.dim > 2 ? g.n[2] : 1;
     const uint64_t nc64 = (uint64_t)n1 * n2 * n3;
     if (nc64 >= 0xFFFFFFFFull) return cudaErrorInvalidValue;
@@ -186,7 +189,7 @@ namespace eb200 {
     }
 
     {
-      uint32_t* w[20];
+      uint32_t* w[20 + 2 * EB200_MAX_PLD];
       int       nw = 0;
       auto      add = [&](void* q) {
         if (q) w[nw++] = (uint32_t*)q;
@@ -196,6 +199,13 @@ namespace eb200 {
       if (g.dim > 2) add(S.i3), add(S.dx3), add(S.i3_prev), add(S.dx3_prev);
       add(S.ux1), add(S.ux2), add(S.ux3), add(S.weight);
       add(S.phi);
+      // payload planes travel with their particles (particles_sort.cpp:150-160, 239-247)
+      if (S.pld_r) {
+        for (int k = 0; k < S.npld_r; ++k) add(S.pld_r + (size_t)k * S.pld_stride);
+      }
+      if (S.pld_i) {
+        for (int k = 0; k < S.npld_i; ++k) add(S.pld_i + (size_t)k * S.pld_stride);
+      }
       permute_words(w, nw, perm, npart, (char*)tmp, n4, st);
     }
     permute(S.tag, perm, npart, tmp, st);

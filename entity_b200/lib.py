@@ -50,7 +50,8 @@ class Grid(C.Structure):
 
 
 class Prtls(C.Structure):
-    _fields_ = [(name, C.c_void_p) for name in PRTL_FIELDS]
+    _fields_ = [(name, C.c_void_p) for name in PRTL_FIELDS] + [
+        ("npld_r", C.c_int), ("npld_i", C.c_int), ("pld_stride", C.c_uint32)]
 
 
 class Pusher(C.Structure):
@@ -414,6 +415,12 @@ class Context:
         for name in PRTL_FIELDS:
             t = arrays.get(name)
             setattr(s, name, _ptr(t) if t is not None and t.numel() else None)
+        # payload planes: tensors of shape [npld, capacity] (plane k contiguous)
+        for nm, cnt in (("pld_r", "npld_r"), ("pld_i", "npld_i")):
+            t = arrays.get(nm)
+            if t is not None and t.numel():
+                setattr(s, cnt, int(t.shape[0]))
+                s.pld_stride = int(t.shape[1])
         return s
 
     # -- field solvers

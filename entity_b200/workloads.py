@@ -176,8 +176,7 @@ def turbulence(n=(128, 128, 128), ppc0=16, order=3, nfilter=4, seed=0x9abc, **kw
     dx = 256.0 / 1024.0
     sim = Simulation(n, order, Scales(3, dx, larmor0=1.0, skindepth0=1.0, ppc0=ppc0),
                      nfilter=nfilter, **kw)
-    sim.em[5] = 1.0 / 1.0  # B_x3 = 1 (out-of-plane components carry no metric factor in 3D? see below)
-    # in 3D every component is in-plane: contravariant = physical / dx
+    # B_x3 = 1; in 3D every component is in-plane: contravariant = physical / dx
     sim.em[5] = 1.0 / dx
     gen = _gen(sim, seed)
     per = math.prod(n) * (ppc0 // 2)

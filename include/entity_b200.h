@@ -101,10 +101,16 @@ typedef struct {
   float*    dx2_prev;
   float*    dx3_prev;
   short*    tag;
-  float*    pld_r; /* [npart][npld_r], may be NULL */
-  uint32_t* pld_i; /* [npart][npld_i], may be NULL */
+  float*    pld_r; /* payload k of particle p at pld_r[p + k * pld_stride], may be NULL */
+  uint32_t* pld_i; /* same layout (Kokkos LayoutLeft = the reference's device build), may be NULL */
   float*    phi;   /* 2D non-Cartesian only, may be NULL */
+  /* payload planes (ParticleSpecies::npld_r / npld_i, particles.h:62-65): sorted, compacted and
+   * migrated with their particles (particles_sort.cpp:104-253, particles_comm.cpp:180-389);
+   * the pusher and the deposit do not touch them. pld_stride = extent(0) of the views. */
+  int       npld_r, npld_i; /* each <= EB200_MAX_PLD */
+  uint32_t  pld_stride;
 } eb200_prtls_t;
+#define EB200_MAX_PLD 16
 
 /* scalar arguments of kernel::sr::Pusher_kernel: PusherContext + PusherBoundaries
  * (src/kernels/pushers/context.h:74-178), filled by the host exactly like
@@ -191,8 +197,11 @@ int eb200_pack_fields_hold(eb200_ctx_t* ctx, const float* em, eb200_stream_t str
 int eb200_pack_fields_release(eb200_ctx_t* ctx);
 /* which fused kernel eb200_push_deposit_sr / eb200_srpic_step launch in AGGREGATED mode:
  * 0 = automatic (default), 1 = one particle per thread, 2 = TMA-staged persistent chunks,
- * 3 = four particles per thread with 128-bit accesses (zig-zag only). A tuning knob for
- * measurements; results are the same up to the summation order of J. */
+ * 3 = four particles per thread with 128-bit accesses (zig-zag only), 4 = 3 with the E/B
+ * nodes of a CTA staged in shared memory, 5 = 3 gathering from the packed E/B nodes (2D; what
+ * 0 selects for 2D zig-zag), 6 = pipelined persistent CTAs, 7 = shared-memory resident
+ * slices. A tuning knob for measurements; results are the same up to the summation order
+ * of J. */
 int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which);
 
 /* ------------------------------------------------- single-domain ghost exchange */

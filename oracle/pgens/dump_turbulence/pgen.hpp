@@ -1,0 +1,6 @@
+// TEST INFRASTRUCTURE (oracle): the reference's pgens/turbulence problem generator + a state dump hook.
+#ifndef PROBLEM_GENERATOR_WRAP_H
+#define PROBLEM_GENERATOR_WRAP_H
+#define EB_REF_PGEN "/root/reference/pgens/turbulence/pgen.hpp"
+#include "../dump_common.hpp"
+#endif

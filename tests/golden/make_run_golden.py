@@ -1,0 +1,89 @@
+"""Generates tests/golden/run_*.npz: whole-run golden states from the reference's own
+entity.xc (built by oracle/build_entity_xc.sh with the dump-wrapper pgens of oracle/pgens/),
+Kokkos-OpenMP with ONE thread (= serial program order: particles of a species deposit in
+array order, species in index order -- the order eb200's ORDERED deposit mode reproduces).
+
+    python tests/golden/make_run_golden.py          # needs /root/reference + the built binaries
+
+Per case: the full state after step S0 (import point) and, for every later step up to S1,
+the fields em / cur, npart (before and after the pgen's own injection) and per-array
+checksums; full particle arrays again at the last step; for runs with an injector the
+injected tail [npart_pre, npart) of every step (the reference's Kokkos RNG stream is not
+part of the hot path: the test re-imports what the injector appended)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refdump  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BIN = os.path.join(ROOT, "baseline", "_ref", "omp")
+
+PRTL = ["i1", "i2", "i3", "dx1", "dx2", "dx3", "ux1", "ux2", "ux3", "weight", "i1_prev", "i2_prev",
+        "i3_prev", "dx1_prev", "dx2_prev", "dx3_prev", "tag", "phi"]
+
+CASES = {
+    # name: (binary, input, first step, last step)
+    "stream2d": ("entity_streaming.xc", "stream2d.toml", 0, 10),
+    "reconnection_small": ("entity_reconnection.xc", "reconnection_small.toml", 0, 7),
+}
+
+
+def checksum(a: np.ndarray) -> np.uint64:
+    """order-sensitive 64-bit checksum of the raw bits (numpy only)"""
+    b = np.ascontiguousarray(a).view(np.uint8)
+    pad = (-b.size) % 4
+    if pad:
+        b = np.concatenate([b, np.zeros(pad, np.uint8)])
+    w = b.view(np.uint32).astype(np.uint64)
+    k = (np.arange(w.size, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1)) & np.uint64(0xFFFFFFFF)
+    return np.uint64((w * k).sum(dtype=np.uint64))
+
+
+def run_case(name):
+    exe, inp, s0, s1 = CASES[name]
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        env = dict(os.environ, OMP_NUM_THREADS="1", EB_DUMP_DIR=tmp,
+                   EB_DUMP_STEPS=",".join(str(s) for s in range(s0, s1 + 1)))
+        r = subprocess.run([os.path.join(BIN, exe), "-input", os.path.join(HERE, "run_inputs", inp)],
+                           cwd=tmp, env=env, capture_output=True, text=True, timeout=1200)
+        if r.returncode != 0:
+            raise RuntimeError(r.stdout[-2000:] + r.stderr[-2000:])
+        for s in range(s0, s1 + 1):
+            d = refdump.read(os.path.join(tmp, f"s{s}_d0.bin"))
+            nsp = sum(1 for k in d if k.endswith("_npart"))
+            out[f"s{s}/time"] = d["time"]
+            out[f"s{s}/em"] = d["em"]
+            out[f"s{s}/cur"] = d["cur"]
+            for k in range(nsp):
+                p = f"sp{k}_"
+                n, npre = int(d[p + "npart"][0]), int(d[p + "npart_pre"][0])
+                out[f"s{s}/{p}npart"] = np.array([npre, n], np.int64)
+                out[f"meta/{p}mass_charge"] = d[p + "mass_charge"]
+                for a in PRTL:
+                    v = d[p + a]
+                    if v.size == 0:
+                        continue
+                    if s in (s0, s1):
+                        out[f"s{s}/{p}{a}"] = v[:n]
+                    else:
+                        out[f"s{s}/{p}{a}_sum"] = np.array([checksum(v[:npre])], np.uint64)
+                        if n > npre:
+                            out[f"s{s}/{p}{a}_inj"] = v[npre:n]
+    out["meta/steps"] = np.array([s0, s1], np.int64)
+    path = os.path.join(HERE, f"run_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(name, os.path.getsize(path) // 1024, "KiB", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    for nm in (sys.argv[1:] or CASES):
+        run_case(nm)

@@ -1,0 +1,71 @@
+"""Whole-run golden cases (tests/golden/run_*.npz, made by tests/golden/make_run_golden.py from
+the reference's own entity.xc): builders that import a dumped state into the oracle stepper
+and into an entity_b200 Simulation. Shared by the CPU pin (test_run_golden.py) and the GPU
+parity test (test_gpu_run_golden.py)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+PRTL = ["i1", "i2", "i3", "dx1", "dx2", "dx3", "ux1", "ux2", "ux3", "weight", "i1_prev", "i2_prev",
+        "i3_prev", "dx1_prev", "dx2_prev", "dx3_prev", "tag"]
+
+# name -> parameters of the input file (tests/golden/run_inputs/<name>.toml)
+CASES = {
+    "stream2d": dict(n=(48, 32), dx=0.1, xmin=(0.0, 0.0), larmor0=100.0, skindepth0=10.0, ppc0=16.0,
+                     nfilter=4, pushers=[2, 0, 2, 0], cap=8192, walls=None),
+    "reconnection_small": dict(n=(64, 48), dx=0.5, xmin=(-16.0, -12.0), larmor0=0.1, skindepth0=1.0,
+                               ppc0=8.0, nfilter=8, pushers=[2, 2], cap=40000,
+                               walls=dict(ds=2.0, bg_B=1.0, cs_width=1.5, cs_y=0.0)),
+}
+
+
+def load(name):
+    return np.load(os.path.join(HERE, "golden", f"run_{name}.npz"))
+
+
+def checksum(a: np.ndarray) -> np.uint64:
+    b = np.ascontiguousarray(a).view(np.uint8)
+    pad = (-b.size) % 4
+    if pad:
+        b = np.concatenate([b, np.zeros(pad, np.uint8)])
+    w = b.view(np.uint32).astype(np.uint64)
+    k = (np.arange(w.size, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1)) & np.uint64(0xFFFFFFFF)
+    return np.uint64((w * k).sum(dtype=np.uint64))
+
+
+def scales(case):
+    from entity_b200.srpic import Scales
+    c = CASES[case]
+    return Scales(len(c["n"]), c["dx"], larmor0=c["larmor0"], skindepth0=c["skindepth0"], ppc0=c["ppc0"])
+
+
+def match_target(case, g):
+    """BoundaryFieldsInX2 of pgens/reconnection/pgen.hpp:104-135 on every component's own node:
+    bx1 = bg_B tanh((x2 - cs_y) / cs_width), everything else 0 (bg_Bguide = 0), fp32."""
+    c = CASES[case]
+    w = c["walls"]
+    f32 = np.float32
+    tgt = np.zeros(g.shape(6), f32)
+    jj = np.arange(g.n[1] + 2 * g.ng, dtype=f32) - f32(g.ng)
+    # bx1 lives on (i, j + 1/2)
+    y = ((jj + f32(0.5)) * f32(c["dx"]) + f32(c["xmin"][1])).astype(f32)
+    from oracle import bcs
+    tgt[3] = (f32(w["bg_B"]) * bcs.tanhf(((y - f32(w["cs_y"])) / f32(w["cs_width"])).astype(f32))).astype(f32)[:, None]
+    return tgt
+
+
+def match_faces(case, g):
+    """the two x2 layers as MatchFieldsIn hands them to the kernel (fields_bcs.h:72-114)"""
+    c = CASES[case]
+    f32 = np.float32
+    ds, dx, n = c["walls"]["ds"], c["dx"], c["n"]
+    ymin = float(f32(c["xmin"][1]))
+    ymax = float(f32(c["xmin"][1]) + f32(dx) * f32(n[1]))
+    nds = int(round(ds / dx))
+    ext = [n[0] + 2 * g.ng, n[1] + 2 * g.ng]
+    return [(1, ymin, ds, [0, 0], [ext[0], g.ng + nds]),
+            (1, ymax, ds, [0, g.ng + n[1] - nds], [ext[0], ext[1]])]
