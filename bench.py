@@ -191,11 +191,42 @@ def cpu_reconnection(impl, size, ppc0, nfilter, seed=0x5678):
     return o
 
 
+REF_CUT = (1024, 512)  # CPU-sized cut of configs[1]
+
+
+def entity_xc_sample(flavour, size, nsteps, skip, ppc0=32, nfilter=8):
+    """The UNMODIFIED reference (entity.xc built from /root/reference by oracle/build_entity_xc.sh,
+    binaries under baseline/_ref/) on reconnection.toml at `size`, timed by its own per-step
+    timers. Returns (info dict for the JSON line, raw result) or (None, why)."""
+    from baseline import refrun
+    if refrun.binary(flavour) is None:
+        return None, f"baseline/_ref/{flavour}/entity_reconnection.xc not built"
+    r = refrun.run(flavour, size, ppc0=ppc0, nfilter=nfilter, nsteps=nsteps, skip=skip)
+    if r is None or "error" in r:
+        return None, (r or {}).get("error", "no result")
+    t = r["s_per_step"]
+    info = {"value": r["path_pss"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+            "sample": (f"entity.xc ({'Kokkos-OpenMP' if flavour.startswith('omp') else 'Kokkos-CUDA sm_100'}, "
+                       f"pgens/reconnection incl. MATCH walls + replenish injector), {size[0]}x{size[1]} cells, "
+                       f"{ppc0} ppc, {int(r['particles'])} particles, median of the reference's own timers over "
+                       f"steps {r['steps_run'] - r['steps_timed']}..{r['steps_run'] - 1}: "
+                       "ParticlePusher+CurrentDeposit+FieldSolver+CurrentFiltering+Communications+FieldBoundaries"),
+            "push_deposit_only": r["pushdep_pss"], "whole_step_incl_injector": r["total_pss"],
+            "ms_per_step": {k: 1e3 * v for k, v in t.items()}}
+    return info, r
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    val, info, sec_per_step = reference_sample(args.steps, args.warmup)
+    info, r = entity_xc_sample("omp", REF_CUT, args.steps + args.warmup, args.warmup)
+    if info is None:
+        # entity.xc not prebuilt: the reference's kernel headers compiled in place (oracle/_ref)
+        val, info, sec_per_step = reference_sample(args.steps, args.warmup)
+        info["note"] = f"entity.xc unavailable ({r}); oracle/_ref kernels with a std::thread driver"
+    else:
+        val, sec_per_step = info["value"], r["s_per_step"]["path"]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step,
@@ -272,7 +303,30 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    # The cell sort runs every `sort_interval` steps. So that `value` does not depend on whether
+    # --steps happens to contain one: (1) the window is aligned to the sort period -- the state is
+    # sorted once, then run untimed up to the point where the K timed steps see the steady-state
+    # mean staleness of the particle order ((interval - 1) / 2 steps since the last sort); (2)
+    # the sorts inside the window are timed by their own events and replaced by the amortised
+    # charge sort_ms / sort_interval per step (sort_ms measured separately when the window holds
+    # none).
+    si = args.sort_interval
+    K, W = args.steps, args.warmup
+
+    def sort_all():
+        for sp in sim.species:
+            if sp.npart:
+                sim.ctx.sort_particles(sp.arrays, sp.npart, remove_dead=False)
+
+    pre = 0
+    if si > 0:
+        sort_all()
+        sim.step_index = 1  # "a sort ran at the end of step 0"
+        t_start = 1 + ((si - K) // 2 if K < si else 0)  # index of the first timed step
+        pre = (t_start - W - 1) % si
+        for _ in range(pre):
+            sim.step()
+    for _ in range(W):
         sim.step()
     barrier()
     sim.profile(True)
@@ -282,25 +336,44 @@ def run_ours(args):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_first = sim.step_index
     ev0.record()
-    sim.step(args.steps)
+    sim.step(K)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     launches = sim.ctx.launch_count - launches0
     prof = sim.read_profile()
+    sort_in_ms = prof["ParticleSort"][0]  # the phase is bracketed every step; empty when no sort ran
+    sorts_in = sum(1 for t_ in range(t_first, t_first + K) if si > 0 and t_ % si == 0)
+    if si > 0 and sorts_in == 0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        sort_all()
+        e1.record()
+        barrier()
+        sort_ms = e0.elapsed_time(e1)
+    else:
+        sort_ms = sort_in_ms / max(sorts_in, 1)
     sim.profile(False)
     # particles advanced per step: alive particles of the pushed species (migration leaves holes)
     n_pushed = sum(int((sp.arrays["tag"][:sp.npart] == 1).sum()) for sp in sim.species
                    if sp.pusher != eb.PUSHER_NONE)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    ms_amortised = ms - sort_in_ms + (K * sort_ms / si if si > 0 else 0.0)
+    t = torch.tensor([ms_amortised, ms, sort_ms], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([float(n_pushed)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_max, total = float(t.item()), float(cnt.item())
-    value = total * args.steps / (ms_max * 1e-3)
+    ms_max, ms_raw, sort_ms = (float(x) for x in t.tolist())
+    total = float(cnt.item())
+    value = total * K / (ms_max * 1e-3)
+    timing = {"window_ms": ms_raw, "sorts_in_window": int(sorts_in), "sort_ms": sort_ms,
+              "sort_interval": si, "sort_charge_ms_per_step": sort_ms / si if si > 0 else 0.0,
+              "ms_per_step_raw": ms_raw / K, "alignment_steps": pre,
+              "note": "ms_per_step = (window - sorts inside) / steps + sort_ms / sort_interval"}
 
     # roofline of the dominant kernel (fused push+deposit), from the in-step CUDA events
     peak, peak_src = measured_peaks()
@@ -308,14 +381,18 @@ def run_ours(args):
     per_launch_s = 1e-3 * pd_ms / max(args.steps, 1)  # one push+deposit phase per step
     b_p = 102.0 if turb else B_P_2D  # 78 B (2D), 102 B (3D) per particle-step
     achieved = n_pushed * b_p / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    with_sort_s = per_launch_s + 1e-3 * timing["sort_charge_ms_per_step"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
+                "frac_with_sort_charged": (n_pushed * b_p / with_sort_s / 1e9 / peak) if with_sort_s > 0 else 0.0,
                 "kernel": "push_deposit (all species of one step)", "peak_source": peak_src,
                 "phase_ms_per_step": {k: v[0] / max(args.steps, 1) for k, v in prof.items()}}
+    # DRAM bytes of one launch from the ncu full capture of THIS workload's kernel, else null
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         with open(tr) as f:
-            roofline["traffic"] = json.load(f).get("push_deposit_bytes_per_launch")
+            roofline["traffic"] = json.load(f).get(
+                "turbulence_push_deposit_bytes_per_launch" if turb else "push_deposit_bytes_per_launch")
 
     # end to end through the host-buffer C-ABI entry (pinned host state, H2D + D2H per step)
     e2e = None
@@ -337,9 +414,21 @@ def run_ours(args):
                "h2d_bytes_per_step": up, "d2h_bytes_per_step": down, "steps": args.e2e_steps}
         del hs
 
-    cpu = None
+    cpu = gpu_ref = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        _, cpu, _ = reference_sample(args.cpu_steps, 1)
+        # the reference's Kokkos-OpenMP entity.xc on all host cores, its own timers
+        cpu, why = entity_xc_sample("omp", REF_CUT, args.cpu_steps + 10, 10)
+        if cpu is None:
+            _, cpu, _ = reference_sample(args.cpu_steps, 1)
+            cpu["note"] = f"entity.xc unavailable ({why}); oracle/_ref kernels with a std::thread driver"
+    if rank == 0 and world == 1 and not args.no_gpu_ref and not turb:
+        # the reference's own sm_100 build (Kokkos-CUDA, Kokkos_ARCH_BLACKWELL100) on this GPU,
+        # full-size reconnection.toml at 32 ppc: "the existing Blackwell kernel" 
+        del sim
+        torch.cuda.empty_cache()
+        gpu_ref, why = entity_xc_sample("cuda", tuple(args.size), 30, 10, ppc0=args.ppc, nfilter=args.filters)
+        if gpu_ref is None:
+            gpu_ref = {"unavailable": str(why)[-300:]}
 
     if rank == 0:
         line = {
@@ -363,7 +452,8 @@ def run_ours(args):
                                        f"one block per GPU, NCCL halo + particle exchange")
                        if world > 1 else "single domain",
                        "l2": "inputs larger than L2 (particle state >> 126 MB), no flush"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_ref, "e2e": e2e,
+            "gpu_launches": int(launches),
             "clocks": clocks,
         }
         emit(line)
@@ -414,6 +504,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gpu-ref", action="store_true",
+                    help="skip the reference's own Kokkos-CUDA sm_100 build (gpu_baseline)")
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

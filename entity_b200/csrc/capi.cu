@@ -509,7 +509,7 @@ int eb200_deposit(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, 
 
 // the fused 2D zig-zag kernel that gathers from packed nodes (kernel 5)
 static bool uses_packed_nodes(const eb200_ctx* ctx, int mode) {
-  return (ctx->pd_kernel == 5 || ctx->pd_kernel == 6 || ctx->pd_kernel == 7 || ctx->pd_kernel == 0) && ctx->cfg.metric == EB200_METRIC_MINKOWSKI && ctx->cfg.grid.dim == 2 &&
+  return (ctx->pd_kernel == 5 || ctx->pd_kernel == 6 || ctx->pd_kernel == 7 || ctx->pd_kernel == 8 || ctx->pd_kernel == 0) && ctx->cfg.metric == EB200_METRIC_MINKOWSKI && ctx->cfg.grid.dim == 2 &&
          ctx->cfg.shape_order == 0 && mode == EB200_DEPOSIT_AGGREGATED;
 }
 
@@ -828,8 +828,8 @@ int eb200_metric_eval(int metric, const int* n_active, const float* metric_param
 
 int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which) {
   ENTER(ctx);
-  REQUIRE(ctx, which >= 0 && which <= 7,
-          "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4, 4 shared-memory tiles, 5 vec4 + packed nodes, 6 pipelined, 7 shared-memory resident");
+  REQUIRE(ctx, which >= 0 && which <= 8,
+          "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4, 4 shared-memory tiles, 5 vec4 + packed nodes, 6 pipelined, 7 shared-memory resident, 8 vec4 + packed nodes + moment deposit");
   ctx->pd_kernel = which;
   return EB200_OK;
 }

@@ -695,6 +695,58 @@ namespace eb200 {
            !c.has_atmosphere;
   }
 
+  // sr.hpp:659-751 (Cartesian): what happens to a particle that left [0, ni) along some axis --
+  // periodic wrap (shifts i_prev too), absorption, reflection -- and the migration send tag
+  template <int D>
+#ifdef EB200_BC_NOINLINE
+  __device__ __noinline__ void particle_boundaries(const PushArgs& A, Prtl<D>& P) {
+#else
+  __device__ __forceinline__ void particle_boundaries(const PushArgs& A, Prtl<D>& P) {
+#endif
+    const eb200_pusher_t& c = A.c;
+    int lin = 0, centre = 0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const int ni  = A.ni[a];
+      bool      inv = false;
+      if (P.i[a] < 0) {
+        const int b = c.pbc[2 * a];
+        if (b == EB200_PBC_PERIODIC) {
+          P.i[a]  += ni;
+          P.ip[a] += ni;
+        } else if (b == EB200_PBC_ABSORB) {
+          P.tag = 0;
+        } else if (b == EB200_PBC_REFLECT || b == EB200_PBC_AXIS) {
+          P.i[a] = 0;
+          P.d[a] = ONE - P.d[a];
+          inv    = (b == EB200_PBC_REFLECT);
+        }
+      } else if (P.i[a] >= ni) {
+        const int b = c.pbc[2 * a + 1];
+        if (b == EB200_PBC_PERIODIC) {
+          P.i[a]  -= ni;
+          P.ip[a] -= ni;
+        } else if (b == EB200_PBC_ABSORB) {
+          P.tag = 0;
+        } else if (b == EB200_PBC_REFLECT || b == EB200_PBC_AXIS) {
+          P.i[a] = ni - 1;
+          P.d[a] = ONE - P.d[a];
+          inv    = (b == EB200_PBC_REFLECT);
+        }
+      }
+      if (inv) {
+        P.u[a] = -P.u[a];
+      }
+      const int dir = (P.i[a] < 0) ? 0 : ((P.i[a] >= ni) ? 2 : 1);
+      lin           = lin * 3 + dir;
+      centre        = centre * 3 + 1;
+    }
+    if (c.tag_outgoing && lin != centre) {
+      // mpi::SendTag: 2 + lexicographic index of the direction, null direction skipped
+      P.tag = static_cast<short>((2 + lin - (lin > centre ? 1 : 0)) * P.tag);
+    }
+  }
+
   template <int D, int O, class EM, bool LEAN = false>
   // returns true when the particle left [0, ni) along some axis, i.e. when the boundary block
   // ran (only then can tag, i_prev or u have been touched by a boundary condition)
@@ -762,47 +814,7 @@ namespace eb200 {
     if (inside) {
       return false;
     }
-    int lin = 0, centre = 0;
-#pragma unroll
-    for (int a = 0; a < D; ++a) {
-      const int ni  = A.ni[a];
-      bool      inv = false;
-      if (P.i[a] < 0) {
-        const int b = c.pbc[2 * a];
-        if (b == EB200_PBC_PERIODIC) {
-          P.i[a]  += ni;
-          P.ip[a] += ni;
-        } else if (b == EB200_PBC_ABSORB) {
-          P.tag = 0;
-        } else if (b == EB200_PBC_REFLECT || b == EB200_PBC_AXIS) {
-          P.i[a] = 0;
-          P.d[a] = ONE - P.d[a];
-          inv    = (b == EB200_PBC_REFLECT);
-        }
-      } else if (P.i[a] >= ni) {
-        const int b = c.pbc[2 * a + 1];
-        if (b == EB200_PBC_PERIODIC) {
-          P.i[a]  -= ni;
-          P.ip[a] -= ni;
-        } else if (b == EB200_PBC_ABSORB) {
-          P.tag = 0;
-        } else if (b == EB200_PBC_REFLECT || b == EB200_PBC_AXIS) {
-          P.i[a] = ni - 1;
-          P.d[a] = ONE - P.d[a];
-          inv    = (b == EB200_PBC_REFLECT);
-        }
-      }
-      if (inv) {
-        P.u[a] = -P.u[a];
-      }
-      const int dir = (P.i[a] < 0) ? 0 : ((P.i[a] >= ni) ? 2 : 1);
-      lin           = lin * 3 + dir;
-      centre        = centre * 3 + 1;
-    }
-    if (c.tag_outgoing && lin != centre) {
-      // mpi::SendTag: 2 + lexicographic index of the direction, null direction skipped
-      P.tag = static_cast<short>((2 + lin - (lin > centre ? 1 : 0)) * P.tag);
-    }
+    particle_boundaries<D>(A, P);
     return true;
   }
 

@@ -6,6 +6,9 @@
 #include "particle.cuh"
 #include "launch.h"
 
+#include <mutex>
+#include <vector>
+
 #include <cub/device/device_radix_sort.cuh>
 
 namespace eb200 {
@@ -647,6 +650,314 @@ namespace eb200 {
         }
       }
     }
+
+    /* ------------- moment-accumulating push + deposit (2D zig-zag, packed nodes, plain Boris) */
+#if !EB200_STRICT
+    // Kernel 8: the organisation of push_deposit_vec_kernel (four consecutive particles per
+    // thread, 128-bit streaming accesses, packed E/B nodes, L2 prefetch of the next wave) with
+    // the per-particle instruction count cut where the r1p capture put it:
+    //  * the zig-zag deposit is linear in eight MOMENTS of a segment -- (A, A wy, B, B wx, F,
+    //    F wx, F wy, F wx wy) with A / B the in-plane charge fluxes, F the out-of-plane one and
+    //    (wx, wy) the segment's midpoint -- from which the eight node values of
+    //    currents_deposit.hpp:171-405 follow by seven additions. Moments are what is summed in
+    //    registers and in the warp's segmented reduction; the conversion runs once per flush
+    //    instead of once per particle and segment. A particle that stays in its cell (97 % of
+    //    the cold background) contributes ONE merged segment (midpoint of the move + the
+    //    dx dy / 16 cross term of the two half segments); only crossers take the two-segment
+    //    form, under a branch;
+    //  * 1 / gamma of the position push is reused for the out-of-plane velocity;
+    //  * the staggered gather weights come from a compare + select instead of float -> int ->
+    //    float conversions (XU pipe), same values;
+    //  * i_prev is re-stored only for the rare particle that went through the boundary block.
+    // Fast build only: the rounding differs from the reference's operation order at the 1e-7
+    // level (same tolerances as kernel 5 in tests/).
+    struct Mom2 {
+      float m[8];
+    };
+
+    __device__ __forceinline__ void mom_flush(const FieldView<2>& J, int key, const float (&m)[8]) {
+      float* jx = J.p + key;
+      float* jy = jx + J.plane;
+      float* jz = jy + J.plane;
+      const int N1 = J.N1;
+      atomicAdd(jx, m[0] - m[1]);
+      atomicAdd(jx + N1, m[1]);
+      atomicAdd(jy, m[2] - m[3]);
+      atomicAdd(jy + 1, m[3]);
+      atomicAdd(jz, (m[4] - m[5]) - (m[6] - m[7]));
+      atomicAdd(jz + 1, m[5] - m[7]);
+      atomicAdd(jz + N1, m[6] - m[7]);
+      atomicAdd(jz + N1 + 1, m[7]);
+    }
+
+    // staggered / primal bilinear weights without conversions; same values as gather_packed()
+    __device__ __forceinline__ void gather_packed_sel(const PackedEM2& F, int ng, const int (&i)[2],
+                                                      const float (&d)[2], float* e0, float* b0) {
+      float          wp[2][2], wd[2][2];
+      unsigned       back[2];
+      const unsigned st[2] = { 24u, F.rowb };
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const float h  = d[a] + HALF;
+        const bool  up = h >= ONE; // == static_cast<int>(d + 1/2) for d in [0, 1)
+        back[a]        = up ? 0u : st[a];
+        wp[a][0]       = ONE - d[a];
+        wp[a][1]       = d[a];
+        wd[a][0]       = (up ? TWO : ONE) - h;
+        wd[a][1]       = ONE - wd[a][0];
+      }
+      const unsigned b00 = static_cast<unsigned>(i[0] + ng) * 24u +
+                           static_cast<unsigned>(i[1] + ng) * F.rowb;
+      const unsigned b10 = b00 - back[0], b01 = b00 - back[1], b11 = b10 - back[1];
+      {
+        const char*  q  = F.p + b10;
+        const char*  r  = F.p + (b10 + F.rowb);
+        const float2 q0 = ld_keep2(q), q1 = ld_keep2(q + 24), r0 = ld_keep2(r), r1 = ld_keep2(r + 24);
+        const float* wx = wd[0];
+        const float* wy = wp[1];
+        e0[0] = (q0.x * wx[0] + q1.x * wx[1]) * wy[0] + (r0.x * wx[0] + r1.x * wx[1]) * wy[1];
+        b0[1] = (q0.y * wx[0] + q1.y * wx[1]) * wy[0] + (r0.y * wx[0] + r1.y * wx[1]) * wy[1];
+      }
+      {
+        const char*  q  = F.p + (b01 + 8u);
+        const char*  r  = F.p + (b01 + 8u + F.rowb);
+        const float2 q0 = ld_keep2(q), q1 = ld_keep2(q + 24), r0 = ld_keep2(r), r1 = ld_keep2(r + 24);
+        const float* wx = wp[0];
+        const float* wy = wd[1];
+        e0[1] = (q0.x * wx[0] + q1.x * wx[1]) * wy[0] + (r0.x * wx[0] + r1.x * wx[1]) * wy[1];
+        b0[0] = (q0.y * wx[0] + q1.y * wx[1]) * wy[0] + (r0.y * wx[0] + r1.y * wx[1]) * wy[1];
+      }
+      {
+        const char*  q  = F.p + (b00 + 16u);
+        const char*  r  = F.p + (b00 + 16u + F.rowb);
+        const float* wx = wp[0];
+        const float* wy = wp[1];
+        e0[2] = (ld_keep1(q) * wx[0] + ld_keep1(q + 24) * wx[1]) * wy[0] +
+                (ld_keep1(r) * wx[0] + ld_keep1(r + 24) * wx[1]) * wy[1];
+      }
+      {
+        const char*  q  = F.p + (b11 + 20u);
+        const char*  r  = F.p + (b11 + 20u + F.rowb);
+        const float* wx = wd[0];
+        const float* wy = wd[1];
+        b0[2] = (ld_keep1(q) * wx[0] + ld_keep1(q + 24) * wx[1]) * wy[0] +
+                (ld_keep1(r) * wx[0] + ld_keep1(r + 24) * wx[1]) * wy[1];
+      }
+    }
+
+  #ifndef EB200_MOM_MINBLOCKS
+    #define EB200_MOM_MINBLOCKS 3
+  #endif
+
+    __global__ void __launch_bounds__(256, EB200_MOM_MINBLOCKS)
+      push_deposit_mom_kernel(PushArgs A, eb200_prtls_t S, uint32_t ngroups, uint32_t ahead,
+                              PackedEM2 EB, float charge, float inv_dt, FieldView<2> J) {
+      constexpr int  D        = 2;
+      const uint32_t g        = blockIdx.x * blockDim.x + threadIdx.x;
+      const bool     in_range = g < ngroups;
+      const size_t   p0       = (size_t)g * VEC;
+      int*           ii[2]    = { S.i1, S.i2 };
+      float*         dd[2]    = { S.dx1, S.dx2 };
+      int*           iip[2]   = { S.i1_prev, S.i2_prev };
+      float*         ddp[2]   = { S.dx1_prev, S.dx2_prev };
+      int            iv[2][VEC];
+      float          dv[2][VEC], uv[3][VEC], wv[VEC];
+      short          tv[VEC] = { 0, 0, 0, 0 };
+      bool           all_pushed = false;
+  #ifndef EB200_VEC_NOPREFETCH
+      if (threadIdx.x == 0) {
+        const size_t q0 = ((size_t)blockIdx.x + ahead) * blockDim.x * VEC;
+        if (q0 + (size_t)blockDim.x * VEC <= (size_t)ngroups * VEC) {
+          const unsigned b4 = blockDim.x * VEC * 4, b2 = blockDim.x * VEC * 2;
+  #pragma unroll
+          for (int a = 0; a < D; ++a) {
+            tma::prefetch_l2(ii[a] + q0, b4);
+            tma::prefetch_l2(dd[a] + q0, b4);
+          }
+          tma::prefetch_l2(S.ux1 + q0, b4);
+          tma::prefetch_l2(S.ux2 + q0, b4);
+          tma::prefetch_l2(S.ux3 + q0, b4);
+          tma::prefetch_l2(S.weight + q0, b4);
+          tma::prefetch_l2(S.tag + q0, b2);
+        }
+      }
+  #endif
+      if (in_range) {
+        ld4<short4>(S.tag + p0, tv);
+  #pragma unroll
+        for (int a = 0; a < D; ++a) {
+          ld4<int4>(ii[a] + p0, iv[a]);
+          ld4<float4>(dd[a] + p0, dv[a]);
+        }
+        ld4<float4>(S.ux1 + p0, uv[0]);
+        ld4<float4>(S.ux2 + p0, uv[1]);
+        ld4<float4>(S.ux3 + p0, uv[2]);
+        ld4<float4>(S.weight + p0, wv);
+        all_pushed = (tv[0] == 1) && (tv[1] == 1) && (tv[2] == 1) && (tv[3] == 1);
+        if (all_pushed) {
+  #pragma unroll
+          for (int a = 0; a < D; ++a) {
+            st4<int4>(iip[a] + p0, iv[a]);
+            st4<float4>(ddp[a] + p0, dv[a]);
+          }
+        }
+      }
+      const int   G    = A.ng;
+      const float cdx  = A.c.dx;
+      const float cpos = A.c.dt * A.inv_dx; // dt / dx
+      float       acc[8];
+  #pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n] = ZERO;
+      int cur = -1; // cell whose moments `acc` holds
+  #pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        if (tv[k] != 1) {
+          continue;
+        }
+        int   ip[2] = { iv[0][k], iv[1][k] };
+        float dp[2] = { dv[0][k], dv[1][k] };
+        float u[3]  = { uv[0][k], uv[1][k], uv[2][k] };
+        float ec[3], bc[3];
+        gather_packed_sel(EB, G, ip, dp, ec, bc);
+        ec[0] *= cdx;
+        ec[1] *= cdx;
+        bc[0] *= cdx;
+        bc[1] *= cdx;
+        boris(A.ndh, u, ec, bc);
+        const float ig = rsqrtf(ONE + nsq(u)); // 1 / gamma
+        const float cs = cpos * ig;
+        int         in[2];
+        float       dn[2];
+  #pragma unroll
+        for (int a = 0; a < D; ++a) {
+          const float x    = fmaf(u[a], cs, dp[a]);
+          const bool  up   = x >= ONE;
+          const bool  down = x < ZERO;
+          in[a]            = ip[a] + (up ? 1 : 0) - (down ? 1 : 0);
+          dn[a]            = up ? (x - ONE) : (down ? (x + ONE) : x);
+        }
+        short tag = 1;
+        if ((static_cast<unsigned>(in[0]) >= static_cast<unsigned>(A.ni[0])) ||
+            (static_cast<unsigned>(in[1]) >= static_cast<unsigned>(A.ni[1]))) {
+          Prtl<2> P;
+          P.i[0] = in[0], P.i[1] = in[1], P.i[2] = 0;
+          P.ip[0] = ip[0], P.ip[1] = ip[1], P.ip[2] = 0;
+          P.d[0] = dn[0], P.d[1] = dn[1], P.d[2] = ZERO;
+          P.dp[0] = dp[0], P.dp[1] = dp[1], P.dp[2] = ZERO;
+          P.u[0] = u[0], P.u[1] = u[1], P.u[2] = u[2];
+          P.w   = wv[k];
+          P.tag = 1;
+          particle_boundaries<2>(A, P);
+          in[0] = P.i[0], in[1] = P.i[1];
+          dn[0] = P.d[0], dn[1] = P.d[1];
+          u[0] = P.u[0], u[1] = P.u[1], u[2] = P.u[2];
+          tag = P.tag;
+          if (tag != 1) {
+            S.tag[p0 + k] = tag;
+          }
+          if (all_pushed) {
+            // a periodic wrap shifted i_prev with i (sr.hpp:664-677)
+  #pragma unroll
+            for (int a = 0; a < D; ++a) {
+              if (P.ip[a] != ip[a]) iip[a][p0 + k] = P.ip[a];
+            }
+          }
+          ip[0] = P.ip[0], ip[1] = P.ip[1];
+        }
+        if (!all_pushed) {
+  #pragma unroll
+          for (int a = 0; a < D; ++a) {
+            iip[a][p0 + k] = ip[a];
+            ddp[a][p0 + k] = dp[a];
+          }
+        }
+  #pragma unroll
+        for (int a = 0; a < D; ++a) {
+          iv[a][k] = in[a];
+          dv[a][k] = dn[a];
+        }
+  #pragma unroll
+        for (int a = 0; a < 3; ++a) uv[a][k] = u[a];
+        if (tag == 0) {
+          continue; // absorbed by a boundary: no current
+        }
+        // ---- deposit
+        const float coeff = wv[k] * charge;
+        const float Q     = coeff * inv_dt;
+        float       vz    = u[2];
+        if (!(fabsf(vz) <= 3.4028235e38f)) vz = ZERO; // nan / inf guard of currents_deposit.hpp
+        const float Fz  = coeff * (vz * ig);
+        const int   di0 = in[0] - ip[0], di1 = in[1] - ip[1];
+        const int   key0 = (ip[0] + G) + (ip[1] + G) * J.N1;
+        float       m[8];
+        if ((di0 | di1) == 0) {
+          // one merged segment: midpoint weights + the cross term of the two half segments
+          const float mx = HALF * (dn[0] + dp[0]), my = HALF * (dn[1] + dp[1]);
+          const float lx = dn[0] - dp[0], ly = dn[1] - dp[1];
+          const float Ax = Q * lx, By = Q * ly;
+          m[0] = Ax;
+          m[1] = Ax * my;
+          m[2] = By;
+          m[3] = By * mx;
+          m[4] = Fz;
+          m[5] = Fz * mx;
+          m[6] = Fz * my;
+          m[7] = Fz * fmaf(mx, my, INV_16 * lx * ly);
+        } else {
+          // relay point seen from the old / new cell; two segments, the second in the new cell
+          const float r0x = (di0 == 0) ? HALF * (dn[0] + dp[0]) : ((di0 > 0) ? ONE : ZERO);
+          const float r1x = (di0 == 0) ? r0x : ((di0 > 0) ? ZERO : ONE);
+          const float r0y = (di1 == 0) ? HALF * (dn[1] + dp[1]) : ((di1 > 0) ? ONE : ZERO);
+          const float r1y = (di1 == 0) ? r0y : ((di1 > 0) ? ZERO : ONE);
+          const float Fh  = HALF * Fz;
+          {
+            const float wx = HALF * (dn[0] + r1x), wy = HALF * (dn[1] + r1y);
+            const float Ax = (dn[0] - r1x) * Q, By = (dn[1] - r1y) * Q;
+            const float s[8] = { Ax, Ax * wy, By, By * wx, Fh, Fh * wx, Fh * wy, Fh * wx * wy };
+            mom_flush(J, (in[0] + G) + (in[1] + G) * J.N1, s);
+          }
+          const float wx = HALF * (r0x + dp[0]), wy = HALF * (r0y + dp[1]);
+          const float Ax = (r0x - dp[0]) * Q, By = (r0y - dp[1]) * Q;
+          m[0] = Ax;
+          m[1] = Ax * wy;
+          m[2] = By;
+          m[3] = By * wx;
+          m[4] = Fh;
+          m[5] = Fh * wx;
+          m[6] = Fh * wy;
+          m[7] = Fh * wx * wy;
+        }
+        if (key0 != cur) {
+          if (cur >= 0) {
+            mom_flush(J, cur, acc);
+          }
+          cur = key0;
+  #pragma unroll
+          for (int n = 0; n < 8; ++n) acc[n] = m[n];
+        } else {
+  #pragma unroll
+          for (int n = 0; n < 8; ++n) acc[n] += m[n];
+        }
+      }
+      if (in_range) {
+  #pragma unroll
+        for (int a = 0; a < D; ++a) {
+          st4<int4>(ii[a] + p0, iv[a]);
+          st4<float4>(dd[a] + p0, dv[a]);
+        }
+        st4<float4>(S.ux1 + p0, uv[0]);
+        st4<float4>(S.ux2 + p0, uv[1]);
+        st4<float4>(S.ux3 + p0, uv[2]);
+      }
+      // what is left in `acc`: one segmented reduction of the moments over the warp
+      const WarpRun run = warp_runs(cur);
+  #pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n] = run_sum(acc[n], run);
+      if (run.head && cur >= 0) {
+        mom_flush(J, cur, acc);
+      }
+    }
+#endif // !EB200_STRICT
 
     /* ------------- pipelined push + deposit (2D zig-zag, packed nodes, persistent CTAs) */
     // The vectorised kernel spends its stall cycles in two dependent waits per thread: the
@@ -1392,6 +1703,35 @@ namespace eb200 {
       return cudaGetLastError();
     }
 
+
+    // resident CTAs of one wave of `kern` on the current device (occupancy x SM count), cached per
+    // (device, kernel): the prefetch distance of the vectorised kernels
+    inline uint32_t resident_ctas(const void* kern, int threads) {
+      struct Key {
+        int         dev;
+        const void* f;
+        uint32_t    v;
+      };
+      static std::mutex       mu;
+      static std::vector<Key> cache;
+      int                     dev = 0;
+      cudaGetDevice(&dev);
+      std::lock_guard<std::mutex> lk(mu);
+      for (const Key& k : cache) {
+        if (k.dev == dev && k.f == kern) return k.v;
+      }
+      int nsm = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
+      const uint32_t v = (uint32_t)(nsm * (per_sm > 0 ? per_sm : 1));
+      cache.push_back({ dev, kern, v });
+      return v;
+    }
+
+    inline bool mom_disabled() {
+      static const bool off = getenv("EB200_NO_MOM") != nullptr;
+      return off;
+    }
     template <int D, int O>
     cudaError_t launch_push_deposit(const PushArgs& A, const eb200_prtls_t& S, uint32_t npart,
                                     const eb200_grid_t& g, const float* em, float* cur,
@@ -1481,7 +1821,29 @@ namespace eb200 {
           p_begin = ngroups * VEC;
           if (p_begin == npart) return cudaGetLastError();
         }
-        if ((which == 5 || which == 0) && p_begin == 0 && packed != nullptr && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) &&
+#if !EB200_STRICT
+        // 8 (what 0 selects for a plain Boris push): moment-accumulating form of kernel 5
+        if ((which == 8 || (which == 0 && !mom_disabled())) && lean_pusher(A.c) && p_begin == 0 &&
+            packed != nullptr && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) && npart >= VEC &&
+            J.plane * 3 < 0x7fffffffL && EB.plane * 24 < 0xffffffffL) {
+          if (do_pack) {
+            pack_em2d_kernel<<<(unsigned)((EB.plane + 255) / 256), 256, 0, st>>>(
+              em, EB.plane, reinterpret_cast<float2*>(packed));
+            count_launch();
+          }
+          PackedEM2 PK;
+          PK.p    = reinterpret_cast<const char*>(packed);
+          PK.rowb = 24u * (unsigned)EB.N1;
+          const uint32_t ngroups = npart / VEC;
+          const uint32_t wave    = resident_ctas(reinterpret_cast<const void*>(push_deposit_mom_kernel), 256);
+          push_deposit_mom_kernel<<<(ngroups + 255) / 256, 256, 0, st>>>(A, S, ngroups, wave, PK,
+                                                                        A.c.charge, inv_dt, J);
+          count_launch();
+          p_begin = ngroups * VEC;
+          if (p_begin == npart) return cudaGetLastError();
+        }
+#endif
+        if ((which == 5 || which == 0 || which == 8) && p_begin == 0 && packed != nullptr && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) &&
             npart >= VEC && J.plane < 0x7fffffffL && EB.plane * 24 < 0xffffffffL) {
           if (do_pack) {
             pack_em2d_kernel<<<(unsigned)((EB.plane + 255) / 256), 256, 0, st>>>(

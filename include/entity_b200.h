@@ -199,9 +199,10 @@ int eb200_pack_fields_release(eb200_ctx_t* ctx);
  * 0 = automatic (default), 1 = one particle per thread, 2 = TMA-staged persistent chunks,
  * 3 = four particles per thread with 128-bit accesses (zig-zag only), 4 = 3 with the E/B
  * nodes of a CTA staged in shared memory, 5 = 3 gathering from the packed E/B nodes (2D; what
- * 0 selects for 2D zig-zag), 6 = pipelined persistent CTAs, 7 = shared-memory resident
- * slices. A tuning knob for measurements; results are the same up to the summation order
- * of J. */
+ * 0 selects for 2D zig-zag in the strict build), 6 = pipelined persistent CTAs, 7 =
+ * shared-memory resident slices, 8 = 5 with the zig-zag deposit accumulated as segment
+ * moments (fast build, plain Boris push; what 0 selects there). A tuning knob for
+ * measurements; results are the same up to the summation order of J. */
 int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which);
 
 /* ------------------------------------------------- single-domain ghost exchange */

@@ -235,12 +235,14 @@ def test_errors(eb):
         ctx.push(ctx.make_pusher(dt=0.1, pusher_flags=0), {}, 0, None)
 
 
-@pytest.mark.parametrize("which", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("which", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("strict", [False, True])
 @pytest.mark.parametrize("order_kind", ["sorted", "stale", "random"])
 def test_fused_kernels_wide_mesh(eb, orc_mod, which, strict, order_kind):
     """Every fused push+deposit kernel (1 per-thread, 2 TMA chunks, 3 four particles per thread,
-    4 shared-memory field tile, 5 four per thread gathering from packed nodes) on a mesh wide enough for the tile kernel, on cell-sorted
+    4 shared-memory field tile, 5 four per thread gathering from packed nodes, 6 pipelined,
+    7 shared-memory resident, 8 moment-accumulating deposit -- fast build only, the strict
+    build falls through to kernel 5) on a mesh wide enough for the tile kernel, on cell-sorted
     particles, on a 'stale' order (sorted, then pushed twice without re-sorting: the state
     between two sorts) and on a random order; two consecutive steps so that crossings, periodic
     wraps and strays outside the tile all occur. Strict build: particles bit-exact (the pusher
