@@ -268,31 +268,33 @@ def run_ours(args):
     if turb:
         # configs[2]-shaped block (3D, T = 1 pair plasma, 3rd-order shapes, 4 filter passes) at the
         # n^3 given: a second bench line for the Esirkepov path, single GPU, not the headline
-        if world > 1:
-            raise SystemExit("bench.py --turbulence: single-GPU line")
         size = (args.turbulence,) * 3
         if args.sort_interval == 40:
             args.sort_interval = 5  # hot plasma, wide windows: the order decays within a few steps
         sim = workloads.turbulence(size, ppc0=args.ppc if args.ppc != 32 else 16, order=3, nfilter=4,
                                    fused=not args.unfused, sort_interval=args.sort_interval,
-                                   device=local, deposit_mode=dmode, seed=0x9abc)
+                                   device=local, deposit_mode=dmode, seed=0x9abc + rank,
+                                   capacity_factor=1.0 if world == 1 else 1.25)
     else:
         sim = workloads.reconnection(size, ppc0=args.ppc, nfilter=args.filters, fused=not args.unfused,
                                      sort_interval=args.sort_interval, device=local,
                                      deposit_mode=dmode, seed=0x5678 + rank, walls=args.walls,
                                      capacity_factor=1.0 if world == 1 else 1.1)
-    decomposition = [1, 1]
+    decomposition = [1] * len(size)
     if world > 1:
         # spatial block decomposition as the reference's reconnection.toml asks ([-1, 2]); every
         # GPU owns one block of `size` cells (weak scaling), fields and particles cross block
         # boundaries through the library's NCCL exchange
         from entity_b200 import lib as L
         from entity_b200.metadomain import Metadomain, bootstrap_unique_id
-        dec = [-1, 2] if world % 2 == 0 else [-1, 1]
+        if turb:
+            dec = [-1, -1, -1]  # configs[2]: 2x2x2 blocks on 8 GPUs
+        else:
+            dec = [-1, 2] if world % 2 == 0 else [-1, 1]
         if args.decomp:
             dec = list(args.decomp)
-        nd = [len(e) for e in L.decompose(world, [size[0] * world, size[1] * world], dec)]
-        mdm = Metadomain((size[0] * nd[0], size[1] * nd[1]), world, rank, dec)
+        nd = [len(e) for e in L.decompose(world, [s_ * world for s_ in size], dec)]
+        mdm = Metadomain(tuple(s_ * n_ for s_, n_ in zip(size, nd)), world, rank, dec)
         assert mdm.local_n == size
         mdm.attach(sim, bootstrap_unique_id())
         decomposition = nd
@@ -316,7 +318,7 @@ def run_ours(args):
     def sort_all():
         for sp in sim.species:
             if sp.npart:
-                sim.ctx.sort_particles(sp.arrays, sp.npart, remove_dead=False)
+                sim.ctx.sort_particles(sp.arrays, sp.npart, remove_dead=2)  # EB200_SORT_SKIP_PREV, as the step sorts
 
     pre = 0
     if si > 0:
@@ -433,7 +435,8 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "timing": timing,
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": (f"turbulence-shaped 3D Cartesian SR pair plasma, {size[0]}^3 cells, "
                                     f"{16 if args.ppc == 32 else args.ppc} ppc, 3rd-order shapes (reduced from 1024^3)"
@@ -448,7 +451,7 @@ def run_ours(args):
                        "current_filters": 4 if turb else args.filters, "particles_per_gpu": n_pushed0,
                        "fused_push_deposit": not args.unfused, "sort_interval": args.sort_interval,
                        "deposit": args.deposit,
-                       "parallelism": (f"domain decomposition {decomposition[0]}x{decomposition[1]}, "
+                       "parallelism": (f"domain decomposition {'x'.join(str(n_) for n_ in decomposition)}, "
                                        f"one block per GPU, NCCL halo + particle exchange")
                        if world > 1 else "single domain",
                        "l2": "inputs larger than L2 (particle state >> 126 MB), no flush"},
@@ -499,7 +502,7 @@ def main():
     ap.add_argument("--walls", action="store_true",
                     help="x2 boundaries of reconnection.toml (fields MATCH, particles ABSORB) instead "
                          "of the periodic core; single GPU, no replenishing injector")
-    ap.add_argument("--decomp", type=int, nargs=2, default=None,
+    ap.add_argument("--decomp", type=int, nargs="+", default=None,
                     help="override the block decomposition request (default -1 2, as reconnection.toml)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=4)

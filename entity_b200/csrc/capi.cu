@@ -49,6 +49,10 @@ struct eb200_ctx {
   uint64_t       launches_at_init;
   int            pd_kernel = 0; // eb200_set_pd_kernel
   eb200::Scratch packed;        // E/B repacked node by node for the fused 2D zig-zag kernel
+  eb200::Scratch packed_j;      // J as 16-byte nodes {jx1, jx2, jx3, -}: target of kernel 8's flushes
+  void*          packed_j_zeroed = nullptr; // the allocation that has been cleared
+  float*         packed_j_cur    = nullptr; // planes the pending nodes belong to (while held)
+  cudaStream_t   packed_j_stream = nullptr;
   eb200::Scratch stats;         // one double: the device-side accumulator of the reductions
   const float*   packed_hold = nullptr; // em the packed copy is guaranteed current for
   bool           no_filter_fusion = false; // EB200_NO_FILTER_FUSION=1: pass-by-pass filter
@@ -233,6 +237,7 @@ void eb200_finalize(eb200_ctx_t* ctx) {
   cudaSetDevice(ctx->cfg.device);
   ctx->scratch.release();
   ctx->packed.release();
+  ctx->packed_j.release();
   ctx->stats.release();
   if (ctx->comm) eb200::comm_delete(ctx->comm);
   eb200::engine_state_delete(ctx->engine);
@@ -287,6 +292,20 @@ int eb200_currents_ampere(eb200_ctx_t* ctx, float* em, float* cur, float coeff, 
                     VARIANT_CALL(ctx, currents_ampere(ctx->cfg.grid, em, cur, coeff, ppc0,
                                                       (cudaStream_t)stream)),
                     "currents_ampere");
+}
+
+int eb200_currents_ampere_ext(eb200_ctx_t* ctx, float* em, float* cur, float coeff, float ppc0,
+                              const eb200_ext_current_t* ext, eb200_stream_t stream) {
+  ENTER(ctx);
+  if (ext == nullptr) return eb200_currents_ampere(ctx, em, cur, coeff, ppc0, stream);
+  REQUIRE(ctx, em != nullptr && cur != nullptr, "null field");
+  REQUIRE_MINK(ctx, "eb200_currents_ampere_ext");
+  REQUIRE(ctx, ext->nmodes >= 0 && ext->nmodes <= EB200_MAX_MODES, "ext_current: bad number of modes");
+  const float* mp = ctx->cfg.metric_params; // dx, x1min, x2min, x3min
+  return check_cuda(ctx,
+                    VARIANT_CALL(ctx, currents_ampere_ext(ctx->cfg.grid, em, cur, coeff, ppc0, *ext,
+                                                          mp[0], mp + 1, (cudaStream_t)stream)),
+                    "currents_ampere_ext");
 }
 
 static size_t field_bytes(const eb200_grid_t& g, int ncomp) {
@@ -540,12 +559,45 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
       do_pack = ctx->packed_hold != em;
     }
   }
-  return check_cuda(ctx,
-                    VARIANT_CALL(ctx, push_deposit_sr(ctx->cfg.grid, ctx->cfg.shape_order,
-                                                      *pusher, *prtls, npart, em, cur,
-                                                      mode | (ctx->pd_kernel << 8), packed,
-                                                      do_pack, (cudaStream_t)stream)),
-                    "push_deposit_sr");
+  // kernel 8 flushes into 16-byte J nodes; they are added to the planes right away, or when the
+  // engine releases its hold (one unpack per step instead of one per species)
+  float* pj      = nullptr;
+  bool   pj_used = false;
+  if (packed != nullptr && !ctx->cfg.strict_fp) {
+    const size_t nb = packed_bytes(ctx) / 24 * 16;
+    if (check_cuda(ctx, ctx->packed_j.reserve(nb), "packed J") == EB200_OK) {
+      if (ctx->packed_j_zeroed != ctx->packed_j.ptr) {
+        rc = check_cuda(ctx, cudaMemsetAsync(ctx->packed_j.ptr, 0, nb, (cudaStream_t)stream), "packed J");
+        if (rc) return rc;
+        ctx->packed_j_zeroed = ctx->packed_j.ptr;
+      }
+      pj = (float*)ctx->packed_j.ptr;
+      if (ctx->packed_j_cur != nullptr && ctx->packed_j_cur != cur) {
+        // pending nodes of another array: settle them first
+        rc = check_cuda(ctx, VARIANT_CALL(ctx, unpack_j4(ctx->cfg.grid, pj, ctx->packed_j_cur,
+                                                         ctx->packed_j_stream)), "unpack_j4");
+        if (rc) return rc;
+        ctx->packed_j_cur = nullptr;
+      }
+    }
+  }
+  rc = check_cuda(ctx,
+                  VARIANT_CALL(ctx, push_deposit_sr(ctx->cfg.grid, ctx->cfg.shape_order, *pusher,
+                                                    *prtls, npart, em, cur,
+                                                    mode | (ctx->pd_kernel << 8), packed, do_pack,
+                                                    (cudaStream_t)stream, pj, &pj_used)),
+                  "push_deposit_sr");
+  if (rc) return rc;
+  if (pj_used) {
+    if (ctx->packed_hold == em) {
+      ctx->packed_j_cur    = cur;
+      ctx->packed_j_stream = (cudaStream_t)stream;
+    } else {
+      rc = check_cuda(ctx, VARIANT_CALL(ctx, unpack_j4(ctx->cfg.grid, pj, cur, (cudaStream_t)stream)),
+                      "unpack_j4");
+    }
+  }
+  return rc;
 }
 
 int eb200_pack_fields_hold(eb200_ctx_t* ctx, const float* em, eb200_stream_t stream) {
@@ -687,7 +739,14 @@ int eb200_stats_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t
 }
 
 int eb200_pack_fields_release(eb200_ctx_t* ctx) {
-  if (ctx) ctx->packed_hold = nullptr;
+  if (!ctx) return EB200_OK;
+  ctx->packed_hold = nullptr;
+  if (ctx->packed_j_cur != nullptr) {
+    float* cur        = ctx->packed_j_cur;
+    ctx->packed_j_cur = nullptr;
+    return check_cuda(ctx, VARIANT_CALL(ctx, unpack_j4(ctx->cfg.grid, (float*)ctx->packed_j.ptr, cur,
+                                                       ctx->packed_j_stream)), "unpack_j4");
+  }
   return EB200_OK;
 }
 
@@ -828,8 +887,8 @@ int eb200_metric_eval(int metric, const int* n_active, const float* metric_param
 
 int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which) {
   ENTER(ctx);
-  REQUIRE(ctx, which >= 0 && which <= 8,
-          "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4, 4 shared-memory tiles, 5 vec4 + packed nodes, 6 pipelined, 7 shared-memory resident, 8 vec4 + packed nodes + moment deposit");
+  REQUIRE(ctx, which >= 0 && which <= 9,
+          "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4, 4 shared-memory tiles, 5 vec4 + packed nodes, 6 pipelined, 7 shared-memory resident, 8 vec4 + packed nodes + moment deposit, 9 3D O=3 shared-memory J tile");
   ctx->pd_kernel = which;
   return EB200_OK;
 }
@@ -881,7 +940,7 @@ int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t*
   cudaError_t e = eb200::sort_particles(ctx->cfg.grid, *prtls, *npart_inout, ctx->cfg.maxnpart,
                                         remove_dead, &n_alive, ctx->scratch, (cudaStream_t)stream);
   if (e != cudaSuccess) return check_cuda(ctx, e, "sort_particles");
-  if (remove_dead) *npart_inout = n_alive;
+  if (remove_dead & 1) *npart_inout = n_alive;
   return EB200_OK;
 }
 

@@ -79,6 +79,9 @@ namespace eb200 {
     std::vector<eb200_match_face_t> match;
     const float*                    match_target = nullptr;
     int                             match_mask   = 0;
+    // the pgen's ext_current as a mode table (eb200_srpic_set_ext_current)
+    bool                has_ext = false;
+    eb200_ext_current_t ext {};
   };
 
   struct PhaseScope {
@@ -168,6 +171,10 @@ namespace eb200 {
     int CurrentsAmpere(Domain& dom) {
       const eb200_srpic_params_t& p     = *dom.prm;
       const float                 coeff = -p.dt * p.q0 / (p.B0 * p.V0);
+      if (dom.eng && dom.eng->has_ext) {
+        return eb200_currents_ampere_ext(dom.ctx, dom.em, dom.cur, coeff, p.ppc0, &dom.eng->ext,
+                                         dom.stream);
+      }
       return eb200_currents_ampere(dom.ctx, dom.em, dom.cur, coeff, p.ppc0, dom.stream);
     }
 
@@ -291,8 +298,8 @@ namespace eb200 {
       TRY(eb200_zero_currents(dom.ctx, dom.cur, dom.stream));
       TRY(eb200_pack_fields_hold(dom.ctx, dom.em, dom.stream));
       const int rc = dom.host ? StreamedPushAndDeposit(dom, time) : PushAndDepositSpecies(dom, time);
-      eb200_pack_fields_release(dom.ctx);
-      return rc;
+      const int rc2 = eb200_pack_fields_release(dom.ctx);
+      return rc != EB200_OK ? rc : rc2;
     }
 
     static int PushAndDepositSpecies(Domain& dom, double time) {
@@ -328,7 +335,9 @@ namespace eb200 {
         eb200_species_t& sp = dom.species[s];
         if (sp.npart == 0) continue;
         uint32_t n = sp.npart;
-        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, clear ? 1 : 0, dom.stream));
+        // i*_prev / dx*_prev are dead values here (rewritten by the next push before any read)
+        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | EB200_SORT_SKIP_PREV,
+                                 dom.stream));
         sp.npart = n;
       }
       return EB200_OK;
@@ -473,6 +482,19 @@ extern "C" int eb200_srpic_set_match(eb200_ctx_t* ctx, const eb200_match_face_t*
   e->match.assign(faces, faces + nfaces);
   e->match_target = nfaces > 0 ? target : nullptr;
   e->match_mask   = components_mask;
+  return EB200_OK;
+}
+
+extern "C" int eb200_srpic_set_ext_current(eb200_ctx_t* ctx, const eb200_ext_current_t* ext) {
+  if (!ctx) return EB200_ERR_ARG;
+  eb200::EngineState* e = eb200_ctx_engine_state(ctx);
+  if (ext == nullptr) {
+    e->has_ext = false;
+    return EB200_OK;
+  }
+  if (ext->nmodes < 0 || ext->nmodes > EB200_MAX_MODES) return EB200_ERR_ARG;
+  e->ext     = *ext;
+  e->has_ext = true;
   return EB200_OK;
 }
 

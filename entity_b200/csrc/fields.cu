@@ -187,6 +187,47 @@ namespace eb200 {
       }
     }
 
+    // CurrentsAmpere_kernel<D, ExtCurrent> (ampere_mink.hpp:134-215) with the external current
+    // given as a table of Fourier modes (eb200_ext_current_t); the table arrives by value
+    __device__ __forceinline__ float ext_current_at(const eb200_ext_current_t& X, int c, float x1,
+                                                    float x2, float x3, int dim) {
+      float j = ZERO;
+      for (int m = 0; m < X.nmodes; ++m) {
+        float kr = X.k[0][m] * x1 + X.k[1][m] * x2;
+        if (dim == 3) kr = kr + X.k[2][m] * x3;
+        const float cs = cosf(kr), sn = sinf(kr);
+        j += X.pref[c][m] * (X.a_real[m] * cs - X.a_imag[m] * sn);
+        if (X.pref2[c][m] != ZERO) {
+          j += X.pref2[c][m] * (X.a_real2[m] * cs - X.a_imag2[m] * sn);
+        }
+      }
+      return j;
+    }
+
+    template <int D>
+    __global__ void __launch_bounds__(256)
+      currents_ampere_ext_kernel(Box box, FieldView<D> E, FieldView<D> J, float coeff, float ppc0,
+                                 const __grid_constant__ eb200_ext_current_t X, float dx,
+                                 float x1min, float x2min, float x3min) {
+      int i1, i2, i3;
+      if (!cell_of<D>(box, (long)blockIdx.x * blockDim.x + threadIdx.x, i1, i2, i3)) return;
+      const float f1 = static_cast<float>(i1 - box.G), f2 = static_cast<float>(i2 - box.G),
+                  f3 = static_cast<float>(i3 - box.G);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        // the component's own node: staggered by half a cell along its own direction
+        const float x1 = ((c == 0) ? (f1 + HALF) : f1) * dx + x1min;
+        const float x2 = (D > 1) ? ((c == 1) ? (f2 + HALF) : f2) * dx + x2min : ZERO;
+        const float x3 = (D > 2) ? ((c == 2) ? (f3 + HALF) : f3) * dx + x3min : ZERO;
+        float       j  = J.at(i1, i2, i3, c);
+        if (c < D || D >= 1) {
+          j += ppc0 * ext_current_at(X, c, x1, x2, x3, D);
+        }
+        E.at(i1, i2, i3, c) += j * coeff;
+        J.at(i1, i2, i3, c) = j / ppc0;
+      }
+    }
+
     /* ------------------------------------------------------------ binomial filter */
     struct FilterBC {
       bool cmin[3], cmax[3]; // conductor faces
@@ -620,6 +661,20 @@ namespace eb200 {
 #define CALL(D)                                                                                \
   currents_ampere_kernel<D>                                                                    \
     <<<blocks_for(n), 256, 0, st>>>(box, FieldView<D>(g, em), FieldView<D>(g, cur), coeff, ppc0);
+      BY_DIM(g, CALL)
+#undef CALL
+      count_launch();
+      return cudaGetLastError();
+    }
+
+    cudaError_t currents_ampere_ext(const eb200_grid_t& g, float* em, float* cur, float coeff,
+                                    float ppc0, const eb200_ext_current_t& ext, float dx,
+                                    const float* xmin, cudaStream_t st) {
+      const Box  box = make_box(g);
+      const long n   = n_active(g);
+#define CALL(D)                                                                                \
+  currents_ampere_ext_kernel<D><<<blocks_for(n), 256, 0, st>>>(                                \
+    box, FieldView<D>(g, em), FieldView<D>(g, cur), coeff, ppc0, ext, dx, xmin[0], xmin[1], xmin[2]);
       BY_DIM(g, CALL)
 #undef CALL
       count_launch();

@@ -71,7 +71,9 @@ namespace eb200 {
     cudaError_t push_deposit_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,    \
                                 const eb200_prtls_t& S, uint32_t npart, const float* em,       \
                                 float* cur, int mode, float* packed, bool do_pack,             \
-                                cudaStream_t st);                                              \
+                                cudaStream_t st, float* packed_j, bool* packed_j_used);        \
+    cudaError_t unpack_j4(const eb200_grid_t& g, float* packed_j, float* cur,                 \
+                          cudaStream_t st);                                                    \
     cudaError_t pack_em2d(const eb200_grid_t& g, const float* em, float* packed,              \
                           cudaStream_t st);                                                    \
     cudaError_t faraday(const eb200_grid_t& g, float* em, float c1, float c2,                 \
@@ -79,6 +81,9 @@ namespace eb200 {
     cudaError_t ampere(const eb200_grid_t& g, float* em, float c1, float c2, cudaStream_t st); \
     cudaError_t currents_ampere(const eb200_grid_t& g, float* em, float* cur, float coeff,    \
                                 float ppc0, cudaStream_t st);                                  \
+    cudaError_t currents_ampere_ext(const eb200_grid_t& g, float* em, float* cur, float coeff, \
+                                    float ppc0, const eb200_ext_current_t& ext, float dx,      \
+                                    const float* xmin, cudaStream_t st);                       \
     cudaError_t filter_pass(const eb200_grid_t& g, float* cur, const float* buff,             \
                             const int* fbc, int extend, cudaStream_t st);                      \
     cudaError_t filter_fused(const eb200_grid_t& g, const float* src, float* dst, int passes, \

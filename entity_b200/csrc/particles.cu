@@ -423,6 +423,306 @@ namespace eb200 {
       }
     }
 
+    /* ------------- 3D third-order push + deposit with a shared-memory J tile (kernel 9) */
+#if !EB200_STRICT
+    // The per-lane deposit of a 5 x 5 x 5 Esirkepov window sends up to 375 reductions per
+    // particle to L2 and is bound by their throughput (0.019 of the HBM roofline, r1w). Here a
+    // CTA owns the J nodes around its chunk of 256 cell-sorted particles in shared memory:
+    //  * the chunk travels global -> shared -> global with cp.async.bulk (TMA), like the
+    //    stream kernel; thread t works on slot (9 t) mod 256, so the lanes of a warp are nine
+    //    particles (about one cell) apart: their windows start on consecutive nodes, their
+    //    shared-memory accesses fall into different banks and rarely on the same address;
+    //  * the tile is FIXED POINT: fp32 atomicAdd on shared memory is a compare-and-swap loop
+    //    on sm_100 (ATOMS.CAST.SPIN), integer ATOMS.ADD is one fire-and-forget instruction.
+    //    A contribution x becomes round(x * scale) with one FFMA (the 1.5 * 2^23 trick) and one
+    //    IADD; scale = 2^22 / max|w q / dt| over the chunk, so that |x * scale| < 2^21 and a
+    //    node's sum over the 256 particles stays below 2^29. Resolution = 2.4e-7 of the
+    //    largest single contribution, and the sum does not depend on the order of the adds;
+    //  * the window is evaluated in its separable form (currents_deposit.hpp:618-752 factored):
+    //    jx1(i, j, k) = -Q/3 CS1(i) F23(j, k), F23 = iS2 U3 + fS2 V3, U = iS + fS / 2,
+    //    V = fS + iS / 2, CS = running sum of fS - iS (zero from the window's last node on,
+    //    the reference's guard): two FFMA per (j, k) and FFMA + IADD + ATOMS per node;
+    //  * one flush per chunk: the non-zero tile elements go to J as coalesced fp32 reductions
+    //    (<= 56 per particle instead of 375). Particles whose window does not lie inside the
+    //    tile (strays of a stale order, chunks that straddle a mesh row) take the per-lane
+    //    global path, so the result is correct for any particle order.
+    constexpr int T3X = 48, T3Y = 10, T3Z = 10, T3N = T3X * T3Y * T3Z;
+    constexpr int T3_STAGES = 2;
+    constexpr float T3_MAGIC = 12582912.0f; // 1.5 * 2^23
+    constexpr int   T3_MAGIC_BITS = 0x4B400000;
+
+    struct Tile3Smem {
+      StreamIn<3>  in[T3_STAGES];
+      StreamOut<3> out;
+      uint64_t     full[T3_STAGES];
+      float        wmax[8];
+      int          box[4]; // touched tile rows of the current chunk: min / max of o2, min / max of o3
+      int          tile[3 * T3N];
+    };
+
+    __device__ __forceinline__ void tile_add(int* p, float a, float f) {
+      atomicAdd(p, __float_as_int(fmaf(a, f, T3_MAGIC)) - T3_MAGIC_BITS);
+    }
+
+    // the 5 x 5 x 5 window of one particle into the tile whose element (0, 0, 0) is node `org`
+    __device__ __forceinline__ void deposit_esirkepov3_tile(const Prtl<3>& P, float qs, int G,
+                                                            const int (&org)[3], int* tile,
+                                                            bool& done, int& row2, int& row3) {
+      constexpr int N = 5;
+      float iS1[N], fS1[N], iS2[N], fS2[N], iS3[N], fS3[N];
+      int   min1, max1, min2, max2, min3, max3;
+      deposit_shapes<3>(P.ip[0], P.dp[0], P.i[0], P.d[0], min1, max1, iS1, fS1);
+      deposit_shapes<3>(P.ip[1], P.dp[1], P.i[1], P.d[1], min2, max2, iS2, fS2);
+      deposit_shapes<3>(P.ip[2], P.dp[2], P.i[2], P.d[2], min3, max3, iS3, fS3);
+      const int o1 = min1 + G - org[0], o2 = min2 + G - org[1], o3 = min3 + G - org[2];
+      done = (static_cast<unsigned>(o1) <= static_cast<unsigned>(T3X - N)) &&
+             (static_cast<unsigned>(o2) <= static_cast<unsigned>(T3Y - N)) &&
+             (static_cast<unsigned>(o3) <= static_cast<unsigned>(T3Z - N));
+      if (!done) return;
+      row2 = o2;
+      row3 = o3;
+      const int d1 = max1 - min1, d2 = max2 - min2, d3 = max3 - min3;
+      float     A1[N - 1], A2[N - 1], A3[N - 1];
+      {
+        float c1 = ZERO, c2 = ZERO, c3 = ZERO;
+#pragma unroll
+        for (int n = 0; n < N - 1; ++n) {
+          c1 += fS1[n] - iS1[n];
+          c2 += fS2[n] - iS2[n];
+          c3 += fS3[n] - iS3[n];
+          A1[n] = (n < d1) ? qs * c1 : ZERO;
+          A2[n] = (n < d2) ? qs * c2 : ZERO;
+          A3[n] = (n < d3) ? qs * c3 : ZERO;
+        }
+      }
+      float U2[N], V2[N], U3[N], V3[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        U2[n] = fmaf(HALF, fS2[n], iS2[n]);
+        V2[n] = fmaf(HALF, iS2[n], fS2[n]);
+        U3[n] = fmaf(HALF, fS3[n], iS3[n]);
+        V3[n] = fmaf(HALF, iS3[n], fS3[n]);
+      }
+      int* t0 = tile + (o3 * T3Y + o2) * T3X + o1;
+      // jx1
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float f = fmaf(iS2[j], U3[k], fS2[j] * V3[k]);
+#pragma unroll
+          for (int i = 0; i < N - 1; ++i) tile_add(t0 + (k * T3Y + j) * T3X + i, A1[i], f);
+        }
+      }
+      // jx2
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float f = fmaf(iS1[i], U3[k], fS1[i] * V3[k]);
+#pragma unroll
+          for (int j = 0; j < N - 1; ++j) tile_add(t0 + T3N + (k * T3Y + j) * T3X + i, A2[j], f);
+        }
+      }
+      // jx3
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float f = fmaf(iS1[i], U2[j], fS1[i] * V2[j]);
+#pragma unroll
+          for (int k = 0; k < N - 1; ++k) tile_add(t0 + 2 * T3N + (k * T3Y + j) * T3X + i, A3[k], f);
+        }
+      }
+    }
+
+    // the rare out-of-tile particle: per-lane reductions straight to global memory, kept out of
+    // line so that its registers do not weigh on the tile path
+    __device__ __noinline__ void deposit_esirkepov3_stray(const Prtl<3>& P, float charge,
+                                                          float inv_dt, float dxc, int G,
+                                                          const FieldView<3>& J) {
+      deposit_esirkepov3_rows(P, charge, inv_dt, dxc, G, J);
+    }
+
+    template <bool LEAN>
+    __global__ void __launch_bounds__(STREAM_CHUNK, 2)
+      push_deposit_tile3_kernel(PushArgs A, eb200_prtls_t S, uint32_t nchunks, FieldView<3> EB,
+                                float charge, float inv_dt, FieldView<3> J) {
+      constexpr int D = 3;
+      extern __shared__ __align__(128) unsigned char smem_raw[];
+      Tile3Smem& sm  = *reinterpret_cast<Tile3Smem*>(smem_raw);
+      const int  tid = threadIdx.x;
+      for (int e = tid; e < 3 * T3N; e += STREAM_CHUNK) sm.tile[e] = 0;
+      if (tid == 0) {
+        sm.box[0] = T3Y, sm.box[1] = -1, sm.box[2] = T3Z, sm.box[3] = -1;
+#pragma unroll
+        for (int s = 0; s < T3_STAGES; ++s) tma::mbar_init(&sm.full[s], 1);
+        tma::fence_mbar_init();
+      }
+      __syncthreads();
+      const uint32_t first = blockIdx.x, stride = gridDim.x;
+      if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < T3_STAGES - 1; ++s) {
+          const uint32_t c = first + s * stride;
+          if (c < nchunks) {
+            stream_issue_load<D>(sm.in[s], &sm.full[s], S, (size_t)c * STREAM_CHUNK);
+          }
+        }
+      }
+      auto      F     = [&](int i, int j, int k, int c) { return EB.ld(i, j, k, c); };
+      const int q     = (9 * tid) & (STREAM_CHUNK - 1); // this thread's slot in every chunk
+      const int G     = A.ng;
+      int       stage = 0;
+      unsigned  phase = 0;
+      for (uint32_t c = first; c < nchunks; c += stride) {
+        StreamIn<D>& st = sm.in[stage];
+        tma::mbar_wait(&sm.full[stage], phase);
+        const size_t p   = (size_t)c * STREAM_CHUNK + q;
+        const short  tag = st.tag[q];
+        Prtl<D>      P;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          P.i[a] = P.ip[a] = st.i[a][q];
+          P.d[a] = P.dp[a] = st.d[a][q];
+          P.u[a]           = st.u[a][q];
+        }
+        P.w         = st.w[q];
+        P.tag       = tag;
+        bool active = (tag == 1);
+        // tile origin: centred on the cell of the chunk's middle particle (ghost-inclusive node)
+        const int org[3] = { st.i[0][STREAM_CHUNK / 2] + G - T3X / 2,
+                             st.i[1][STREAM_CHUNK / 2] + G - 4, st.i[2][STREAM_CHUNK / 2] + G - 4 };
+        // fixed-point scale from the chunk's largest |weight|
+        float wm = active ? fabsf(P.w) : ZERO;
+#pragma unroll
+        for (int l = 16; l > 0; l >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, l));
+        if ((tid & 31) == 0) sm.wmax[tid >> 5] = wm;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < STREAM_CHUNK / 32; ++w) wm = fmaxf(wm, sm.wmax[w]);
+        const float qmax  = wm * fabsf(charge) * inv_dt;
+        const float scale = (qmax > ZERO) ? 4194304.0f / qmax : ZERO;
+        int         lo2 = T3Y, hi2 = -1, lo3 = T3Z, hi3 = -1; // tile rows this lane's window starts on
+        if (active) {
+          push_particle<D, 3, decltype(F), LEAN>(A, F, P);
+          if (P.tag != tag) {
+            S.tag[p] = P.tag;
+          }
+          if (P.tag != 0) {
+            bool done = false;
+            int  r2 = 0, r3 = 0;
+            deposit_esirkepov3_tile(P, -THIRD * (P.w * charge * inv_dt) * scale, G, org, sm.tile,
+                                    done, r2, r3);
+            if (!done) {
+              deposit_esirkepov3_stray(P, charge, inv_dt, A.c.dx, G, J);
+            } else {
+              lo2 = hi2 = r2;
+              lo3 = hi3 = r3;
+            }
+          }
+        }
+        // the tile rows the chunk touched (a window is five rows tall): warp reductions, then
+        // one shared-memory min / max per warp
+        lo2 = __reduce_min_sync(0xffffffffu, lo2);
+        hi2 = __reduce_max_sync(0xffffffffu, hi2);
+        lo3 = __reduce_min_sync(0xffffffffu, lo3);
+        hi3 = __reduce_max_sync(0xffffffffu, hi3);
+        if ((tid & 31) == 0) {
+          atomicMin(&sm.box[0], lo2);
+          atomicMax(&sm.box[1], hi2);
+          atomicMin(&sm.box[2], lo3);
+          atomicMax(&sm.box[3], hi3);
+        }
+        if (tid == 0) {
+          tma::wait_read_all();
+        }
+        const int not_all_alive = __syncthreads_or(!active); // also: every tile add has landed
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          sm.out.i[a][q] = P.i[a];
+          sm.out.d[a][q] = P.d[a];
+          if (P.ip[a] != st.i[a][q]) {
+            st.i[a][q] = P.ip[a]; // periodic wrap shifts i_prev too (sr.hpp:664-677)
+          }
+          sm.out.u[a][q] = P.u[a];
+        }
+        if (not_all_alive && active) {
+          int*   iip[3] = { S.i1_prev, S.i2_prev, S.i3_prev };
+          float* ddp[3] = { S.dx1_prev, S.dx2_prev, S.dx3_prev };
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            iip[a][p] = P.ip[a];
+            ddp[a][p] = P.dp[a];
+          }
+        }
+        // flush: one warp per touched tile row (48 nodes along x1), non-zero elements only
+        const int b2 = sm.box[0], e2 = sm.box[1] + 5, b3 = sm.box[2], e3 = sm.box[3] + 5;
+        if (qmax > ZERO && e2 > b2 && e3 > b3) {
+          const float inv_scale = qmax * (1.0f / 4194304.0f);
+          const int   lane = tid & 31;
+          const int   n2 = e2 - b2, nrow = 3 * n2 * (e3 - b3);
+          const int   N1 = J.N1, N12 = J.N1 * J.N2, plane = (int)J.plane;
+          float*      jbase = J.p + ((long)org[2] * J.N2 + org[1]) * J.N1 + org[0] + lane;
+          for (int row = tid >> 5; row < nrow; row += STREAM_CHUNK / 32) {
+            const int rz = row / n2, jy = b2 + (row - rz * n2);
+            const int comp = rz / (e3 - b3), kz = b3 + (rz - comp * (e3 - b3));
+            int*      trow = sm.tile + ((comp * T3Z + kz) * T3Y + jy) * T3X + lane;
+            float*    jrow = jbase + (comp * plane + kz * N12 + jy * N1);
+            const int v0 = trow[0];
+            const int v1 = (lane < T3X - 32) ? trow[32] : 0;
+            if (v0 != 0) {
+              trow[0] = 0;
+              atomicAdd(jrow, static_cast<float>(v0) * inv_scale);
+            }
+            if (v1 != 0) {
+              trow[32] = 0;
+              atomicAdd(jrow + 32, static_cast<float>(v1) * inv_scale);
+            }
+          }
+        }
+        tma::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          sm.box[0] = T3Y, sm.box[1] = -1, sm.box[2] = T3Z, sm.box[3] = -1;
+        }
+        if (tid == 0) {
+          constexpr unsigned B4 = STREAM_CHUNK * 4;
+          const size_t       p0 = (size_t)c * STREAM_CHUNK;
+          int*   ii[3]  = { S.i1, S.i2, S.i3 };
+          float* dd[3]  = { S.dx1, S.dx2, S.dx3 };
+          int*   iip[3] = { S.i1_prev, S.i2_prev, S.i3_prev };
+          float* ddp[3] = { S.dx1_prev, S.dx2_prev, S.dx3_prev };
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            tma::s2g(ii[a] + p0, sm.out.i[a], B4);
+            tma::s2g(dd[a] + p0, sm.out.d[a], B4);
+            if (!not_all_alive) {
+              tma::s2g(iip[a] + p0, st.i[a], B4);
+              tma::s2g(ddp[a] + p0, st.d[a], B4);
+            }
+          }
+          tma::s2g(S.ux1 + p0, sm.out.u[0], B4);
+          tma::s2g(S.ux2 + p0, sm.out.u[1], B4);
+          tma::s2g(S.ux3 + p0, sm.out.u[2], B4);
+          tma::commit();
+          const uint32_t cn = c + (T3_STAGES - 1) * stride;
+          if (cn < nchunks) {
+            const int sn = (stage + T3_STAGES - 1) % T3_STAGES;
+            stream_issue_load<D>(sm.in[sn], &sm.full[sn], S, (size_t)cn * STREAM_CHUNK);
+          }
+        }
+        if (++stage == T3_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (tid == 0) {
+        tma::wait_all();
+      }
+    }
+#endif // !EB200_STRICT
+
     /* ------------------------------------ vectorised push + deposit (zig-zag, O = 0) */
     // Four consecutive particles per thread. Every SoA array is read and written with one
     // 128-bit streaming access per thread (a warp covers 512 contiguous bytes per array), so
@@ -690,6 +990,38 @@ namespace eb200 {
       atomicAdd(jz + N1 + 1, m[7]);
     }
 
+    // The same flush into a context-owned array of 16-byte nodes {jx1, jx2, jx3, -}: the three
+    // components of a node and of its x1 neighbour share a 32-byte sector, so a flush touches
+    // 2-4 sectors with three 128-bit reductions + one scalar instead of 8 scalar reductions on
+    // 5 sectors of the component planes (stale-order launches spend their extra time on exactly
+    // those sectors, r2c capture). unpack_j4_kernel adds the nodes to the planes afterwards.
+    __device__ __forceinline__ void red_v4(float4* p, float a, float b, float c) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+                   "f"(0.0f)
+                   : "memory");
+    }
+
+    __device__ __forceinline__ void mom_flush_v4(float4* J4, int N1, int key, const float (&m)[8]) {
+      float4* n00 = J4 + key;
+      red_v4(n00, m[0] - m[1], m[2] - m[3], (m[4] - m[5]) - (m[6] - m[7]));
+      red_v4(n00 + 1, ZERO, m[3], m[5] - m[7]);
+      red_v4(n00 + N1, m[1], ZERO, m[6] - m[7]);
+      atomicAdd(&(n00 + N1 + 1)->z, m[7]);
+    }
+
+    __global__ void __launch_bounds__(256)
+      unpack_j4_kernel(float4* __restrict__ J4, long plane, float* __restrict__ cur) {
+      const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+      if (n >= plane) return;
+      const float4 v = J4[n];
+      if (v.x != ZERO || v.y != ZERO || v.z != ZERO) {
+        cur[n] += v.x;
+        cur[plane + n] += v.y;
+        cur[2 * plane + n] += v.z;
+        J4[n] = make_float4(ZERO, ZERO, ZERO, ZERO);
+      }
+    }
+
     // staggered / primal bilinear weights without conversions; same values as gather_packed()
     __device__ __forceinline__ void gather_packed_sel(const PackedEM2& F, int ng, const int (&i)[2],
                                                       const float (&d)[2], float* e0, float* b0) {
@@ -749,9 +1081,18 @@ namespace eb200 {
     #define EB200_MOM_MINBLOCKS 3
   #endif
 
+    template <bool V4>
     __global__ void __launch_bounds__(256, EB200_MOM_MINBLOCKS)
       push_deposit_mom_kernel(PushArgs A, eb200_prtls_t S, uint32_t ngroups, uint32_t ahead,
-                              PackedEM2 EB, float charge, float inv_dt, FieldView<2> J) {
+                              PackedEM2 EB, float charge, float inv_dt, FieldView<2> J,
+                              float4* J4) {
+      auto flush = [&](int key, const float (&m)[8]) {
+        if constexpr (V4) {
+          mom_flush_v4(J4, J.N1, key, m);
+        } else {
+          mom_flush(J, key, m);
+        }
+      };
       constexpr int  D        = 2;
       const uint32_t g        = blockIdx.x * blockDim.x + threadIdx.x;
       const bool     in_range = g < ngroups;
@@ -914,7 +1255,7 @@ namespace eb200 {
             const float wx = HALF * (dn[0] + r1x), wy = HALF * (dn[1] + r1y);
             const float Ax = (dn[0] - r1x) * Q, By = (dn[1] - r1y) * Q;
             const float s[8] = { Ax, Ax * wy, By, By * wx, Fh, Fh * wx, Fh * wy, Fh * wx * wy };
-            mom_flush(J, (in[0] + G) + (in[1] + G) * J.N1, s);
+            flush((in[0] + G) + (in[1] + G) * J.N1, s);
           }
           const float wx = HALF * (r0x + dp[0]), wy = HALF * (r0y + dp[1]);
           const float Ax = (r0x - dp[0]) * Q, By = (r0y - dp[1]) * Q;
@@ -929,7 +1270,7 @@ namespace eb200 {
         }
         if (key0 != cur) {
           if (cur >= 0) {
-            mom_flush(J, cur, acc);
+            flush(cur, acc);
           }
           cur = key0;
   #pragma unroll
@@ -954,7 +1295,7 @@ namespace eb200 {
   #pragma unroll
       for (int n = 0; n < 8; ++n) acc[n] = run_sum(acc[n], run);
       if (run.head && cur >= 0) {
-        mom_flush(J, cur, acc);
+        flush(cur, acc);
       }
     }
 #endif // !EB200_STRICT
@@ -1728,6 +2069,16 @@ namespace eb200 {
       return v;
     }
 
+    inline bool tile3_disabled() {
+      static const bool off = getenv("EB200_NO_TILE3") != nullptr;
+      return off;
+    }
+
+    inline bool j4_disabled() {
+      static const bool off = getenv("EB200_NO_J4") != nullptr;
+      return off;
+    }
+
     inline bool mom_disabled() {
       static const bool off = getenv("EB200_NO_MOM") != nullptr;
       return off;
@@ -1735,7 +2086,8 @@ namespace eb200 {
     template <int D, int O>
     cudaError_t launch_push_deposit(const PushArgs& A, const eb200_prtls_t& S, uint32_t npart,
                                     const eb200_grid_t& g, const float* em, float* cur,
-                                    int mode, float* packed, bool do_pack, cudaStream_t st) {
+                                    int mode, float* packed, bool do_pack, cudaStream_t st,
+                                    float* packed_j = nullptr, bool* packed_j_used = nullptr) {
       if (npart == 0) return cudaSuccess;
       FieldView<D> EB(g, const_cast<float*>(em));
       FieldView<D> J(g, cur);
@@ -1750,6 +2102,42 @@ namespace eb200 {
         mode = EB200_DEPOSIT_ATOMIC;
       }
       const bool want_vec = (O == 0) && (which == 0 || which == 3);
+#if !EB200_STRICT
+      if constexpr (O == 3 && D == 3) {
+        // 9 (what 0 selects): shared-memory fixed-point J tile per chunk of 256 particles
+        if ((which == 9 || (which == 0 && !tile3_disabled())) && mode != EB200_DEPOSIT_ORDERED &&
+            aligned16(S, D) && npart >= (uint32_t)STREAM_CHUNK && J.plane * 3 < 0x7fffffffL) {
+          const uint32_t nchunks = npart / STREAM_CHUNK;
+          const bool     lean    = lean_pusher(A.c);
+          auto           kern    = lean ? push_deposit_tile3_kernel<true> : push_deposit_tile3_kernel<false>;
+          const size_t   smem    = sizeof(Tile3Smem);
+          static std::mutex mu;
+          static bool       attr[2] = { false, false };
+          {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!attr[lean]) {
+              cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+              attr[lean] = true;
+            }
+          }
+          int dev = 0, nsm = 0, per_sm = 0;
+          cudaGetDevice(&dev);
+          cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STREAM_CHUNK, smem);
+          const uint32_t slots = (uint32_t)(nsm * (per_sm > 0 ? per_sm : 1));
+          const uint32_t grid  = nchunks < slots ? nchunks : slots;
+          kern<<<grid, STREAM_CHUNK, smem, st>>>(A, S, nchunks, EB, A.c.charge, inv_dt, J);
+          count_launch();
+          p_begin = nchunks * STREAM_CHUNK;
+          if (p_begin == npart) return cudaGetLastError();
+          // the tail: one particle per thread, per-lane atomics
+          push_deposit_kernel<D, O, false><<<(npart - p_begin + 255) / 256, 256, 0, st>>>(
+            A, S, p_begin, npart, EB, A.c.charge, inv_dt, J);
+          count_launch();
+          return cudaGetLastError();
+        }
+      }
+#endif
       if constexpr (O == 0 && D == 2) {
         if (which == 7 && packed != nullptr && mode == EB200_DEPOSIT_AGGREGATED && aligned16(S, D) &&
             npart >= VEC && J.plane < 0x7fffffffL && EB.plane * 24 < 0xffffffffL) {
@@ -1835,9 +2223,17 @@ namespace eb200 {
           PK.p    = reinterpret_cast<const char*>(packed);
           PK.rowb = 24u * (unsigned)EB.N1;
           const uint32_t ngroups = npart / VEC;
-          const uint32_t wave    = resident_ctas(reinterpret_cast<const void*>(push_deposit_mom_kernel), 256);
-          push_deposit_mom_kernel<<<(ngroups + 255) / 256, 256, 0, st>>>(A, S, ngroups, wave, PK,
-                                                                        A.c.charge, inv_dt, J);
+          const bool     v4      = packed_j != nullptr && packed_j_used != nullptr && !j4_disabled();
+          if (v4) {
+            const uint32_t wave = resident_ctas(reinterpret_cast<const void*>(push_deposit_mom_kernel<true>), 256);
+            push_deposit_mom_kernel<true><<<(ngroups + 255) / 256, 256, 0, st>>>(
+              A, S, ngroups, wave, PK, A.c.charge, inv_dt, J, reinterpret_cast<float4*>(packed_j));
+            *packed_j_used = true;
+          } else {
+            const uint32_t wave = resident_ctas(reinterpret_cast<const void*>(push_deposit_mom_kernel<false>), 256);
+            push_deposit_mom_kernel<false><<<(ngroups + 255) / 256, 256, 0, st>>>(
+              A, S, ngroups, wave, PK, A.c.charge, inv_dt, J, nullptr);
+          }
           count_launch();
           p_begin = ngroups * VEC;
           if (p_begin == npart) return cudaGetLastError();
@@ -2006,16 +2402,30 @@ namespace eb200 {
     cudaError_t push_deposit_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,
                                 const eb200_prtls_t& S, uint32_t npart, const float* em,
                                 float* cur, int mode, float* packed, bool do_pack,
-                                cudaStream_t st) {
+                                cudaStream_t st, float* packed_j, bool* packed_j_used) {
       PushArgs A;
       A.c   = c;
       A.ndh = HALF * (c.charge / c.mass) * c.omegaB0 * c.dt;
       A.ng  = g.ng;
       A.inv_dx = ONE / c.dx;
       for (int a = 0; a < 3; ++a) A.ni[a] = g.n[a];
-#define CALL(D, O) launch_push_deposit<D, O>(A, S, npart, g, em, cur, mode, packed, do_pack, st)
+#define CALL(D, O)                                                                             \
+  launch_push_deposit<D, O>(A, S, npart, g, em, cur, mode, packed, do_pack, st, packed_j, packed_j_used)
       EB200_DISPATCH_DO(g.dim, order, CALL)
 #undef CALL
+    }
+
+    cudaError_t unpack_j4(const eb200_grid_t& g, float* packed_j, float* cur, cudaStream_t st) {
+#if !EB200_STRICT
+      FieldView<2> J(g, cur);
+      unpack_j4_kernel<<<(unsigned)((J.plane + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<float4*>(packed_j), J.plane, cur);
+      count_launch();
+      return cudaGetLastError();
+#else
+      (void)g, (void)packed_j, (void)cur, (void)st; // the strict build never fills the nodes
+      return cudaSuccess;
+#endif
     }
 
     cudaError_t pack_em2d(const eb200_grid_t& g, const float* em, float* packed, cudaStream_t st) {

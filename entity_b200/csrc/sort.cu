@@ -125,8 +125,10 @@ namespace eb200 {
   }
 
   cudaError_t sort_particles(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
-                             uint32_t maxnpart, int remove_dead, uint32_t* n_alive_out,
+                             uint32_t maxnpart, int flags, uint32_t* n_alive_out,
                              Scratch& scratch, cudaStream_t st) {
+    const int  remove_dead = flags & 1;
+    const bool skip_prev   = (flags & EB200_SORT_SKIP_PREV) != 0;
     if (n_alive_out) *n_alive_out = npart;
     if (npart == 0) return cudaSuccess;
     if (S.npld_r < 0 || S.npld_i < 0 || S.npld_r > EB200_MAX_PLD || S.npld_i > EB200_MAX_PLD) {
@@ -194,9 +196,14 @@ namespace eb200 {
       auto      add = [&](void* q) {
         if (q) w[nw++] = (uint32_t*)q;
       };
-      add(S.i1), add(S.dx1), add(S.i1_prev), add(S.dx1_prev);
-      if (g.dim > 1) add(S.i2), add(S.dx2), add(S.i2_prev), add(S.dx2_prev);
-      if (g.dim > 2) add(S.i3), add(S.dx3), add(S.i3_prev), add(S.dx3_prev);
+      add(S.i1), add(S.dx1);
+      if (g.dim > 1) add(S.i2), add(S.dx2);
+      if (g.dim > 2) add(S.i3), add(S.dx3);
+      if (!skip_prev) {
+        add(S.i1_prev), add(S.dx1_prev);
+        if (g.dim > 1) add(S.i2_prev), add(S.dx2_prev);
+        if (g.dim > 2) add(S.i3_prev), add(S.dx3_prev);
+      }
       add(S.ux1), add(S.ux2), add(S.ux3), add(S.weight);
       add(S.phi);
       // payload planes travel with their particles (particles_sort.cpp:150-160, 239-247)

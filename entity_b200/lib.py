@@ -103,6 +103,35 @@ class MatchFaceC(C.Structure):
                 ("range_min", C.c_int * 3), ("range_max", C.c_int * 3)]
 
 
+MAX_MODES = 16
+
+
+class ExtCurrentC(C.Structure):
+    """eb200_ext_current_t"""
+    _fields_ = [("nmodes", C.c_int), ("k", (C.c_float * MAX_MODES) * 3),
+                ("pref", (C.c_float * MAX_MODES) * 3),
+                ("a_real", C.c_float * MAX_MODES), ("a_imag", C.c_float * MAX_MODES),
+                ("pref2", (C.c_float * MAX_MODES) * 3),
+                ("a_real2", C.c_float * MAX_MODES), ("a_imag2", C.c_float * MAX_MODES)]
+
+    @staticmethod
+    def from_table(tab) -> "ExtCurrentC":
+        """tab: dict with nmodes, k[3][n], pref[3][n], a_real[n], a_imag[n], pref2[3][n],
+        a_real2[n], a_imag2[n] (array-likes)"""
+        x = ExtCurrentC()
+        n = int(tab["nmodes"])
+        x.nmodes = n
+        for c in range(3):
+            for m in range(n):
+                x.k[c][m] = float(tab["k"][c][m])
+                x.pref[c][m] = float(tab["pref"][c][m])
+                x.pref2[c][m] = float(tab["pref2"][c][m])
+        for m in range(n):
+            x.a_real[m], x.a_imag[m] = float(tab["a_real"][m]), float(tab["a_imag"][m])
+            x.a_real2[m], x.a_imag2[m] = float(tab["a_real2"][m]), float(tab["a_imag2"][m])
+        return x
+
+
 class ParamsC(C.Structure):
     _fields_ = [
         ("dt", C.c_float), ("correction", C.c_float), ("omegaB0", C.c_float),

@@ -117,6 +117,14 @@ class Simulation:
         self.ctx._check(self.ctx.lib.eb200_srpic_set_match(
             self.ctx.handle, arr, len(faces), target.data_ptr() if len(faces) else None, mask))
 
+    def set_ext_current(self, table):
+        """The pgen's ext_current as a table of Fourier modes (eb200_ext_current_t; see
+        lib.ExtCurrentC.from_table); None clears it. The host refills it whenever the pgen
+        advances the amplitudes (pgens/turbulence/pgen.hpp CustomPostStep)."""
+        x = L.ExtCurrentC.from_table(table) if table is not None else None
+        self.ctx._check(self.ctx.lib.eb200_srpic_set_ext_current(
+            self.ctx.handle, C.byref(x) if x is not None else None))
+
     def add_species(self, mass, charge, arrays: dict, npart: int, pusher=L.PUSHER_BORIS,
                     maxnpart=None):
         """arrays: name -> torch tensor on this device (capacity = maxnpart)."""

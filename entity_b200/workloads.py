@@ -171,7 +171,8 @@ def reconnection(n=(4096, 2048), ppc0=32, nfilter=8, seed=0x5678, sheets=True,
     return sim
 
 
-def turbulence(n=(128, 128, 128), ppc0=16, order=3, nfilter=4, seed=0x9abc, **kw) -> Simulation:
+def turbulence(n=(128, 128, 128), ppc0=16, order=3, nfilter=4, seed=0x9abc, capacity_factor=1.0,
+               **kw) -> Simulation:
     """configs[2] (per-GPU block): 3D pair plasma, T = 1, guide field along x3, 3rd-order shapes."""
     dx = 256.0 / 1024.0
     sim = Simulation(n, order, Scales(3, dx, larmor0=1.0, skindepth0=1.0, ppc0=ppc0),
@@ -181,7 +182,7 @@ def turbulence(n=(128, 128, 128), ppc0=16, order=3, nfilter=4, seed=0x9abc, **kw
     gen = _gen(sim, seed)
     per = math.prod(n) * (ppc0 // 2)
     for charge in (-1.0, +1.0):
-        arr = _alloc(sim, per)
+        arr = _alloc(sim, per, int(per * capacity_factor))
         _uniform_positions(sim, arr, per, gen)
         _maxwellian(sim, arr, per, gen, 1.0)
         sim.add_species(1.0, charge, arr, per)

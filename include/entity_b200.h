@@ -166,6 +166,29 @@ int eb200_ampere(eb200_ctx_t* ctx, float* em, float coeff1, float coeff2, eb200_
  * (fieldsolvers.h:142-199, ampere_mink.hpp:134-215): E += J*coeff; J /= ppc0 */
 int eb200_currents_ampere(eb200_ctx_t* ctx, float* em, float* cur, float coeff, float ppc0,
                           eb200_stream_t stream);
+/* The `ext_current` of a problem generator (traits::pgen::HasExtCurrent; CurrentsAmpere_kernel<D,
+ * ExtCurrent>, ampere_mink.hpp:134-215: J_c += ppc0 * ext_current.jx_c(x) on the component's own
+ * node before E += J coeff) cannot cross a C ABI as a functor. It is handed over as a table of
+ * Fourier modes, which is what the reference's one ext_current is (the turbulence antenna,
+ * pgens/turbulence/pgen.hpp:139-298):
+ *   jx_c(x) = sum_m pref[c][m]  * (a_real[m]  cos(k_m . x) - a_imag[m]  sin(k_m . x))
+ *           + sum_m pref2[c][m] * (a_real2[m] cos(k_m . x) - a_imag2[m] sin(k_m . x))
+ * evaluated mode by mode in this order (the second sum inside the same loop over m, as the 2D
+ * antenna's inverse-helicity term). The host advances the amplitudes (the pgen's
+ * CustomPostStep) and refills the table; k_m . x = k[0][m] x1 + k[1][m] x2 (+ k[2][m] x3). */
+#define EB200_MAX_MODES 16
+typedef struct {
+  int   nmodes;
+  float k[3][EB200_MAX_MODES];
+  float pref[3][EB200_MAX_MODES];
+  float a_real[EB200_MAX_MODES], a_imag[EB200_MAX_MODES];
+  float pref2[3][EB200_MAX_MODES];
+  float a_real2[EB200_MAX_MODES], a_imag2[EB200_MAX_MODES];
+} eb200_ext_current_t;
+int eb200_currents_ampere_ext(eb200_ctx_t* ctx, float* em, float* cur, float coeff, float ppc0,
+                              const eb200_ext_current_t* ext_host, eb200_stream_t stream);
+/* registers (copies) the table eb200_srpic_step uses in srpic::CurrentsAmpere; NULL clears it */
+int eb200_srpic_set_ext_current(eb200_ctx_t* ctx, const eb200_ext_current_t* ext_host);
 /* srpic::CurrentsFilter (src/engines/srpic/currents.h:89-119): nfilter x { buff = cur;
  * DigitalFilter_kernel (digital_filter.hpp:99-388, Cartesian); ghost exchange of J }.
  * fbc_host[6] = EB200_FBC_* per face. */
@@ -266,7 +289,13 @@ int eb200_comm_init(eb200_ctx_t* ctx, const eb200_metadomain_t* md, const char* 
 /* Particles::SortSpatially (particles_sort.cpp:197-253): stable sort by cell index
  * (i1 fastest, matching the field layout), dead particles moved to the end.
  * Particles::RemoveDead (particles_sort.cpp:104-194) is the same call with
- * remove_dead = 1: *npart_inout_host becomes the number of alive particles. */
+ * remove_dead = 1: *npart_inout_host becomes the number of alive particles.
+ * remove_dead | EB200_SORT_SKIP_PREV: i*_prev / dx*_prev are left where they are. Between the
+ * deposit of one step and the pusher of the next they are dead values (the pusher overwrites
+ * them before anything reads them, sr.hpp:137-153), which is where SortParticles runs
+ * (srpic.hpp:184-186): eb200_srpic_step sorts this way; a host that reads them after a sort
+ * (a checkpoint of the raw arrays) passes the plain flags. */
+#define EB200_SORT_SKIP_PREV 2
 int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls,
                          uint32_t* npart_inout_host, int remove_dead, eb200_stream_t stream);
 

@@ -4,7 +4,7 @@
 # dump-wrapper problem generators of oracle/pgens/. Only binaries are kept, under baseline/_ref/
 # (git-ignored, travels to the GPU box). Recipe = BASELINE.md §3 / SURVEY.md §8(c).
 #
-#   oracle/build_entity_xc.sh omp      # Kokkos-OpenMP, zigzag: streaming, reconnection, magnetosphere, wald, accretion
+#   oracle/build_entity_xc.sh omp      # Kokkos-OpenMP, zigzag: streaming, reconnection, turbulence (2D), magnetosphere, wald, accretion
 #   oracle/build_entity_xc.sh omp3     # Kokkos-OpenMP, esirkepov shape_order=3: turbulence
 #   oracle/build_entity_xc.sh cuda     # Kokkos-CUDA sm_100 (Kokkos_ARCH_BLACKWELL100): reconnection
 #   oracle/build_entity_xc.sh cuda3    # Kokkos-CUDA sm_100, esirkepov 3: turbulence
@@ -21,7 +21,7 @@ if [ ! -f "$WORK/CMakeLists.txt" ]; then
 fi
 P=$REPO/oracle/pgens
 case $FLAVOUR in
-  omp)   PG="$P/dump_streaming;$P/dump_reconnection;$P/dump_magnetosphere;$P/dump_wald;$P/dump_accretion"
+  omp)   PG="$P/dump_streaming;$P/dump_reconnection;$P/dump_turbulence;$P/dump_magnetosphere;$P/dump_wald;$P/dump_accretion"
          EXTRA="-D Kokkos_ENABLE_OPENMP=ON" ;;
   omp3)  PG="$P/dump_turbulence"
          EXTRA="-D Kokkos_ENABLE_OPENMP=ON -D deposit=esirkepov -D shape_order=3" ;;

@@ -173,6 +173,33 @@ namespace ebdump {
     std::fclose(f);
   }
 
+  // the turbulence antenna (pgens/turbulence/pgen.hpp:139-298): wave vectors and the complex
+  // amplitudes as they stand AFTER the pgen's own CustomPostStep, i.e. what the next step's
+  // CurrentsAmpere adds as ext_current
+  template <class PG>
+  void antenna(long step, PG& pg) {
+    if constexpr (requires { pg.ext_current.k; pg.ext_current.a_real; pg.ext_current.a_imag_inv; }) {
+      const char* dir = std::getenv("EB_DUMP_DIR");
+      if (!dir || !steps().count(step)) return;
+      std::string fn = std::string(dir) + "/s" + std::to_string(step) + "_ant.bin";
+      std::FILE* f = std::fopen(fn.c_str(), "wb");
+      if (!f) return;
+      auto& ec = pg.ext_current;
+      auto  kh = Kokkos::create_mirror_view(ec.k);
+      Kokkos::deep_copy(kh, ec.k);
+      const std::size_t nd = ec.k.extent(0), nm = ec.k.extent(1);
+      std::vector<float> kb(nd * nm);
+      for (std::size_t d = 0; d < nd; ++d)
+        for (std::size_t m = 0; m < nm; ++m) kb[d * nm + m] = kh(d, m);
+      rec(f, "k", 0, { (std::uint64_t)nd, (std::uint64_t)nm }, kb.data(), kb.size() * 4);
+      arr(f, "a_real", ec.a_real, nm);
+      arr(f, "a_imag", ec.a_imag, nm);
+      arr(f, "a_real_inv", ec.a_real_inv, nm);
+      arr(f, "a_imag_inv", ec.a_imag_inv, nm);
+      std::fclose(f);
+    }
+  }
+
   // EB_COUNT_FILE: one line per step, "step npart_0 npart_1 ..." (host-side counters only;
   // the reference's own stats writer needs -D output=ON)
   template <ntt::SimEngine::type S, class M>
@@ -206,6 +233,7 @@ namespace user {
       if constexpr (::traits::pgen::HasCustomPostStep<base_t, Domain<S, M>>) {
         base_t::CustomPostStep(step, time, dom);
       }
+      ebdump::antenna((long)step, *static_cast<base_t*>(this));
       ebdump::counts((long)step, dom);
       ebdump::dump((long)step, (double)time, dom);
     }

@@ -33,6 +33,7 @@ class OracleSim:
         self.step_index = 0
         self.time = 0.0
         self.match = None  # (faces, target, mask): MATCH field boundaries (oracle/bcs.py)
+        self.ext = None  # mode table of the pgen's ext_current (oracle/antenna.py)
 
     # srpic::FieldBoundaries for MATCH faces (src/engines/srpic/fields_bcs.h:38-215, 600-672)
     def _field_boundaries(self, tags):
@@ -90,6 +91,10 @@ class OracleSim:
         c1, c2 = self._coeffs(1.0)
         im.ampere(g, self.em, c1, c2)
         coeff = -dt * f32(s["q0"]) / (f32(s["B0"]) * f32(s["V0"]))
+        if self.ext is not None:
+            # CurrentsAmpere_kernel<D, ExtCurrent>: J += ppc0 * ext_current first (ampere_mink.hpp:134-215)
+            from . import antenna
+            antenna.add_ext_current(g, self.cur, self.ext, s["ppc0"], self.dx, self.xmin)
         im.currents_ampere(g, self.em, self.cur, coeff, f32(s["ppc0"]))
         im.comm_fields(g, self.em, 0, 3, self.fbc)
         im.comm_fields(g, self.cur, 0, 3, self.fbc)

@@ -24,15 +24,18 @@ sys.path.insert(0, ROOT)
 from oracle import refdump  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-BIN = os.path.join(ROOT, "baseline", "_ref", "omp")
+BIN = os.path.join(ROOT, "baseline", "_ref")
 
 PRTL = ["i1", "i2", "i3", "dx1", "dx2", "dx3", "ux1", "ux2", "ux3", "weight", "i1_prev", "i2_prev",
         "i3_prev", "dx1_prev", "dx2_prev", "dx3_prev", "tag", "phi"]
 
 CASES = {
     # name: (binary, input, first step, last step)
-    "stream2d": ("entity_streaming.xc", "stream2d.toml", 0, 10),
-    "reconnection_small": ("entity_reconnection.xc", "reconnection_small.toml", 0, 7),
+    "stream2d": ("omp/entity_streaming.xc", "stream2d.toml", 0, 10),
+    "reconnection_small": ("omp/entity_reconnection.xc", "reconnection_small.toml", 0, 7),
+    # antenna-driven (ext_current); the 3D one is the esirkepov / shape_order = 3 build
+    "turbulence2d": ("omp/entity_turbulence.xc", "turbulence2d.toml", 0, 8),
+    "turbulence3d": ("omp3/entity_turbulence.xc", "turbulence3d.toml", 0, 4),
 }
 
 
@@ -63,6 +66,10 @@ def run_case(name):
             out[f"s{s}/time"] = d["time"]
             out[f"s{s}/em"] = d["em"]
             out[f"s{s}/cur"] = d["cur"]
+            ant = os.path.join(tmp, f"s{s}_ant.bin")
+            if os.path.exists(ant):
+                for k_, v_ in refdump.read(ant).items():
+                    out[f"s{s}/ant_{k_}"] = v_
             for k in range(nsp):
                 p = f"sp{k}_"
                 n, npre = int(d[p + "npart"][0]), int(d[p + "npart_pre"][0])

@@ -20,6 +20,10 @@ CASES = {
     "reconnection_small": dict(n=(64, 48), dx=0.5, xmin=(-16.0, -12.0), larmor0=0.1, skindepth0=1.0,
                                ppc0=8.0, nfilter=8, pushers=[2, 2], cap=40000,
                                walls=dict(ds=2.0, bg_B=1.0, cs_width=1.5, cs_y=0.0)),
+    "turbulence2d": dict(n=(32, 24), dx=0.25, xmin=(-4.0, -3.0), larmor0=1.0, skindepth0=1.0, ppc0=8.0,
+                         nfilter=4, pushers=[2, 2], cap=4096, walls=None, antenna=True),
+    "turbulence3d": dict(n=(16, 12, 10), dx=0.5, xmin=(-4.0, -3.0, -2.5), larmor0=1.0, skindepth0=1.0,
+                         ppc0=8.0, nfilter=4, pushers=[2, 2], cap=8192, walls=None, antenna=True, order=3),
 }
 
 
@@ -41,6 +45,15 @@ def scales(case):
     from entity_b200.srpic import Scales
     c = CASES[case]
     return Scales(len(c["n"]), c["dx"], larmor0=c["larmor0"], skindepth0=c["skindepth0"], ppc0=c["ppc0"])
+
+
+def antenna_table(case, z, s):
+    """eb200_ext_current_t contents from the antenna state dumped after step s (what step s + 1
+    adds in CurrentsAmpere)"""
+    from oracle import antenna
+    dim = len(CASES[case]["n"])
+    return antenna.mode_table(dim, z[f"s{s}/ant_k"], z[f"s{s}/ant_a_real"], z[f"s{s}/ant_a_imag"],
+                              z[f"s{s}/ant_a_real_inv"], z[f"s{s}/ant_a_imag_inv"])
 
 
 def match_target(case, g):

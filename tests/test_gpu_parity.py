@@ -358,3 +358,65 @@ def test_fused_filter_passes(eb, orc_mod, n_cells, nfilter, strict):
         assert_values_equal(host(d_cur), cur, f"fused filter x{nfilter}")
     else:
         np.testing.assert_allclose(host(d_cur), cur, rtol=RTOL_FAST, atol=ATOL_FAST)
+
+
+@pytest.mark.parametrize("order_kind", ["sorted", "stale", "random"])
+@pytest.mark.parametrize("which", [0, 1, 9])
+@pytest.mark.parametrize("weights", ["unit", "spread"])
+def test_tile3_kernel(eb, orc_mod, order_kind, which, weights):
+    """3D third-order fused push + deposit: the shared-memory fixed-point J tile (kernel 9, what
+    0 selects in the fast build) against the oracle, next to the per-lane kernel (1), on
+    cell-sorted particles (everything inside the tile), on a stale order (strays take the
+    global path) and on a random order (nearly everything does), with unit weights and with
+    weights spread over two decades (the tile's scale follows the chunk's largest weight).
+    Two consecutive steps; particles to the fast-build tolerances, J to 2e-4 of max|J|."""
+    orc = orc_mod.oracle()
+    n_cells = (56, 12, 10)
+    g = orc_mod.Grid.make(n_cells, orc_mod.nghosts_for(3))
+    dx = 0.5
+    common = dict(dt=0.45 * dx, omegaB0=0.7, mass=1.0, charge=-1.0, dx=dx, xmin=[0.1, 0.2, 0.3],
+                  pbc=[orc_mod.PBC_PERIODIC] * 6, pusher_flags=2)
+    octx = orc_mod.make_pusher(**common)
+    ctx = eb.Context(n_cells, order=3, strict=False, dx=dx, xmin=(0.1, 0.2, 0.3))
+    ctx.set_pd_kernel(which)
+    gctx = ctx.make_pusher(**common)
+    em = smooth_fields(g, 91, amp=0.6)
+    n = 8 * n_cells[0] * n_cells[1] * n_cells[2] + 37
+    p = random_particles(g, n, 777, umag=1.0, dead_frac=0.02)
+    if weights == "spread":
+        rng = np.random.default_rng(5)
+        p.weight[:] = (10.0 ** rng.uniform(-1.0, 1.0, n)).astype(np.float32)
+
+    def sort_by_cell(q):
+        key = (q.i1.astype(np.int64) + g.n[0] * q.i2.astype(np.int64)
+               + g.n[0] * g.n[1] * q.i3.astype(np.int64))
+        key[q.tag == 0] = 1 << 40
+        perm = np.argsort(key, kind="stable")
+        for nm in q.names():
+            getattr(q, nm)[:] = getattr(q, nm)[perm]
+
+    if order_kind != "random":
+        sort_by_cell(p)
+    if order_kind == "stale":
+        for _ in range(3):
+            orc.push(g, 3, octx, p, n, em)
+    d_em = dev(em)
+    arr = to_device(p)
+    for step in range(2):
+        j_ref = np.zeros(g.shape(3), np.float32)
+        d_j = dev(j_ref)
+        orc.push(g, 3, octx, p, n, em)
+        orc.deposit(g, 3, p, n, -1.0, octx.dt, dx, j_ref)
+        ctx.push_deposit(gctx, arr, n, d_em, d_j, mode=eb.DEPOSIT_AGGREGATED)
+        q = to_host(arr, n)
+        same = np.ones(n, bool)
+        for nm in ("i1", "i2", "i3", "i1_prev", "i2_prev", "i3_prev", "tag"):
+            same &= getattr(q, nm) == getattr(p, nm)
+        assert (~same).sum() <= 6
+        for nm in ("ux1", "ux2", "ux3", "dx1", "dx2", "dx3"):
+            np.testing.assert_allclose(getattr(q, nm)[same], getattr(p, nm)[same], rtol=1e-4,
+                                       atol=2e-5, err_msg=nm)
+        arr = to_device(p)  # both sides on the same trajectory for the second step
+        scale = np.abs(j_ref).max()
+        err = np.abs(host(d_j) - j_ref).max()
+        assert err <= 2e-4 * scale, f"kernel {which} step {step}: {err / scale:.2e}"

@@ -4,6 +4,10 @@ boundary calls) to the running reference: states dumped from the reference's own
 
 * stream2d            -- BASELINE configs[0] lifted to 2D, doubly periodic: every step of the window
                          bit for bit (fields, currents, every particle array).
+* turbulence2d / 3d   -- pgens/turbulence (BASELINE configs[2]: the 3D case is the esirkepov,
+                         shape_order = 3 build) with the antenna's ext_current: bit for bit, the
+                         antenna amplitudes of every step imported from the dump (the pgen advances
+                         them on the host with its own RNG).
 * reconnection_small  -- BASELINE configs[1] at fixture size with its MATCH / ABSORB x2 walls and the
                          replenishing injector: also bit for bit (the MATCH profiles go through
                          glibc's tanhf, oracle/bcs.py, as the reference's host build does). The
@@ -26,8 +30,8 @@ def build_oracle(case, z, s0):
     if walls:
         fbc[2] = fbc[3] = orc.FBC_NONE
         pbc[2] = pbc[3] = orc.PBC_ABSORB
-    o = pic.OracleSim(orc.oracle(), c["n"], 0, sc, c["dx"], c["nfilter"], fbc=fbc, pbc=pbc,
-                      xmin=tuple(c["xmin"]) + (0.0,))
+    o = pic.OracleSim(orc.oracle(), c["n"], c.get("order", 0), sc, c["dx"], c["nfilter"], fbc=fbc,
+                      pbc=pbc, xmin=(tuple(c["xmin"]) + (0.0,))[:3])
     o.em[...] = z[f"s{s0}/em"]
     o.cur[...] = z[f"s{s0}/cur"]
     for k, pusher in enumerate(c["pushers"]):
@@ -77,11 +81,14 @@ def check_step(case, z, o, s, s1, exact):
             sp["npart"] = n
 
 
-@pytest.mark.parametrize("case,exact", [("stream2d", True), ("reconnection_small", True)])
+@pytest.mark.parametrize("case,exact", [("stream2d", True), ("reconnection_small", True),
+                                        ("turbulence2d", True), ("turbulence3d", True)])
 def test_oracle_step_matches_running_reference(orc_mod, case, exact):
     z = rc.load(case)
     s0, s1 = (int(v) for v in z["meta/steps"])
     o = build_oracle(case, z, s0)
     for s in range(s0 + 1, s1 + 1):
+        if rc.CASES[case].get("antenna"):
+            o.ext = rc.antenna_table(case, z, s - 1)
         o.step()
         check_step(case, z, o, s, s1, exact)
