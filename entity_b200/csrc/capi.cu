@@ -857,6 +857,96 @@ int eb200_currents_ampere_gr(eb200_ctx_t* ctx, float* d_fld, const float* cur, f
                     "currents_ampere_gr");
 }
 
+/* ------------------------------------------- curvilinear / GR field boundaries */
+static int check_range2(eb200_ctx* ctx, const int* rmin, const int* rmax) {
+  REQUIRE(ctx, rmin != nullptr && rmax != nullptr, "null range");
+  const eb200_grid_t& g = ctx->cfg.grid;
+  for (int a = 0; a < 2; ++a) {
+    REQUIRE(ctx, rmin[a] >= 0 && rmax[a] <= g.n[a] + 2 * g.ng, "range outside the array");
+  }
+  return EB200_OK;
+}
+
+int eb200_axis_fields(eb200_ctx_t* ctx, float* fld, int sign, int tags, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, fld != nullptr, "null field");
+  REQUIRE(ctx, ctx->cfg.grid.dim == 2 && (is_sr_curv(ctx) || is_gr(ctx)),
+          "Invalid coordinate type for axis BCs");
+  REQUIRE(ctx, sign != 0, "axis: sign must be -1 or +1");
+  return check_cuda(ctx, eb200::curv::axis_fields(ctx->cfg.grid, fld, sign > 0, tags, (cudaStream_t)stream),
+                    "axis_fields");
+}
+
+int eb200_horizon_fields(eb200_ctx_t* ctx, float* fld, int tags, int nfilter,
+                         eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, fld != nullptr, "null field");
+  REQUIRE(ctx, is_gr(ctx), "HORIZON BCs only applicable for GR");
+  REQUIRE(ctx, nfilter >= 0 && 3 + nfilter <= ctx->cfg.grid.ng + ctx->cfg.grid.n[0],
+          "horizon: nfilter out of range");
+  return check_cuda(ctx, eb200::curv::horizon_fields(ctx->cfg.grid, fld, tags, nfilter, (cudaStream_t)stream),
+                    "horizon_fields");
+}
+
+int eb200_match_fields_curv(eb200_ctx_t* ctx, float* fld, const float* target, int o,
+                            float xg_edge, float ds, int tags, int mask, const int* rmin,
+                            const int* rmax, const int* fbc, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, fld != nullptr && target != nullptr && fbc != nullptr, "null argument");
+  REQUIRE(ctx, ctx->cfg.grid.dim == 2 && (is_sr_curv(ctx) || is_gr(ctx)),
+          "eb200_match_fields_curv: 2D spherical / Kerr-Schild type contexts only");
+  REQUIRE(ctx, o == 0 || o == 1, "matching direction outside the simulated dimensions");
+  REQUIRE(ctx, ds > 0.0f, "match: ds must be positive");
+  int rc = check_range2(ctx, rmin, rmax);
+  if (rc) return rc;
+  return check_cuda(ctx,
+                    eb200::curv::match_fields_curv(ctx->metric, ctx->cfg.grid, fld, target, o, xg_edge,
+                                                   ds, tags, mask & 63, rmin, rmax, fbc,
+                                                   (cudaStream_t)stream),
+                    "match_fields_curv");
+}
+
+int eb200_enforce_fields(eb200_ctx_t* ctx, float* em, const float* target, int o, int sign,
+                         int i_edge, int tags, int mask, const int* rmin, const int* rmax,
+                         eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, em != nullptr && target != nullptr, "null argument");
+  REQUIRE(ctx, ctx->cfg.grid.dim == 2, "eb200_enforce_fields: 2D domains");
+  REQUIRE(ctx, (o == 0 || o == 1) && sign != 0, "Invalid Orientation");
+  int rc = check_range2(ctx, rmin, rmax);
+  if (rc) return rc;
+  return check_cuda(ctx,
+                    eb200::curv::enforce_fields(ctx->cfg.grid, em, target, o, sign > 0, i_edge, tags,
+                                                mask & 63, rmin, rmax, (cudaStream_t)stream),
+                    "enforce_fields");
+}
+
+int eb200_absorb_currents_gr(eb200_ctx_t* ctx, float* cur, float xg_edge, float ds, const int* rmin,
+                             const int* rmax, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, cur != nullptr, "null field");
+  REQUIRE(ctx, is_gr(ctx) && ctx->cfg.grid.dim == 2, "eb200_absorb_currents_gr: 2D Kerr-Schild type contexts only");
+  REQUIRE(ctx, ds > 0.0f, "absorb: ds must be positive");
+  int rc = check_range2(ctx, rmin, rmax);
+  if (rc) return rc;
+  return check_cuda(ctx,
+                    eb200::curv::absorb_currents(ctx->metric, ctx->cfg.grid, cur, xg_edge, ds, rmin, rmax,
+                                                 (cudaStream_t)stream),
+                    "absorb_currents");
+}
+
+int eb200_conductor_fields(eb200_ctx_t* ctx, float* em, int o, int sign, int tags,
+                           eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, em != nullptr, "null field");
+  REQUIRE(ctx, ctx->cfg.metric == EB200_METRIC_MINKOWSKI,
+          "Perfect conductor BCs only applicable to cartesian coordinates");
+  REQUIRE(ctx, ctx->cfg.grid.dim == 2, "eb200_conductor_fields: 2D domains");
+  REQUIRE(ctx, (o == 0 || o == 1) && sign != 0, "Invalid dimension");
+  return check_cuda(ctx, eb200::conductor_fields2d(ctx->cfg.grid, em, o, sign > 0, tags, (cudaStream_t)stream),
+                    "conductor_fields");
+}
+
 int eb200_time_average(eb200_ctx_t* ctx, float* a, const float* b, int ncomp,
                        eb200_stream_t stream) {
   ENTER(ctx);

@@ -437,6 +437,309 @@ namespace eb200 {
   } // namespace srpic
 } // namespace eb200
 
+// ============================================================================ GRPIC
+extern "C" int eb200_ctx_grid(const eb200_ctx_t* ctx, eb200_grid_t* grid, float* dx, float* xmin3);
+
+namespace eb200 {
+  namespace grpic {
+    static bool almost_zero(float x) { return std::fabs(x) <= std::numeric_limits<float>::epsilon(); }
+
+    struct Domain {
+      eb200_ctx_t*                ctx;
+      const eb200_grpic_params_t* prm;
+      eb200_grid_t                grid;
+      float *                     em, *em0, *cur, *cur0, *aux, *buff;
+      const float*                match_target;
+      eb200_species_t*            species;
+      int                         nspecies;
+      eb200_stream_t              stream;
+      Profiler*                   prof;
+    };
+
+    enum class gr_getE { D0_B, D_B0 };
+    enum class gr_getH { D_B0, D0_B0 };
+    enum class gr_faraday { aux, main };
+    enum class gr_ampere { init, aux, main };
+    enum class gr_bc { main, aux, curr };
+
+    // fieldsolvers.h:79-128
+    int ComputeAuxE(Domain& dom, gr_getE g) {
+      const float* D = (g == gr_getE::D0_B) ? dom.em0 : dom.em;
+      const float* B = (g == gr_getE::D0_B) ? dom.em : dom.em0;
+      return eb200_gr_aux_e(dom.ctx, D, B, dom.aux, dom.prm->fbc, dom.stream);
+    }
+
+    int ComputeAuxH(Domain& dom, gr_getH g) {
+      const float* D = (g == gr_getH::D_B0) ? dom.em : dom.em0;
+      return eb200_gr_aux_h(dom.ctx, D, dom.em0, dom.aux, dom.prm->fbc, dom.stream);
+    }
+
+    // fieldsolvers.h:130-166
+    int Faraday(Domain& dom, gr_faraday g, float fraction) {
+      const float dT = fraction * dom.prm->correction * dom.prm->dt;
+      const float* Bin = (g == gr_faraday::aux) ? dom.em0 : dom.em;
+      return eb200_faraday_gr(dom.ctx, Bin, dom.em0, dom.aux, dT, dom.prm->fbc, dom.stream);
+    }
+
+    // fieldsolvers.h:168-222
+    int Ampere(Domain& dom, gr_ampere g, float fraction) {
+      const float  dT   = fraction * dom.prm->correction * dom.prm->dt;
+      const float* Din  = (g == gr_ampere::aux) ? dom.em0 : dom.em;
+      float*       Dout = (g == gr_ampere::init) ? dom.em : dom.em0;
+      return eb200_ampere_gr(dom.ctx, Din, Dout, dom.aux, dT, dom.prm->fbc, dom.stream);
+    }
+
+    // fieldsolvers.h:224-262
+    int AmpereCurrents(Domain& dom, gr_ampere g) {
+      const float coeff = -dom.prm->dt * dom.prm->q0 / dom.prm->B0;
+      const float* J    = (g == gr_ampere::aux) ? dom.cur : dom.cur0;
+      return eb200_currents_ampere_gr(dom.ctx, dom.em0, J, coeff, dom.prm->fbc, dom.stream);
+    }
+
+    // utils.h:41-61
+    int TimeAverageDB(Domain& dom) {
+      return eb200_time_average(dom.ctx, dom.em0, dom.em, 6, dom.stream);
+    }
+
+    int TimeAverageJ(Domain& dom) {
+      return eb200_time_average(dom.ctx, dom.cur, dom.cur0, 3, dom.stream);
+    }
+
+    int CopyFields(Domain& dom) {
+      size_t n = 6;
+      for (int a = 0; a < dom.grid.dim; ++a) n *= (size_t)(dom.grid.n[a] + 2 * dom.grid.ng);
+      return cudaMemcpyAsync(dom.em0, dom.em, n * sizeof(float), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)dom.stream) == cudaSuccess
+               ? EB200_OK
+               : EB200_ERR_CUDA;
+    }
+
+    void SwapFields(Domain& dom) {
+      std::swap(dom.em, dom.em0);
+      std::swap(dom.cur, dom.cur0);
+    }
+
+    // grpic::FieldBoundaries (fields_bcs.h:232-266): directions in the order of
+    // dir::Directions<Dim::_2D>::orth = (-x1, -x2, +x2, +x1) (directions.h:190-195): the axis
+    // rows are mirrored before the MATCH layer blends them. A single domain, so the local and
+    // the global boundary of a face are the same thing
+    int FieldBoundaries(Domain& dom, int tags, gr_bc g) {
+      const eb200_grpic_params_t& p = *dom.prm;
+      PHASE(dom, EB200_PHASE_FIELDSOLVER);
+      static const int orth[4] = { 0, 2, 3, 1 }; // face = 2 * dim + (sign > 0)
+      if (g == gr_bc::main) {
+        for (int q = 0; q < 4; ++q) {
+          const int face = orth[q];
+          const int sign = (face & 1) ? +1 : -1;
+          const int o    = face >> 1;
+          const int bc   = p.fbc[face];
+          if (bc == EB200_FBC_MATCH) {
+            if (o != 0) return EB200_ERR_ARG; // "Invalid dimension"
+            if (dom.match_target == nullptr) continue; // no init_flds: nothing to match to
+            float* flds[2] = { dom.em, dom.em0 };
+            for (float* f : flds) {
+              TRY(eb200_match_fields_curv(dom.ctx, f, dom.match_target, 0, p.match_xg_edge,
+                                          p.match_ds, tags, p.match_mask, p.match_range_min,
+                                          p.match_range_max, p.fbc, dom.stream));
+            }
+          } else if (bc == EB200_FBC_AXIS) {
+            TRY(eb200_axis_fields(dom.ctx, dom.em, sign, tags, dom.stream));
+            TRY(eb200_axis_fields(dom.ctx, dom.em0, sign, tags, dom.stream));
+          } else if (bc == EB200_FBC_HORIZON) {
+            TRY(eb200_horizon_fields(dom.ctx, dom.em, tags, p.nfilter, dom.stream));
+            TRY(eb200_horizon_fields(dom.ctx, dom.em0, tags, p.nfilter, dom.stream));
+          }
+        }
+      } else if (g == gr_bc::aux) {
+        // HorizonFieldsIn acts for gr_bc::main only (fields_bcs.h:150-167): nothing to do
+      } else {
+        for (int face = 0; face < 4; ++face) {
+          if (p.pbc[face] != EB200_PBC_ABSORB || p.fbc[face] == EB200_FBC_HORIZON) continue;
+          if (face != 1) return EB200_ERR_ARG; // "Absorption of currents only possible in +x1 (+r)"
+          TRY(eb200_absorb_currents_gr(dom.ctx, dom.cur0, p.match_xg_edge, p.match_ds,
+                                       p.match_range_min, p.match_range_max, dom.stream));
+        }
+      }
+      return EB200_OK;
+    }
+
+    // particle_pusher.h:27-89
+    int ParticlePush(Domain& dom) {
+      const eb200_grpic_params_t& p = *dom.prm;
+      for (int s = 0; s < dom.nspecies; ++s) {
+        eb200_species_t& sp = dom.species[s];
+        if (sp.npart == 0 || sp.pusher_flags == EB200_PUSHER_NONE) continue;
+        eb200_pusher_gr_t c;
+        std::memset(&c, 0, sizeof(c));
+        c.pusher_flags = sp.pusher_flags;
+        c.mass = sp.mass, c.charge = sp.charge;
+        c.dt = p.dt, c.omegaB0 = p.omegaB0;
+        c.epsilon = p.pusher_eps, c.niter = p.pusher_niter;
+        for (int k = 0; k < 6; ++k) c.pbc[k] = p.pbc[k];
+        c.tag_outgoing = 0;
+        TRY(eb200_push_gr(dom.ctx, &c, &sp.arrays, sp.npart, dom.em, dom.em0, dom.stream));
+      }
+      return EB200_OK;
+    }
+
+    // currents.h:29-73: into cur0
+    int CurrentsDeposit(Domain& dom) {
+      for (int s = 0; s < dom.nspecies; ++s) {
+        eb200_species_t& sp = dom.species[s];
+        if (sp.npart == 0 || almost_zero(sp.charge)) continue;
+        TRY(eb200_deposit(dom.ctx, &sp.arrays, sp.npart, sp.charge, dom.prm->dt, dom.cur0,
+                          dom.prm->deposit_mode, dom.stream));
+      }
+      return EB200_OK;
+    }
+
+    int CurrentsFilter(Domain& dom) {
+      return eb200_filter(dom.ctx, dom.cur0, dom.buff, dom.prm->nfilter, dom.prm->fbc, dom.stream);
+    }
+
+    int SortParticles(Domain& dom, uint32_t step) {
+      const int  ci = dom.prm->clear_interval, si = dom.prm->sort_interval;
+      const bool clear = (ci > 0) && (step % (uint32_t)ci == 0u) && (step > 0u);
+      const bool sort  = (si > 0) && (step % (uint32_t)si == 0u);
+      if (!clear && !sort) return EB200_OK;
+      for (int s = 0; s < dom.nspecies; ++s) {
+        eb200_species_t& sp = dom.species[s];
+        if (sp.npart == 0) continue;
+        uint32_t n = sp.npart;
+        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | EB200_SORT_SKIP_PREV,
+                                 dom.stream));
+        sp.npart = n;
+      }
+      return EB200_OK;
+    }
+
+#define FS(expr)                                                                               \
+  do {                                                                                         \
+    PHASE(dom, EB200_PHASE_FIELDSOLVER);                                                       \
+    TRY(expr);                                                                                 \
+  } while (0)
+
+    // GRPICEngine::step_forward, grpic.hpp:66-634. A single domain has no neighbour: the
+    // CommunicateFields / SynchronizeFields calls between the sub-steps have nothing to move
+    // (no face of a 2D (r, theta) domain is periodic).
+    int step_forward(Domain& dom, uint32_t step) {
+      const eb200_grpic_params_t& p = *dom.prm;
+      const int BC_DB = EB200_BC_E | EB200_BC_B;
+      if (step == 0) {
+        if (p.fieldsolver_enabled) {
+          TRY(FieldBoundaries(dom, BC_DB, gr_bc::main));                 // :99-104
+          TRY(CopyFields(dom));                                          // :112
+          FS(ComputeAuxE(dom, gr_getE::D_B0));                           // :120-121
+          FS(ComputeAuxH(dom, gr_getH::D_B0));
+          TRY(FieldBoundaries(dom, BC_DB, gr_bc::aux));                  // :127-132
+          FS(Faraday(dom, gr_faraday::aux, 0.5f));                       // :139-143
+          TRY(FieldBoundaries(dom, EB200_BC_B, gr_bc::main));            // :149-154
+          FS(Ampere(dom, gr_ampere::init, 0.5f));                        // :161-165
+          TRY(FieldBoundaries(dom, EB200_BC_E, gr_bc::main));            // :171-176
+          FS(ComputeAuxE(dom, gr_getE::D_B0));                           // :184-185
+          FS(ComputeAuxH(dom, gr_getH::D_B0));
+          TRY(FieldBoundaries(dom, BC_DB, gr_bc::aux));                  // :191-196
+          FS(Faraday(dom, gr_faraday::main, 1.0f));                      // :205-209
+          TRY(FieldBoundaries(dom, EB200_BC_B, gr_bc::main));            // :214-219
+          FS(Ampere(dom, gr_ampere::aux, 1.0f));                         // :226
+          TRY(FieldBoundaries(dom, EB200_BC_E, gr_bc::main));            // :231-236
+          FS(ComputeAuxH(dom, gr_getH::D0_B0));                          // :243
+          TRY(FieldBoundaries(dom, EB200_BC_B, gr_bc::aux));             // :248-253
+          FS(Ampere(dom, gr_ampere::main, 1.0f));                        // :261
+          TRY(FieldBoundaries(dom, EB200_BC_E, gr_bc::main));            // :266-271
+          SwapFields(dom);                                               // :278
+        } else {
+          TRY(CopyFields(dom));                                          // :302
+        }
+      }
+      if (p.fieldsolver_enabled) {
+        FS(TimeAverageDB(dom));                                          // :329
+        FS(ComputeAuxE(dom, gr_getE::D0_B));                             // :330
+        TRY(FieldBoundaries(dom, EB200_BC_E, gr_bc::aux));
+        FS(Faraday(dom, gr_faraday::aux, 1.0f));
+        TRY(FieldBoundaries(dom, EB200_BC_B, gr_bc::main));
+        FS(ComputeAuxH(dom, gr_getH::D_B0));
+        TRY(FieldBoundaries(dom, EB200_BC_B, gr_bc::aux));
+      }
+      {
+        {
+          PHASE(dom, EB200_PHASE_PUSH_DEPOSIT);
+          TRY(ParticlePush(dom));
+          if (p.deposit_enabled) {
+            size_t n = 3;
+            for (int a = 0; a < dom.grid.dim; ++a) n *= (size_t)(dom.grid.n[a] + 2 * dom.grid.ng);
+            if (cudaMemsetAsync(dom.cur0, 0, n * sizeof(float), (cudaStream_t)dom.stream) != cudaSuccess) {
+              return EB200_ERR_CUDA;
+            }
+            TRY(CurrentsDeposit(dom));
+          }
+        }
+        if (p.deposit_enabled) {
+          TRY(FieldBoundaries(dom, EB200_BC_E, gr_bc::curr));
+          PHASE(dom, EB200_PHASE_FILTER);
+          TRY(CurrentsFilter(dom));
+        }
+      }
+      if (p.fieldsolver_enabled) {
+        if (p.deposit_enabled) {
+          FS(TimeAverageJ(dom));
+        }
+        FS(ComputeAuxE(dom, gr_getE::D_B0));
+        TRY(FieldBoundaries(dom, EB200_BC_E, gr_bc::aux));
+        FS(Faraday(dom, gr_faraday::main, 1.0f));
+        TRY(FieldBoundaries(dom, EB200_BC_B, gr_bc::main));
+        FS(Ampere(dom, gr_ampere::aux, 1.0f));
+        if (p.deposit_enabled) {
+          FS(AmpereCurrents(dom, gr_ampere::aux));
+        }
+        TRY(FieldBoundaries(dom, EB200_BC_E, gr_bc::main));
+        FS(ComputeAuxH(dom, gr_getH::D0_B0));
+        TRY(FieldBoundaries(dom, EB200_BC_B, gr_bc::aux));
+        FS(Ampere(dom, gr_ampere::main, 1.0f));
+        if (p.deposit_enabled) {
+          FS(AmpereCurrents(dom, gr_ampere::main));
+        }
+        SwapFields(dom);
+        TRY(FieldBoundaries(dom, EB200_BC_E, gr_bc::main));
+      }
+      {
+        PHASE(dom, EB200_PHASE_SORT);
+        TRY(SortParticles(dom, step));
+      }
+      return EB200_OK;
+    }
+#undef FS
+
+  } // namespace grpic
+} // namespace eb200
+
+extern "C" int eb200_grpic_step(eb200_ctx_t* ctx, const eb200_grpic_params_t* prm, float** em,
+                                float** em0, float** cur, float** cur0, float* aux, float* buff,
+                                const float* match_target, eb200_species_t* species, int nspecies,
+                                uint32_t step, double time, eb200_stream_t stream) {
+  (void)time;
+  if (!ctx || !prm || !em || !em0 || !cur || !cur0 || !*em || !*em0 || !*cur || !*cur0 || !aux ||
+      !buff || (nspecies > 0 && !species)) {
+    return EB200_ERR_ARG;
+  }
+  eb200::grpic::Domain dom;
+  dom.ctx = ctx;
+  dom.prm = prm;
+  float dx_unused, xmin_unused[3];
+  int   rc = eb200_ctx_grid(ctx, &dom.grid, &dx_unused, xmin_unused);
+  if (rc != EB200_OK) return rc;
+  if (dom.grid.dim != 2) return EB200_ERR_ARG;
+  dom.em = *em, dom.em0 = *em0, dom.cur = *cur, dom.cur0 = *cur0;
+  dom.aux = aux, dom.buff = buff;
+  dom.match_target = match_target;
+  dom.species = species, dom.nspecies = nspecies;
+  dom.stream = stream;
+  dom.prof   = &eb200_ctx_engine_state(ctx)->prof;
+  rc         = eb200::grpic::step_forward(dom, step);
+  *em = dom.em, *em0 = dom.em0, *cur = dom.cur, *cur0 = dom.cur0;
+  return rc;
+}
+
 // accessors into the opaque context (capi.cu)
 extern "C" int eb200_ctx_grid(const eb200_ctx_t* ctx, eb200_grid_t* grid, float* dx, float* xmin3);
 

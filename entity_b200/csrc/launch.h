@@ -97,9 +97,26 @@ namespace eb200 {
   EB200_DECLARE_VARIANT(strict_fp)
   EB200_DECLARE_VARIANT(fast_fp)
 
+  cudaError_t conductor_fields2d(const eb200_grid_t& g, float* em, int o, bool pos, int tags,
+                                 cudaStream_t st);
+
   // curvilinear SR and GR kernels: curv.cu (one build, IEEE division, no FMA contraction)
   struct MetricParams;
   namespace curv {
+    // field boundaries (bcs.cu)
+    cudaError_t axis_fields(const eb200_grid_t& g, float* fld, bool pos, int tags, cudaStream_t st);
+    cudaError_t horizon_fields(const eb200_grid_t& g, float* fld, int tags, int nfilter,
+                               cudaStream_t st);
+    cudaError_t match_fields_curv(const MetricParams& m, const eb200_grid_t& g, float* fld,
+                                  const float* target, int o, float xg_edge, float ds, int tags,
+                                  int mask, const int* rmin, const int* rmax, const int* fbc,
+                                  cudaStream_t st);
+    cudaError_t enforce_fields(const eb200_grid_t& g, float* em, const float* target, int o,
+                               bool pos, int i_edge, int tags, int mask, const int* rmin,
+                               const int* rmax, cudaStream_t st);
+    cudaError_t absorb_currents(const MetricParams& m, const eb200_grid_t& g, float* cur,
+                                float xg_edge, float ds, const int* rmin, const int* rmax,
+                                cudaStream_t st);
     cudaError_t push_sr(const MetricParams& m, const eb200_grid_t& g, int order,
                         const eb200_pusher_t& c, const eb200_prtls_t& S, uint32_t npart,
                         const float* em, cudaStream_t st);

@@ -11,6 +11,7 @@ PUSHER_NONE, PUSHER_PHOTON, PUSHER_BORIS, PUSHER_VAY, PUSHER_GCA = 0, 1, 2, 4, 8
 DRAG_NONE, DRAG_SYNCHROTRON, DRAG_COMPTON = 0, 1, 2
 PBC_NONE, PBC_PERIODIC, PBC_ABSORB, PBC_REFLECT, PBC_AXIS = 0, 1, 2, 3, 4
 FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC = 0, 1, 2, 3, 4
+FBC_MATCH, FBC_HORIZON, FBC_ATMOSPHERE = 5, 6, 7
 DEPOSIT_ATOMIC, DEPOSIT_ORDERED, DEPOSIT_AGGREGATED = 0, 1, 2
 STATS_B2, STATS_E2, STATS_EXB, STATS_JDOTE = 0, 1, 2, 3
 BC_E, BC_B = 1, 2
@@ -144,6 +145,21 @@ class ParamsC(C.Structure):
         ("sort_interval", C.c_int), ("clear_interval", C.c_int),
     ]
 
+
+
+class GRParamsC(C.Structure):
+    """eb200_grpic_params_t"""
+    _fields_ = [
+        ("dt", C.c_float), ("correction", C.c_float), ("omegaB0", C.c_float),
+        ("q0", C.c_float), ("B0", C.c_float),
+        ("nfilter", C.c_int), ("fieldsolver_enabled", C.c_int), ("deposit_enabled", C.c_int),
+        ("fbc", C.c_int * 6), ("pbc", C.c_int * 6),
+        ("pusher_eps", C.c_float), ("pusher_niter", C.c_int),
+        ("deposit_mode", C.c_int), ("sort_interval", C.c_int), ("clear_interval", C.c_int),
+        ("match_xg_edge", C.c_float), ("match_ds", C.c_float),
+        ("match_range_min", C.c_int * 2), ("match_range_max", C.c_int * 2),
+        ("match_mask", C.c_int),
+    ]
 
 
 class MetadomainC(C.Structure):

@@ -53,7 +53,9 @@ enum { EB200_DRAG_NONE = 0, EB200_DRAG_SYNCHROTRON = 1, EB200_DRAG_COMPTON = 2 }
  * (src/kernels/pushers/context.h:124-178). NONE = SYNC/other: particle leaves, gets a send tag. */
 enum { EB200_PBC_NONE = 0, EB200_PBC_PERIODIC = 1, EB200_PBC_ABSORB = 2, EB200_PBC_REFLECT = 3, EB200_PBC_AXIS = 4 };
 /* field boundary per face, as far as filter and ghost exchange need it (ntt::FldsBC) */
-enum { EB200_FBC_NONE = 0, EB200_FBC_PERIODIC = 1, EB200_FBC_CONDUCTOR = 2, EB200_FBC_AXIS = 3, EB200_FBC_SYNC = 4 };
+enum { EB200_FBC_NONE = 0, EB200_FBC_PERIODIC = 1, EB200_FBC_CONDUCTOR = 2, EB200_FBC_AXIS = 3, EB200_FBC_SYNC = 4,
+       /* faces the step mirrors apply a boundary kernel to (srpic / grpic ::FieldBoundaries) */
+       EB200_FBC_MATCH = 5, EB200_FBC_HORIZON = 6, EB200_FBC_ATMOSPHERE = 7 };
 /* ntt::Metric (src/global/enums.h): the curvilinear metrics are 2D axisymmetric, like the
  * reference's (static_asserts in src/metrics/qspherical.h:34-35 etc.) */
 enum {
@@ -495,6 +497,82 @@ int eb200_currents_ampere_gr(eb200_ctx_t* ctx, float* d_fld, const float* cur, f
  * a = (a + b) / 2 on the active cells of an ncomp-component field */
 int eb200_time_average(eb200_ctx_t* ctx, float* a, const float* b, int ncomp,
                        eb200_stream_t stream);
+
+/* ============ field boundaries of 2D curvilinear SRPIC and GRPIC domains ==========
+ * What srpic::FieldBoundaries / grpic::FieldBoundaries launch (src/engines/srpic/fields_bcs.h:
+ * 39-672, src/engines/grpic/fields_bcs.h:42-270). tags: EB200_BC_E = the first three components
+ * of the field (E, D, aux E), EB200_BC_B = the last three (B, aux H) -- what the reference's
+ * BC::E | BC::D and BC::B | BC::H select. Ranges are ghost-inclusive [min, max) per dimension,
+ * as Mesh::ExtentToRange returns them. Functor arguments of the reference's kernels (the pgen's
+ * MatchFields / AtmFields / init_flds) arrive as `target`: six component planes in the layout
+ * of the field, every value taken at the component's own node, in the basis the reference's
+ * kernel blends with (SRPIC: metric.transform<c, Idx::T, Idx::U>(node, f(x_Ph)); GRPIC: f(x_Ph)
+ * as returned); `mask` bit c = the functor defines component c. */
+/* kernel::bc::AxisBoundaries_kernel<Dim::_2D, P> (fields_bcs.hpp:824-868) on the x2 face given
+ * by sign (< 0: i2min, > 0: i2max); fld = em, em0 (6 components) */
+int eb200_axis_fields(eb200_ctx_t* ctx, float* fld, int sign, int tags, eb200_stream_t stream);
+/* kernel::bc::gr::HorizonBoundaries_kernel<Dim::_2D> (fields_bcs.hpp:1187-1240) at i1min;
+ * nfilter = algorithms.current_filters; fld = em, em0 or aux */
+int eb200_horizon_fields(eb200_ctx_t* ctx, float* fld, int tags, int nfilter,
+                         eb200_stream_t stream);
+/* kernel::bc::MatchBoundaries_kernel<S, M, FS, o> for a non-Cartesian metric (fields_bcs.hpp:
+ * 176-340): F = s F + (1 - s) target, s = tanh(|x_o - xg_edge| 4 / ds) at the component's node;
+ * fbc_host[6]: the AXIS flags of the x2 faces switch off the target of the third E / D
+ * component on the axis rows. o = 0 (x1) or 1 (x2). */
+int eb200_match_fields_curv(eb200_ctx_t* ctx, float* fld, const float* target, int o,
+                            float xg_edge, float ds, int tags, int components_mask,
+                            const int* range_min, const int* range_max, const int* fbc_host,
+                            eb200_stream_t stream);
+/* kernel::bc::EnforcedBoundaries_kernel<M, FS, P, O> (fields_bcs.hpp:870-1185; the ATMOSPHERE
+ * field boundary of srpic::AtmosphereFieldsIn, fields_bcs.h:470-600): inside the range the
+ * defined components are SET to target, the normal E and tangential B components only on the
+ * far side of i_edge (ghost-inclusive cell index; i >= i_edge for sign > 0, i < i_edge else) */
+int eb200_enforce_fields(eb200_ctx_t* ctx, float* em, const float* target, int o, int sign,
+                         int i_edge, int tags, int components_mask, const int* range_min,
+                         const int* range_max, eb200_stream_t stream);
+/* kernel::bc::gr::AbsorbCurrents_kernel<M, 1> (fields_bcs.hpp:1242-1283; grpic gr_bc::curr):
+ * J *= tanh(|r - xg_edge| / (ds / 4)) inside the range; cur = the 3-component cur0 */
+int eb200_absorb_currents_gr(eb200_ctx_t* ctx, float* cur, float xg_edge, float ds,
+                             const int* range_min, const int* range_max, eb200_stream_t stream);
+/* kernel::bc::ConductorBoundaries_kernel<Dim::_2D, o, P> over the range of
+ * srpic::PerfectConductorFieldsIn (fields_bcs.h:384-470), Minkowski 2D domains */
+int eb200_conductor_fields(eb200_ctx_t* ctx, float* em, int o, int sign, int tags,
+                           eb200_stream_t stream);
+
+/* ------------------------------------------------------------ the GRPIC step (2D) */
+/* What GRPICEngine::step_forward reads from SimulationParams / Domain, by value. */
+typedef struct {
+  float dt;           /* algorithms.timestep.dt */
+  float correction;   /* algorithms.timestep.correction */
+  float omegaB0;      /* scales.omegaB0 */
+  float q0, B0;       /* scales.* */
+  int   nfilter;      /* algorithms.current_filters */
+  int   fieldsolver_enabled, deposit_enabled;
+  int   fbc[6];       /* EB200_FBC_* per face: x1 = {HORIZON, MATCH}, x2 = {AXIS, AXIS} */
+  int   pbc[6];       /* EB200_PBC_* per face: x1 = {ABSORB (horizon), ABSORB}, x2 = {AXIS, AXIS} */
+  float pusher_eps;   /* algorithms.gr.pusher_eps */
+  int   pusher_niter; /* algorithms.gr.pusher_niter */
+  int   deposit_mode; /* EB200_DEPOSIT_* */
+  int   sort_interval, clear_interval;
+  /* the +x1 MATCH layer of grpic::MatchFieldsIn (fields_bcs.h:42-133): edge of the global box,
+   * grid.boundaries.match.ds and the ghost-inclusive cell range Mesh::ExtentToRange gives;
+   * currents are absorbed in the same layer (gr_bc::curr) where pbc[1] is ABSORB */
+  float match_xg_edge, match_ds;
+  int   match_range_min[2], match_range_max[2];
+  int   match_mask;   /* components pgen.init_flds defines */
+} eb200_grpic_params_t;
+/* One call = GRPICEngine::step_forward (src/engines/grpic/grpic.hpp:66-634) for a single 2D
+ * Kerr-Schild type domain, including the start-up sequence of step 0: time averages, auxiliary
+ * fields, the two Faraday / Ampere sub-steps with currents, pusher, deposit into cur0, filter,
+ * every grpic::FieldBoundaries call (MATCH towards match_target = pgen.init_flds tabulated on
+ * each component's node, AXIS, HORIZON, AbsorbCurrents), SwapFields and SortParticles.
+ * SwapFields exchanges the caller's POINTERS (the reference swaps its views, utils.h:31-35):
+ * *em <-> *em0 and *cur <-> *cur0 on return. aux and buff are 6- / 3-component scratch fields
+ * of the host (Fields::aux, Fields::buff). */
+int eb200_grpic_step(eb200_ctx_t* ctx, const eb200_grpic_params_t* prm, float** em, float** em0,
+                     float** cur, float** cur0, float* aux, float* buff,
+                     const float* match_target, eb200_species_t* species, int nspecies,
+                     uint32_t step, double time, eb200_stream_t stream);
 
 /* Host-side evaluation of the metric functions the kernels use (same source, compiled for the
  * host): what the reference's setup code gets from metric.h_<i,j>() etc. (src/metrics/*.h).

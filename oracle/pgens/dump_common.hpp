@@ -200,6 +200,106 @@ namespace ebdump {
     }
   }
 
+  // What a field-setter functor of the pgen (init_flds for GRPIC MATCH, MatchFields / AtmFields
+  // for SRPIC) evaluates to on every component's own node of the ghost-inclusive 2D mesh, in
+  // the basis the boundary kernels blend with (fields_bcs.hpp:176-340, 975-1060): SRPIC =
+  // transform<c, T, U>(node, f(x_Ph)), GRPIC = f(x_Ph) as is. Components the functor does not
+  // define stay 0; `mask` bit c says which are defined. This is the table a host hands to the
+  // C ABI in place of the functor.
+  template <ntt::SimEngine::type S, class M, class FS>
+  void target2d(std::FILE* f, const std::string& name, const FS& fs, ntt::Domain<S, M>& dom) {
+    if constexpr (M::Dim == Dim::_2D) {
+      const auto&       metric = dom.mesh.metric;
+      const std::size_t N1 = dom.fields.em.extent(0), N2 = dom.fields.em.extent(1);
+      std::vector<float> buf(6 * N1 * N2, 0.0f);
+      std::uint32_t      mask = 0;
+      auto put = [&](int c, std::size_t i, std::size_t j, real_t v) { buf[(c * N2 + j) * N1 + i] = v; };
+      for (std::size_t j = 0; j < N2; ++j) {
+        for (std::size_t i = 0; i < N1; ++i) {
+          const real_t i1_ = static_cast<real_t>(static_cast<int>(i) - static_cast<int>(N_GHOSTS));
+          const real_t i2_ = static_cast<real_t>(static_cast<int>(j) - static_cast<int>(N_GHOSTS));
+          coord_t<Dim::_2D> x00 { ZERO }, x0H { ZERO }, xH0 { ZERO }, xHH { ZERO };
+          metric.template convert<Crd::Cd, Crd::Ph>({ i1_, i2_ }, x00);
+          metric.template convert<Crd::Cd, Crd::Ph>({ i1_, i2_ + HALF }, x0H);
+          metric.template convert<Crd::Cd, Crd::Ph>({ i1_ + HALF, i2_ }, xH0);
+          metric.template convert<Crd::Cd, Crd::Ph>({ i1_ + HALF, i2_ + HALF }, xHH);
+          if constexpr (S == ntt::SimEngine::SRPIC) {
+            if constexpr (requires { fs.ex1(xH0); }) {
+              mask |= 1u;
+              put(0, i, j, metric.template transform<1, Idx::T, Idx::U>({ i1_ + HALF, i2_ }, fs.ex1(xH0)));
+            }
+            if constexpr (requires { fs.ex2(x0H); }) {
+              mask |= 2u;
+              put(1, i, j, metric.template transform<2, Idx::T, Idx::U>({ i1_, i2_ + HALF }, fs.ex2(x0H)));
+            }
+            if constexpr (requires { fs.ex3(x00); }) {
+              mask |= 4u;
+              put(2, i, j, metric.template transform<3, Idx::T, Idx::U>({ i1_, i2_ }, fs.ex3(x00)));
+            }
+            if constexpr (requires { fs.bx1(x0H); }) {
+              mask |= 8u;
+              put(3, i, j, metric.template transform<1, Idx::T, Idx::U>({ i1_, i2_ + HALF }, fs.bx1(x0H)));
+            }
+            if constexpr (requires { fs.bx2(xH0); }) {
+              mask |= 16u;
+              put(4, i, j, metric.template transform<2, Idx::T, Idx::U>({ i1_ + HALF, i2_ }, fs.bx2(xH0)));
+            }
+            if constexpr (requires { fs.bx3(xHH); }) {
+              mask |= 32u;
+              put(5, i, j, metric.template transform<3, Idx::T, Idx::U>({ i1_ + HALF, i2_ + HALF }, fs.bx3(xHH)));
+            }
+          } else {
+            if constexpr (requires { fs.dx1(xH0); }) { mask |= 1u; put(0, i, j, fs.dx1(xH0)); }
+            if constexpr (requires { fs.dx2(x0H); }) { mask |= 2u; put(1, i, j, fs.dx2(x0H)); }
+            if constexpr (requires { fs.dx3(x00); }) { mask |= 4u; put(2, i, j, fs.dx3(x00)); }
+            if constexpr (requires { fs.bx1(x0H); }) { mask |= 8u; put(3, i, j, fs.bx1(x0H)); }
+            if constexpr (requires { fs.bx2(xH0); }) { mask |= 16u; put(4, i, j, fs.bx2(xH0)); }
+            if constexpr (requires { fs.bx3(xHH); }) { mask |= 32u; put(5, i, j, fs.bx3(xHH)); }
+          }
+        }
+      }
+      rec(f, name, 0, { 6, (std::uint64_t)N2, (std::uint64_t)N1 }, buf.data(), buf.size() * 4);
+      rec(f, name + "_mask", 4, { 1 }, &mask, 4);
+    }
+  }
+
+  template <ntt::SimEngine::type S, class M, class PG>
+  void targets(long step, double time, PG& pg, ntt::Domain<S, M>& dom) {
+    const char* dir = std::getenv("EB_DUMP_DIR");
+    if (!dir || !steps().count(step)) return;
+    if constexpr (M::Dim == Dim::_2D && M::CoordType != Coord::Cartesian) {
+      std::string fn = std::string(dir) + "/s" + std::to_string(step) + "_tgt.bin";
+      std::FILE* f = std::fopen(fn.c_str(), "wb");
+      if (!f) return;
+      if constexpr (S == ntt::SimEngine::GRPIC) {
+        if constexpr (requires { pg.init_flds; }) target2d<S, M>(f, "init_flds", pg.init_flds, dom);
+      } else {
+        if constexpr (requires { pg.MatchFields(time); }) target2d<S, M>(f, "match", pg.MatchFields(time), dom);
+        if constexpr (requires { pg.AtmFields(time); }) target2d<S, M>(f, "atm", pg.AtmFields(time), dom);
+      }
+      std::fclose(f);
+    }
+  }
+
+  // the derived scalars the engines read from SimulationParams (parameters.cpp:47-78,
+  // algorithms.cpp:18-30): what a host passes by value across the C ABI
+  inline void scales(long step, const ntt::SimulationParams& params) {
+    const char* dir = std::getenv("EB_DUMP_DIR");
+    if (!dir || !steps().count(step)) return;
+    std::string fn = std::string(dir) + "/s" + std::to_string(step) + "_scl.bin";
+    std::FILE* f = std::fopen(fn.c_str(), "wb");
+    if (!f) return;
+    const char* names[] = { "algorithms.timestep.dt", "algorithms.timestep.correction",
+                            "scales.q0", "scales.B0", "scales.omegaB0", "scales.V0", "scales.n0",
+                            "scales.sigma0", "scales.larmor0", "scales.skindepth0", "scales.dx0",
+                            "particles.ppc0" };
+    for (const char* nm : names) {
+      const float v = (float)params.template get<real_t>(nm);
+      rec(f, nm, 0, { 1 }, &v, 4);
+    }
+    std::fclose(f);
+  }
+
   // EB_COUNT_FILE: one line per step, "step npart_0 npart_1 ..." (host-side counters only;
   // the reference's own stats writer needs -D output=ON)
   template <ntt::SimEngine::type S, class M>
@@ -225,7 +325,9 @@ namespace user {
 
     // the reference's pgens differ in the constness of their constructor arguments
     template <class P, class MD>
-    PGen(P&& p, MD&& m) : base_t { std::forward<P>(p), std::forward<MD>(m) } {}
+    PGen(P&& p, MD&& m) : base_t { std::forward<P>(p), std::forward<MD>(m) }, eb_params { &p } {}
+
+    const SimulationParams* eb_params;
 
     void CustomPostStep(timestep_t step, simtime_t time, Domain<S, M>& dom) {
       ebdump::npart_pre().clear();
@@ -233,7 +335,9 @@ namespace user {
       if constexpr (::traits::pgen::HasCustomPostStep<base_t, Domain<S, M>>) {
         base_t::CustomPostStep(step, time, dom);
       }
+      ebdump::scales((long)step, *eb_params);
       ebdump::antenna((long)step, *static_cast<base_t*>(this));
+      ebdump::targets((long)step, (double)time, *static_cast<base_t*>(this), dom);
       ebdump::counts((long)step, dom);
       ebdump::dump((long)step, (double)time, dom);
     }

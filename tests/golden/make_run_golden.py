@@ -36,6 +36,10 @@ CASES = {
     # antenna-driven (ext_current); the 3D one is the esirkepov / shape_order = 3 build
     "turbulence2d": ("omp/entity_turbulence.xc", "turbulence2d.toml", 0, 8),
     "turbulence3d": ("omp3/entity_turbulence.xc", "turbulence3d.toml", 0, 4),
+    # GRPIC: vacuum Wald solution (fields + boundaries only)
+    "wald_small": ("omp/entity_wald.xc", "wald_small.toml", 0, 6),
+    # GRPIC with particles: pusher, deposit into cur0, AbsorbCurrents, filter, both AmpereCurrents
+    "accretion_small": ("omp/entity_accretion.xc", "accretion_small.toml", 0, 5),
 }
 
 
@@ -66,6 +70,17 @@ def run_case(name):
             out[f"s{s}/time"] = d["time"]
             out[f"s{s}/em"] = d["em"]
             out[f"s{s}/cur"] = d["cur"]
+            for extra in ("em0", "cur0", "aux"):
+                if extra in d:
+                    out[f"s{s}/{extra}"] = d[extra]
+            scl = os.path.join(tmp, f"s{s}_scl.bin")
+            if s == s0 and os.path.exists(scl):
+                for k_, v_ in refdump.read(scl).items():
+                    out[f"meta/{k_}"] = v_
+            tgt = os.path.join(tmp, f"s{s}_tgt.bin")
+            if s == s0 and os.path.exists(tgt):
+                for k_, v_ in refdump.read(tgt).items():
+                    out[f"meta/target_{k_}"] = v_
             ant = os.path.join(tmp, f"s{s}_ant.bin")
             if os.path.exists(ant):
                 for k_, v_ in refdump.read(ant).items():

@@ -82,3 +82,32 @@ def match_faces(case, g):
     ext = [n[0] + 2 * g.ng, n[1] + 2 * g.ng]
     return [(1, ymin, ds, [0, 0], [ext[0], g.ng + nds]),
             (1, ymax, ds, [0, g.ng + n[1] - nds], [ext[0], ext[1]])]
+
+
+# ------------------------------------------------------------------ GRPIC cases
+GR_CASES = {
+    # pgens/wald/wald.toml at fixture size (tests/golden/run_inputs/wald_small.toml)
+    "wald_small": dict(n=(64, 48), metric="qkerr_schild", extent=(1.0, 10.0), r0=0.0, h=0.0, a=0.95,
+                       larmor0=0.0025, skindepth0=0.05, ppc0=2.0, nfilter=0, deposit=False,
+                       match_ds=1.0, pushers=[], cap=0),
+    # pgens/accretion/accretion.toml at fixture size (run_inputs/accretion_small.toml)
+    "accretion_small": dict(n=(48, 32), metric="qkerr_schild", extent=(1.0, 6.0), r0=0.0, h=0.0, a=0.95,
+                            larmor0=0.025, skindepth0=0.5, ppc0=2.0, nfilter=4, deposit=True,
+                            match_ds=1.0, pushers=[2, 2], cap=8192, niter=10, eps=1e-2),
+}
+
+
+def gr_match_range(case, ng):
+    """grpic::MatchFieldsIn for the +x1 face (fields_bcs.h:42-96): box [x1max - ds, x1max] through
+    Mesh::ExtentToRange with incl_ghosts = (false, true) along x1 and (true, true) along x2
+    (mesh.h:133-200); qkerr_schild: x1 = (ln(r - r0) - chi_min) / dchi in fp32."""
+    c = GR_CASES[case]
+    f32 = np.float32
+    n1, n2 = c["n"]
+    r_min, r_max = f32(c["extent"][0]), f32(c["extent"][1])
+    chi_min = np.log(r_min - f32(c["r0"]))
+    dchi = (np.log(r_max - f32(c["r0"])) - chi_min) / f32(n1)
+    to_cd = lambda r: (np.log(f32(r) - f32(c["r0"])) - chi_min) / dchi
+    lo = max(float(np.floor(to_cd(r_max - f32(c["match_ds"])))), 0.0)
+    hi = float(np.ceil(to_cd(r_max)))
+    return [int(lo) + ng, 0], [int(hi) + 2 * ng, n2 + 2 * ng]
