@@ -255,6 +255,8 @@ int eb200_ctx_grid(const eb200_ctx_t* ctx, eb200_grid_t* grid, float* dx, float*
   return EB200_OK;
 }
 
+int eb200_ctx_metric(const eb200_ctx_t* ctx) { return ctx ? ctx->cfg.metric : -1; }
+
 static bool is_sr_curv(const eb200_ctx* ctx) {
   return ctx->cfg.metric == EB200_METRIC_SPHERICAL || ctx->cfg.metric == EB200_METRIC_QSPHERICAL;
 }

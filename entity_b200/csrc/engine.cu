@@ -79,6 +79,8 @@ namespace eb200 {
     std::vector<eb200_match_face_t> match;
     const float*                    match_target = nullptr;
     int                             match_mask   = 0;
+    // MATCH / ATMOSPHERE faces of a curvilinear domain (eb200_srpic_set_field_bcs)
+    std::vector<eb200_field_bc_t> curv_bcs;
     // the pgen's ext_current as a mode table (eb200_srpic_set_ext_current)
     bool                has_ext = false;
     eb200_ext_current_t ext {};
@@ -107,6 +109,7 @@ namespace eb200 {
 } // namespace eb200
 
 extern "C" eb200::EngineState* eb200_ctx_engine_state(eb200_ctx_t* ctx);
+extern "C" int                 eb200_ctx_metric(const eb200_ctx_t* ctx);
 extern "C" int                 eb200_ctx_has_comm(const eb200_ctx_t* ctx);
 
 namespace eb200 {
@@ -125,6 +128,7 @@ namespace eb200 {
       Profiler*                   prof;
       HostStreamer*               host = nullptr; // non-null: particle arrays stream from/to the host
       const EngineState*          eng  = nullptr; // MATCH faces, if any
+      bool                        curv = false;   // spherical / qspherical metric
     };
 
 #define PHASE(dom, which) PhaseScope phase_scope_((dom).prof, (which), (cudaStream_t)(dom).stream)
@@ -139,6 +143,9 @@ namespace eb200 {
     int Faraday(Domain& dom, float fraction) {
       const float dt = dom.prm->dt;
       const float dT = fraction * dom.prm->correction * dt;
+      if (dom.curv) { // kernel::sr::Faraday_kernel over rangeActiveCells (fieldsolvers.h:89-97)
+        return eb200_faraday_sr(dom.ctx, dom.em, dT, dom.prm->fbc, dom.stream);
+      }
       const float dx = std::sqrt(dom.dx * dom.dx); // sqrt(h_<1,1>)
       float       coeff1, coeff2;
       if (dom.grid.dim == 2) {
@@ -155,6 +162,9 @@ namespace eb200 {
     int Ampere(Domain& dom, float fraction) {
       const float dt = dom.prm->dt;
       const float dT = fraction * dom.prm->correction * dt;
+      if (dom.curv) { // kernel::sr::Ampere_kernel over RangeWithAxisBCs (fieldsolvers.h:128-137)
+        return eb200_ampere_sr(dom.ctx, dom.em, dT, dom.prm->fbc, dom.stream);
+      }
       const float dx = std::sqrt(dom.dx * dom.dx);
       float       coeff1, coeff2;
       if (dom.grid.dim == 2) {
@@ -170,6 +180,11 @@ namespace eb200 {
     // srpic::CurrentsAmpere, fieldsolvers.h:142-199 (Cartesian, no external current)
     int CurrentsAmpere(Domain& dom) {
       const eb200_srpic_params_t& p     = *dom.prm;
+      if (dom.curv) { // fieldsolvers.h:183-198
+        const float coeff = -p.dt * p.q0 * p.n0 / p.B0;
+        return eb200_currents_ampere_sr(dom.ctx, dom.em, dom.cur, coeff, 1.0f / p.n0, p.fbc,
+                                        dom.stream);
+      }
       const float                 coeff = -p.dt * p.q0 / (p.B0 * p.V0);
       if (dom.eng && dom.eng->has_ext) {
         return eb200_currents_ampere_ext(dom.ctx, dom.em, dom.cur, coeff, p.ppc0, &dom.eng->ext,
@@ -201,6 +216,12 @@ namespace eb200 {
       if (sp.drag_flags & EB200_DRAG_COMPTON) {
         const float gm  = p.compton_gamma_rad * sp.mass;
         c.compton_coeff = 0.1f * p.dt * p.omegaB0 / (gm * gm);
+      }
+      if (p.has_atmosphere) { // particle_pusher.h:45-80, 121-127
+        c.has_atmosphere = 1;
+        c.atm_gx1 = p.atm_g[0], c.atm_gx2 = p.atm_g[1], c.atm_gx3 = p.atm_g[2];
+        c.atm_x_surf = p.atm_x_surf;
+        c.atm_ds     = p.atm_ds;
       }
       for (int a = 0; a < 6; ++a) c.pbc[a] = p.pbc[a];
       c.tag_outgoing = 0;
@@ -347,6 +368,30 @@ namespace eb200 {
     // context; the other kinds (CONDUCTOR inside the filter / field kernels, PERIODIC and SYNC
     // inside the exchanges) are handled where the data moves
     int FieldBoundaries(Domain& dom, int tags) {
+      if (dom.curv) {
+        // dir::Directions<Dim::_2D>::orth = (-x1, -x2, +x2, +x1), fields_bcs.h:619-668
+        PHASE(dom, EB200_PHASE_FIELDSOLVER);
+        static const int orth[4] = { 0, 2, 3, 1 }; // face = 2 * dim + (sign > 0)
+        for (int q = 0; q < 4; ++q) {
+          const int face = orth[q], o = face >> 1, sign = (face & 1) ? +1 : -1;
+          if (dom.prm->fbc[face] == EB200_FBC_AXIS) {
+            TRY(eb200_axis_fields(dom.ctx, dom.em, sign, tags, dom.stream));
+            continue;
+          }
+          if (!dom.eng) continue;
+          for (const eb200_field_bc_t& b : dom.eng->curv_bcs) {
+            if (b.o != o || (b.sign > 0) != (sign > 0)) continue;
+            if (b.kind == EB200_FBC_MATCH) {
+              TRY(eb200_match_fields_curv(dom.ctx, dom.em, b.target, b.o, b.xg_edge, b.ds, tags, b.mask,
+                                          b.range_min, b.range_max, dom.prm->fbc, dom.stream));
+            } else if (b.kind == EB200_FBC_ATMOSPHERE) {
+              TRY(eb200_enforce_fields(dom.ctx, dom.em, b.target, b.o, b.sign, b.i_edge, tags, b.mask,
+                                       b.range_min, b.range_max, dom.stream));
+            }
+          }
+        }
+        return EB200_OK;
+      }
       if (!dom.eng || dom.eng->match.empty()) return EB200_OK;
       PHASE(dom, EB200_PHASE_FIELDSOLVER);
       for (const eb200_match_face_t& f : dom.eng->match) {
@@ -379,7 +424,7 @@ namespace eb200 {
       }
       {
         PHASE(dom, EB200_PHASE_PUSH_DEPOSIT);
-        if (p.deposit_enabled && p.fuse_push_deposit) {
+        if (p.deposit_enabled && p.fuse_push_deposit && !dom.curv) {
           TRY(ParticlePushAndDeposit(dom, time));
         } else {
           TRY(ParticlePush(dom, time));
@@ -759,6 +804,9 @@ extern "C" int eb200_srpic_step(eb200_ctx_t* ctx, const eb200_srpic_params_t* pr
   dom.stream   = stream;
   dom.prof     = &eb200_ctx_engine_state(ctx)->prof;
   dom.eng      = eb200_ctx_engine_state(ctx);
+  const int metric = eb200_ctx_metric(ctx);
+  dom.curv         = metric == EB200_METRIC_SPHERICAL || metric == EB200_METRIC_QSPHERICAL;
+  if (metric != EB200_METRIC_MINKOWSKI && !dom.curv) return EB200_ERR_UNSUPPORTED; // GRPIC: eb200_grpic_step
   return eb200::srpic::step_forward(dom, step, time);
 }
 
@@ -785,6 +833,18 @@ extern "C" int eb200_srpic_set_match(eb200_ctx_t* ctx, const eb200_match_face_t*
   e->match.assign(faces, faces + nfaces);
   e->match_target = nfaces > 0 ? target : nullptr;
   e->match_mask   = components_mask;
+  return EB200_OK;
+}
+
+extern "C" int eb200_srpic_set_field_bcs(eb200_ctx_t* ctx, const eb200_field_bc_t* bcs, int n) {
+  if (!ctx || n < 0 || (n > 0 && !bcs)) return EB200_ERR_ARG;
+  for (int k = 0; k < n; ++k) {
+    if ((bcs[k].kind != EB200_FBC_MATCH && bcs[k].kind != EB200_FBC_ATMOSPHERE) || !bcs[k].target ||
+        (bcs[k].o != 0 && bcs[k].o != 1) || bcs[k].sign == 0) {
+      return EB200_ERR_ARG;
+    }
+  }
+  eb200_ctx_engine_state(ctx)->curv_bcs.assign(bcs, bcs + n);
   return EB200_OK;
 }
 

@@ -143,7 +143,17 @@ class ParamsC(C.Structure):
         ("sync_gamma_rad", C.c_float), ("compton_gamma_rad", C.c_float),
         ("fuse_push_deposit", C.c_int), ("deposit_mode", C.c_int),
         ("sort_interval", C.c_int), ("clear_interval", C.c_int),
+        ("n0", C.c_float), ("has_atmosphere", C.c_int), ("atm_g", C.c_float * 3),
+        ("atm_x_surf", C.c_float), ("atm_ds", C.c_float),
     ]
+
+
+class FieldBCC(C.Structure):
+    """eb200_field_bc_t"""
+    _fields_ = [("kind", C.c_int), ("o", C.c_int), ("sign", C.c_int),
+                ("xg_edge", C.c_float), ("ds", C.c_float), ("i_edge", C.c_int),
+                ("range_min", C.c_int * 2), ("range_max", C.c_int * 2),
+                ("target", C.c_void_p), ("mask", C.c_int)]
 
 
 

@@ -65,17 +65,24 @@ class Species:
 class Simulation:
     """One Minkowski domain: em/cur/buff fields + species on one GPU."""
 
-    def __init__(self, n, order, scales: Scales, nfilter=0, strict=False, fused=False,
+    def __init__(self, n, order, scales, nfilter=0, strict=False, fused=False,
                  deposit_mode=L.DEPOSIT_ATOMIC, fbc=None, pbc=None, sort_interval=0,
                  clear_interval=0, device=0, xmin=(0.0, 0.0, 0.0), stencil=None,
-                 fieldsolver=True, deposit=True):
+                 fieldsolver=True, deposit=True, metric=L.METRIC_MINKOWSKI, metric_params=None):
+        """`scales`: a Scales (Minkowski: derived as the reference derives them) or a dict with
+        dt, omegaB0, q0, B0, V0, n0, ppc0, correction (curvilinear: what the host passes)."""
         import torch
         self.torch = torch
         self.device = torch.device("cuda", device)
         self.dim = len(n)
-        self.ctx = L.Context(n, order=order, strict=strict, device=device, dx=scales.dx, xmin=xmin)
+        self.metric = metric
+        if metric == L.METRIC_MINKOWSKI:
+            self.ctx = L.Context(n, order=order, strict=strict, device=device, dx=scales.dx, xmin=xmin)
+        else:
+            self.ctx = L.Context(n, order=order, strict=strict, device=device, metric=metric,
+                                 metric_params=metric_params)
         self.grid = self.ctx.grid
-        self.scales = scales.derive()
+        self.scales = scales.derive() if isinstance(scales, Scales) else dict(scales)
         self.order = order
         shape6, shape3 = self.grid.shape(6), self.grid.shape(3)
         self.em = torch.zeros(shape6, dtype=torch.float32, device=self.device)
@@ -96,8 +103,10 @@ class Simulation:
         p.fuse_push_deposit = int(fused)
         p.deposit_mode = deposit_mode
         p.sort_interval, p.clear_interval = sort_interval, clear_interval
+        p.n0 = s.get("n0", 0.0)
         self.params = p
         self._species_c = None
+        self._field_bcs = None
 
     @property
     def dt(self):
@@ -116,6 +125,33 @@ class Simulation:
         self._match = (arr, target, list(faces), mask)
         self.ctx._check(self.ctx.lib.eb200_srpic_set_match(
             self.ctx.handle, arr, len(faces), target.data_ptr() if len(faces) else None, mask))
+
+    def set_gca(self, larmor_max, e_ovr_b_max):
+        self.params.gca_larmor_max, self.params.gca_e_ovr_b_max = larmor_max, e_ovr_b_max
+
+    def set_atmosphere(self, g, x_surf, ds):
+        """srpic::ParticlePush's atmosphere context (particle_pusher.h:45-80): g = (gx1, gx2, gx3)
+        with the direction's sign, the surface coordinate and grid.boundaries.atmosphere.ds"""
+        p = self.params
+        p.has_atmosphere = 1
+        p.atm_g = (C.c_float * 3)(*g)
+        p.atm_x_surf, p.atm_ds = x_surf, ds
+
+    def set_field_bcs(self, bcs):
+        """MATCH / ATMOSPHERE faces of a curvilinear domain: list of dicts with kind, o, sign,
+        target (device tensor, layout of em), mask, range_min, range_max and xg_edge, ds (MATCH) or
+        i_edge (ATMOSPHERE). Tensors are kept alive here."""
+        arr = (L.FieldBCC * max(1, len(bcs)))()
+        for k, b in enumerate(bcs):
+            arr[k].kind, arr[k].o, arr[k].sign = b["kind"], b["o"], b["sign"]
+            arr[k].xg_edge, arr[k].ds = b.get("xg_edge", 0.0), b.get("ds", 1.0)
+            arr[k].i_edge = b.get("i_edge", 0)
+            arr[k].range_min = (C.c_int * 2)(*b["range_min"])
+            arr[k].range_max = (C.c_int * 2)(*b["range_max"])
+            arr[k].target = b["target"].data_ptr()
+            arr[k].mask = b["mask"]
+        self._field_bcs = (arr, [b["target"] for b in bcs])
+        self.ctx._check(self.ctx.lib.eb200_srpic_set_field_bcs(self.ctx.handle, arr, len(bcs)))
 
     def set_ext_current(self, table):
         """The pgen's ext_current as a table of Fourier modes (eb200_ext_current_t; see
@@ -143,6 +179,8 @@ class Simulation:
                 continue
             arrays[k] = torch.zeros(maxnpart, dtype=getattr(torch, PRTL_DTYPES[k]),
                                     device=self.device)
+        if self.metric != L.METRIC_MINKOWSKI:
+            arrays["phi"] = torch.zeros(maxnpart, dtype=torch.float32, device=self.device)
         return self.add_species(mass, charge, arrays, 0, pusher, maxnpart)
 
     def _pack_species(self):

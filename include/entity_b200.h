@@ -370,13 +370,25 @@ typedef struct {
   int   deposit_mode;      /* EB200_DEPOSIT_* */
   int   sort_interval;     /* particles.spatial_sorting_interval (0: never) */
   int   clear_interval;    /* particles.clear_interval (0: never) */
+  /* curvilinear (spherical / qspherical) domains */
+  float n0;                /* scales.n0: CurrentsAmpere uses coeff = -dt q0 n0 / B0, 1 / n0 */
+  /* the atmosphere as srpic::ParticlePush hands it to the pusher (particle_pusher.h:45-80):
+   * g along the boundary's direction with its sign, the surface coordinate and
+   * grid.boundaries.atmosphere.ds; has_atmosphere = a face carries PrtlBC::ATMOSPHERE */
+  int   has_atmosphere;
+  float atm_g[3], atm_x_surf, atm_ds;
 } eb200_srpic_params_t;
 
-/* SRPICEngine::step_forward (src/engines/srpic/srpic.hpp:65-188) for one Minkowski domain:
+/* SRPICEngine::step_forward (src/engines/srpic/srpic.hpp:65-188) for one domain:
  * Faraday(1/2) -> comm B -> ParticlePush -> CurrentsDeposit -> sync J, comm J -> CurrentsFilter ->
  * [particle migration] -> Faraday(1/2) -> comm B -> Ampere -> CurrentsAmpere -> comm E|J ->
- * SortParticles. Field/particle boundary kernels other than periodic wrap, absorb and reflect
- * are outside this library. species[s].npart is updated in place. */
+ * SortParticles, with srpic::FieldBoundaries after every field exchange. Minkowski contexts:
+ * 1D / 2D / 3D, MATCH faces registered with eb200_srpic_set_match. Spherical / qspherical
+ * contexts (2D): the curvilinear dispatchers (eb200_faraday_sr, ...), AXIS faces from
+ * prm->fbc, MATCH and ATMOSPHERE faces registered with eb200_srpic_set_field_bcs, the
+ * atmosphere's gravity in the pusher; push and deposit run as two passes there. The injectors
+ * (srpic::ParticleInjector, the pgen's CustomPostStep) stay the host's. species[s].npart is
+ * updated in place. */
 int eb200_srpic_step(eb200_ctx_t* ctx, const eb200_srpic_params_t* prm, float* em, float* cur,
                      float* buff, eb200_species_t* species, int nspecies, uint32_t step,
                      double time, eb200_stream_t stream);
@@ -387,6 +399,23 @@ int eb200_srpic_step(eb200_ctx_t* ctx, const eb200_srpic_params_t* prm, float* e
  * exchange, for E after the Ampere / CurrentsAmpere exchange, and for both at step 0. `target`
  * and the face table are borrowed until the next call (nfaces = 0 clears them); faces of a
  * matched dimension carry EB200_FBC_NONE in eb200_srpic_params_t.fbc. */
+/* Functor-driven field boundaries of a curvilinear SRPIC domain inside eb200_srpic_step
+ * (srpic::MatchFieldsIn / AtmosphereFieldsIn, src/engines/srpic/fields_bcs.h:39-215, 470-600):
+ * applied in the order of dir::Directions<D>::orth (-x1, -x2, +x2, +x1) together with the AXIS
+ * faces of prm->fbc. `target` (device pointer, layout of em, contravariant components on each
+ * component's node) stands for the pgen's MatchFields / AtmFields functor and is borrowed until
+ * the next call; n = 0 clears the table. */
+typedef struct {
+  int          kind;    /* EB200_FBC_MATCH or EB200_FBC_ATMOSPHERE */
+  int          o, sign; /* face: dimension 0 / 1 and side */
+  float        xg_edge, ds;                /* MATCH: edge of the global box, layer thickness */
+  int          i_edge;                     /* ATMOSPHERE: ghost-inclusive cell index of the edge */
+  int          range_min[2], range_max[2]; /* ghost-inclusive cell range (Mesh::ExtentToRange) */
+  const float* target;
+  int          mask;                       /* components the functor defines */
+} eb200_field_bc_t;
+int eb200_srpic_set_field_bcs(eb200_ctx_t* ctx, const eb200_field_bc_t* bcs, int n);
+
 typedef struct {
   int   o;                          /* matching direction */
   float xg_edge, ds;                /* edge of the global box on that side, layer thickness */

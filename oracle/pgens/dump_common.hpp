@@ -292,8 +292,13 @@ namespace ebdump {
     const char* names[] = { "algorithms.timestep.dt", "algorithms.timestep.correction",
                             "scales.q0", "scales.B0", "scales.omegaB0", "scales.V0", "scales.n0",
                             "scales.sigma0", "scales.larmor0", "scales.skindepth0", "scales.dx0",
-                            "particles.ppc0" };
+                            "particles.ppc0", "grid.boundaries.atmosphere.g",
+                            "grid.boundaries.atmosphere.ds", "grid.boundaries.atmosphere.height",
+                            "grid.boundaries.atmosphere.temperature",
+                            "grid.boundaries.atmosphere.density", "algorithms.gca.larmor_max",
+                            "algorithms.gca.e_ovr_b_max" };
     for (const char* nm : names) {
+      if (!params.contains(nm)) continue;
       const float v = (float)params.template get<real_t>(nm);
       rec(f, nm, 0, { 1 }, &v, 4);
     }

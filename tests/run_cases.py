@@ -111,3 +111,39 @@ def gr_match_range(case, ng):
     lo = max(float(np.floor(to_cd(r_max - f32(c["match_ds"])))), 0.0)
     hi = float(np.ceil(to_cd(r_max)))
     return [int(lo) + ng, 0], [int(hi) + 2 * ng, n2 + 2 * ng]
+
+
+# ------------------------------------------------------------------ curvilinear SRPIC cases
+SPH_CASES = {
+    # pgens/magnetosphere/magnetosphere.toml at fixture size (run_inputs/magnetosphere_small.toml)
+    "magnetosphere_small": dict(n=(64, 48), metric="qspherical", extent=(1.0, 10.0), r0=0.0, h=0.0,
+                                nfilter=4, match_ds=1.0, pushers=[2 | 8, 2 | 8], cap=4096),
+}
+
+
+def sph_geometry(case, ng):
+    """The ranges srpic::MatchFieldsIn (+x1) and srpic::AtmosphereFieldsIn (-x1) hand to their
+    kernels (fields_bcs.h:39-215, 470-560) and the atmosphere's extent (utils.h:48-104) for a
+    qspherical mesh (x1 = (ln(r - r0) - chi_min) / dchi), in fp32."""
+    c = SPH_CASES[case]
+    f32 = np.float32
+    n1, n2 = c["n"]
+    r0 = f32(c["r0"])
+    r_min, r_max = f32(c["extent"][0]), f32(c["extent"][1])
+    chi_min = np.log(r_min - r0)
+    dchi = (np.log(r_max - r0) - chi_min) / f32(n1)
+    to_cd = lambda r: (np.log(f32(r) - r0) - chi_min) / dchi
+    to_ph = lambda x: r0 + np.exp(f32(x) * dchi + chi_min)
+    # MATCH: box [r_max - ds, r_max], incl_ghosts (false, true) along x1
+    lo = max(float(np.floor(to_cd(r_max - f32(c["match_ds"])))), 0.0)
+    hi = float(np.ceil(to_cd(r_max)))
+    match = dict(range_min=[int(lo) + ng, 0], range_max=[int(hi) + 2 * ng, n2 + 2 * ng],
+                 xg_edge=float(r_max))
+    # ATMOSPHERE at -x1: buffer of max(nfilter + 2, 5) cells from the inner edge
+    buf = max(c["nfilter"] + 2, 5)
+    xg_min, xg_max = to_ph(0.0), to_ph(float(buf))
+    a_lo = float(np.floor(to_cd(max(xg_min, r_min))))
+    a_hi = min(float(np.ceil(to_cd(xg_max))), float(n1))
+    rmin, rmax = [int(a_lo) + 0, 0], [int(a_hi) + ng, n2 + 2 * ng]
+    atm = dict(range_min=rmin, range_max=rmax, i_edge=rmax[0] - 1, x_surf=float(xg_max))
+    return match, atm
