@@ -265,7 +265,19 @@ def run_ours(args):
     dmode = {"atomic": eb.DEPOSIT_ATOMIC, "aggregated": eb.DEPOSIT_AGGREGATED,
              "ordered": eb.DEPOSIT_ORDERED}[args.deposit]
     turb = args.turbulence is not None
-    if turb:
+    other = args.shape  # "wald" | "magnetosphere": secondary bench lines (configs[4], configs[3])
+    if other:
+        if world > 1:
+            raise SystemExit("bench.py --shape: single-GPU lines (curvilinear multi-domain exchange is not built)")
+        args.sort_interval = 0
+        args.no_e2e = True
+        if other == "wald":
+            size = tuple(args.size) if tuple(args.size) != (4096, 2048) else (512, 512)
+            sim = workloads.wald(size, ppc=args.ppc if args.ppc != 32 else 8, device=local)
+        else:
+            size = tuple(args.size) if tuple(args.size) != (4096, 2048) else (2048, 1024)
+            sim = workloads.magnetosphere(size, ppc=args.ppc if args.ppc != 32 else 10, device=local)
+    elif turb:
         # configs[2]-shaped block (3D, T = 1 pair plasma, 3rd-order shapes, 4 filter passes) at the
         # n^3 given: a second bench line for the Esirkepov path, single GPU, not the headline
         size = (args.turbulence,) * 3
@@ -382,6 +394,8 @@ def run_ours(args):
     pd_ms, pd_calls = prof["PushDeposit"]
     per_launch_s = 1e-3 * pd_ms / max(args.steps, 1)  # one push+deposit phase per step
     b_p = 102.0 if turb else B_P_2D  # 78 B (2D), 102 B (3D) per particle-step
+    if other:
+        b_p = 86.0  # 2D + phi carried (read 4 + write 4)
     achieved = n_pushed * b_p / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
     with_sort_s = per_launch_s + 1e-3 * timing["sort_charge_ms_per_step"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -394,7 +408,11 @@ def run_ours(args):
     if os.path.exists(tr):
         with open(tr) as f:
             roofline["traffic"] = json.load(f).get(
+                f"{other}_push_deposit_bytes_per_launch" if other else
                 "turbulence_push_deposit_bytes_per_launch" if turb else "push_deposit_bytes_per_launch")
+    if other:
+        roofline["note"] = ("two passes (push, deposit), ALU bound: the metric's transcendental functions "
+                            "per particle (x pusher_niter for GRPIC), see DESIGN.md")
 
     # end to end through the host-buffer C-ABI entry (pinned host state, H2D + D2H per step)
     e2e = None
@@ -417,13 +435,13 @@ def run_ours(args):
         del hs
 
     cpu = gpu_ref = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not other:
         # the reference's Kokkos-OpenMP entity.xc on all host cores, its own timers
         cpu, why = entity_xc_sample("omp", REF_CUT, args.cpu_steps + 10, 10)
         if cpu is None:
             _, cpu, _ = reference_sample(args.cpu_steps, 1)
             cpu["note"] = f"entity.xc unavailable ({why}); oracle/_ref kernels with a std::thread driver"
-    if rank == 0 and world == 1 and not args.no_gpu_ref and not turb:
+    if rank == 0 and world == 1 and not args.no_gpu_ref and not turb and not other:
         # the reference's own sm_100 build (Kokkos-CUDA, Kokkos_ARCH_BLACKWELL100) on this GPU,
         # full-size reconnection.toml at 32 ppc: "the existing Blackwell kernel" 
         del sim
@@ -438,7 +456,11 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "timing": timing,
             "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"turbulence-shaped 3D Cartesian SR pair plasma, {size[0]}^3 cells, "
+            "config": {"workload": (f"wald-with-species: 2D GRPIC qkerr_schild a=0.95, {size[0]}x{size[1]} cells, two Boris species in r in [2, 8], pusher_niter=10"
+                                    if other == "wald" else
+                                    f"magnetosphere: 2D qspherical SRPIC dipole, {size[0]}x{size[1]} cells, Boris+GCA, atmosphere gravity, ATMOSPHERE/MATCH/AXIS field boundaries"
+                                    if other == "magnetosphere" else
+                                    f"turbulence-shaped 3D Cartesian SR pair plasma, {size[0]}^3 cells, "
                                     f"{16 if args.ppc == 32 else args.ppc} ppc, 3rd-order shapes (reduced from 1024^3)"
                                     if turb else
                                     WORKLOAD if size == (4096, 2048) and args.ppc == 32 else
@@ -446,11 +468,15 @@ def run_ours(args):
                        + (" [x2 walls: fields MATCH ds=20, particles ABSORB, no injector]"
                           if args.walls else ""),
                        "cells_per_gpu": list(size),
-                       "ppc0": (16 if args.ppc == 32 else args.ppc) if turb else args.ppc,
+                       "ppc0": ((8 if args.ppc == 32 else args.ppc) if other == "wald" else
+                                (10 if args.ppc == 32 else args.ppc) if other == "magnetosphere" else
+                                (16 if args.ppc == 32 else args.ppc) if turb else args.ppc),
                        "shape_order": 3 if turb else 0,
-                       "current_filters": 4 if turb else args.filters, "particles_per_gpu": n_pushed0,
-                       "fused_push_deposit": not args.unfused, "sort_interval": args.sort_interval,
-                       "deposit": args.deposit,
+                       "current_filters": 4 if (turb or other) else args.filters,
+                       "particles_per_gpu": n_pushed0,
+                       "fused_push_deposit": (not args.unfused) and not other,
+                       "sort_interval": args.sort_interval,
+                       "deposit": "atomic" if other else args.deposit,
                        "parallelism": (f"domain decomposition {'x'.join(str(n_) for n_ in decomposition)}, "
                                        f"one block per GPU, NCCL halo + particle exchange")
                        if world > 1 else "single domain",
@@ -499,6 +525,9 @@ def main():
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--turbulence", type=int, default=None, metavar="N",
                     help="bench the turbulence-shaped 3D block (N^3 cells, 16 ppc, O=3) instead")
+    ap.add_argument("--shape", default=None, choices=["wald", "magnetosphere"],
+                    help="secondary bench lines: the GRPIC step (configs[4] with species) or the "
+                         "curvilinear SRPIC step (configs[3]) instead of the reconnection headline")
     ap.add_argument("--walls", action="store_true",
                     help="x2 boundaries of reconnection.toml (fields MATCH, particles ABSORB) instead "
                          "of the periodic core; single GPU, no replenishing injector")

@@ -187,3 +187,151 @@ def turbulence(n=(128, 128, 128), ppc0=16, order=3, nfilter=4, seed=0x9abc, capa
         _maxwellian(sim, arr, per, gen, 1.0)
         sim.add_species(1.0, charge, arr, per)
     return sim
+
+
+# --------------------------------------------------------------- curvilinear / GR shapes
+def _node_metric(metric, n, mp, ng):
+    """metric quantities (lib.metric_eval) on the four staggerings of the ghost-inclusive 2D
+    mesh: dict key (s1, s2) in {0, 1}^2 -> array [N2, N1, nq]; host setup code, like the
+    reference's pgens evaluate the metric when they fill the initial fields"""
+    import numpy as np
+    N1, N2 = n[0] + 2 * ng, n[1] + 2 * ng
+    i = np.arange(N1, dtype=np.float32) - ng
+    j = np.arange(N2, dtype=np.float32) - ng
+    out = {}
+    for s1 in (0, 1):
+        for s2 in (0, 1):
+            x1, x2 = np.meshgrid(i + 0.5 * s1, j + 0.5 * s2)
+            # keep the query inside the coordinate range of the metric (ghost rows beyond the axis
+            # mirror the first interior row)
+            x2c = np.clip(x2, 0.0, float(n[1]))
+            q = L.metric_eval(metric, n, mp, x1.ravel(), x2c.ravel())
+            out[(s1, s2)] = q.reshape(N2, N1, -1)
+    return out
+
+
+def _cell_particles(sim_like, torch, device, cap, i_lo, i_hi, n2, per_cell, gen, temperature, phi=True):
+    """per_cell particles in every cell of [i_lo, i_hi) x [0, n2), cell-sorted (i1 fastest)"""
+    ncell = (i_hi - i_lo) * n2
+    n = ncell * per_cell
+    arrays = {}
+    for k, dt in PRTL_DTYPES.items():
+        axis = [c for c in k if c in "123"]
+        if k.startswith(("i", "dx")) and axis and int(axis[0]) > 2:
+            continue
+        arrays[k] = torch.zeros(cap, dtype=getattr(torch, dt), device=device)
+    if phi:
+        arrays["phi"] = torch.zeros(cap, dtype=torch.float32, device=device)
+    cell = torch.arange(n, device=device, dtype=torch.int64) // per_cell
+    arrays["i1"][:n] = (i_lo + cell % (i_hi - i_lo)).to(torch.int32)
+    arrays["i2"][:n] = (cell // (i_hi - i_lo)).to(torch.int32)
+    for a in ("dx1", "dx2"):
+        arrays[a][:n] = torch.rand(n, device=device, generator=gen).clamp_(max=0.99999994)
+    for a in ("ux1", "ux2", "ux3"):
+        arrays[a][:n] = torch.randn(n, device=device, generator=gen) * math.sqrt(temperature)
+    arrays["weight"][:n] = 1.0
+    arrays["tag"][:n] = 1
+    for a in ("i1", "i2", "dx1", "dx2"):
+        arrays[a + "_prev"][:n] = arrays[a][:n]
+    return arrays, n
+
+
+def wald(n=(512, 512), ppc=8, niter=10, seed=0x77, metric=L.METRIC_QKERR_SCHILD, spin=0.95,
+         extent=(1.0, 10.0), nfilter=4, device=0):
+    """configs[4]: pgens/wald (2D GR, qkerr_schild a = 0.95, 512 x 512) with two Boris species
+    loaded uniformly in r in [2, 8] (the reference's wald.toml is a vacuum setup; species as in
+    pgens/accretion/accretion.toml:43-55), pusher_niter = 10. Synthetic fields: the
+    flat-space limit of a uniform vertical field in the orthonormal frame, no E."""
+    import numpy as np
+    import torch
+    from .grpic import GRSimulation
+    mp = [extent[0], extent[1], 0.0, float(np.float32(np.pi)), 0.0, 0.0, spin]
+    # scales of wald.toml: larmor0 = 0.0025, skindepth0 = 0.05; dt = CFL dx0 with dx0 ~ the
+    # smallest proper cell size (near the horizon)
+    ng = 2
+    q = _node_metric(metric, n, mp, ng)
+    h11, h22 = q[(0, 0)][ng:-ng, ng:-ng, 0], q[(0, 0)][ng:-ng, ng:-ng, 1]
+    dx0 = float(min(np.sqrt(h11).min(), np.sqrt(h22).min()))
+    dt = 0.5 * dx0 / math.sqrt(2.0)
+    larmor0, skin0 = 0.0025, 0.05
+    V0 = float(q[(1, 1)][ng + n[1] // 2, ng + n[0] // 2, 10])  # sqrt_det_h at the mesh centre
+    sim = GRSimulation(n, metric, mp, dt=dt, omegaB0=1.0 / larmor0, q0=V0 / (2 * ppc * skin0 ** 2),
+                       B0=1.0 / larmor0, nfilter=nfilter, pusher_niter=niter, pusher_eps=1e-2,
+                       deposit_mode=L.DEPOSIT_ATOMIC, device=device)
+    # B^r = cos(theta) / sqrt(h_11) on (i, j + 1/2); B^theta = -sin(theta) / sqrt(h_22) on (i + 1/2, j)
+    th01, th10 = q[(0, 1)][:, :, 25], q[(1, 0)][:, :, 25]
+    b1 = np.cos(th01) / np.sqrt(q[(0, 1)][:, :, 0])
+    b2 = -np.sin(th10) / np.sqrt(q[(1, 0)][:, :, 1])
+    for f in (sim.em, sim.em0):
+        f[3] = torch.from_numpy(np.nan_to_num(b1).astype(np.float32)).to(sim.device)
+        f[4] = torch.from_numpy(np.nan_to_num(b2).astype(np.float32)).to(sim.device)
+    # MATCH layer at the outer edge towards the initial field, 1 r_g thick
+    tgt = sim.em.clone()
+    chi_min = math.log(extent[0])
+    dchi = (math.log(extent[1]) - chi_min) / n[0]
+    lo = int(math.floor((math.log(extent[1] - 1.0) - chi_min) / dchi))
+    sim.set_match(tgt, 0b111000, extent[1], 1.0, [lo + ng, 0], [n[0] + 2 * ng, n[1] + 2 * ng])
+    gen = torch.Generator(device=sim.device)
+    gen.manual_seed(seed)
+    i_lo = int(math.ceil((math.log(2.0) - chi_min) / dchi))
+    i_hi = int(math.floor((math.log(8.0) - chi_min) / dchi))
+    for charge in (-1.0, 1.0):
+        cap = (i_hi - i_lo) * n[1] * ppc
+        arrays, npart = _cell_particles(sim, torch, sim.device, cap, i_lo, i_hi, n[1], ppc, gen, 0.01)
+        sp = sim.alloc_species(1.0, charge, cap)
+        sp.arrays, sp.npart = arrays, npart
+    sim._species_c = None
+    return sim
+
+
+def magnetosphere(n=(2048, 1024), ppc=10, seed=0x88, extent=(1.0, 50.0), nfilter=4, device=0):
+    """configs[3]: pgens/magnetosphere/magnetosphere.toml (2D qspherical SR, 2048 x 1024): a
+    dipole, ATMOSPHERE / MATCH / AXIS field boundaries, Boris + GCA pusher with the atmosphere's
+    gravity, weighted particles. The injector is the host's: the synthetic state carries `ppc`
+    pairs per cell throughout the domain instead of the atmosphere's outflow."""
+    import numpy as np
+    import torch
+    metric = L.METRIC_QSPHERICAL
+    mp = [extent[0], extent[1], 0.0, float(np.float32(np.pi)), 0.0, 0.0, 0.0]
+    ng = 2
+    q = _node_metric(metric, n, mp, ng)
+    sh11, sh22 = q[(0, 0)][ng:-ng, ng:-ng, 3], q[(0, 0)][ng:-ng, ng:-ng, 4]
+    dx0 = float(min(sh11.min(), sh22.min()))
+    dt = 0.5 * dx0 / math.sqrt(2.0)
+    larmor0, skin0 = 2e-5, 0.01
+    V0 = float(q[(1, 1)][ng + n[1] // 2, ng + n[0] // 2, 6])
+    scales = dict(dt=dt, omegaB0=1.0 / larmor0, q0=V0 / (ppc * skin0 ** 2), B0=1.0 / larmor0, V0=V0,
+                  n0=ppc / V0, ppc0=float(ppc), correction=1.0)
+    fbc = [L.FBC_ATMOSPHERE, L.FBC_MATCH, L.FBC_AXIS, L.FBC_AXIS, 0, 0]
+    pbc = [L.PBC_ABSORB, L.PBC_ABSORB, L.PBC_AXIS, L.PBC_AXIS, 0, 0]
+    sim = Simulation(n, 0, scales, nfilter=nfilter, fused=False, deposit_mode=L.DEPOSIT_ATOMIC,
+                     fbc=fbc, pbc=pbc, metric=metric, metric_params=mp, device=device)
+    # dipole (pgen.hpp:40-57): B^r = cos(theta) / r^3, B^theta = sin(theta) / (2 r^3) in the
+    # orthonormal frame; contravariant = / sqrt(h_ii)
+    r01, th01 = q[(0, 1)][:, :, 8], q[(0, 1)][:, :, 9]
+    r10, th10 = q[(1, 0)][:, :, 8], q[(1, 0)][:, :, 9]
+    b1 = np.cos(th01) / r01 ** 3 / q[(0, 1)][:, :, 3]
+    b2 = 0.5 * np.sin(th10) / r10 ** 3 / q[(1, 0)][:, :, 4]
+    sim.em[3] = torch.from_numpy(np.nan_to_num(b1).astype(np.float32)).to(sim.device)
+    sim.em[4] = torch.from_numpy(np.nan_to_num(b2).astype(np.float32)).to(sim.device)
+    tgt = sim.em.clone()
+    chi_min = math.log(extent[0])
+    dchi = (math.log(extent[1]) - chi_min) / n[0]
+    lo = int(math.floor((math.log(extent[1] - 1.0) - chi_min) / dchi))
+    buf = max(nfilter + 2, 5)
+    sim.set_field_bcs([
+        dict(kind=L.FBC_ATMOSPHERE, o=0, sign=-1, target=tgt, mask=63, range_min=[0, 0],
+             range_max=[buf + ng, n[1] + 2 * ng], i_edge=buf + ng - 1),
+        dict(kind=L.FBC_MATCH, o=0, sign=+1, target=tgt, mask=0b011000, range_min=[lo + ng, 0],
+             range_max=[n[0] + 2 * ng, n[1] + 2 * ng], xg_edge=extent[1], ds=1.0),
+    ])
+    sim.set_gca(1.0, 0.9)
+    sim.set_atmosphere((-5.0, 0.0, 0.0), extent[0] * math.exp(buf * dchi), 2.0)
+    gen = torch.Generator(device=sim.device)
+    gen.manual_seed(seed)
+    per = max(1, ppc // 2)
+    for charge in (-1.0, 1.0):
+        cap = n[0] * n[1] * per
+        arrays, npart = _cell_particles(sim, torch, sim.device, cap, 0, n[0], n[1], per, gen, 0.1)
+        sim.add_species(1.0, charge, arrays, npart, L.PUSHER_BORIS | L.PUSHER_GCA, cap)
+    return sim

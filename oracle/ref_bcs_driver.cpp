@@ -134,7 +134,45 @@ namespace {
   }
 } // namespace
 
+namespace {
+  // kernel::bc::ConductorBoundaries_kernel<Dim::_2D, o, P> over the range
+  // srpic::PerfectConductorFieldsIn builds (src/engines/srpic/fields_bcs.h:384-470)
+  template <in O, bool P>
+  void conductor_run(const orc_grid_t* g, float* em, int tags) {
+    auto           fld = wrap6<Dim::_2D>(g, em);
+    const int      o   = (O == in::x1) ? 0 : 1;
+    const ncells_t G   = (ncells_t)g->ng;
+    const ncells_t i_edge = P ? (G + (ncells_t)g->n[o]) : G; // i_max / i_min
+    kernel::bc::ConductorBoundaries_kernel<Dim::_2D, O, P> k(fld, i_edge, (BCTags)tags);
+    ncells_t lo[2] = { 0, 0 }, hi[2] = { (ncells_t)g->n[0] + 2 * G, (ncells_t)g->n[1] + 2 * G };
+    hi[o] = P ? G : G + 1;
+    for (ncells_t i = lo[0]; i < hi[0]; ++i)
+      for (ncells_t j = lo[1]; j < hi[1]; ++j) k(i, j);
+  }
+
+  // kernel::bc::AxisBoundaries_kernel<Dim::_2D, P> over n_all(x1) (fields_bcs.h:205-232)
+  template <bool P>
+  void axis_run(const orc_grid_t* g, float* em, int tags) {
+    auto           fld = wrap6<Dim::_2D>(g, em);
+    const ncells_t G   = (ncells_t)g->ng;
+    const ncells_t i_edge = P ? (G + (ncells_t)g->n[1]) : G;
+    kernel::bc::AxisBoundaries_kernel<Dim::_2D, P> k(fld, i_edge, (BCTags)tags);
+    for (ncells_t i = 0; i < (ncells_t)g->n[0] + 2 * G; ++i) k(i);
+  }
+} // namespace
+
 extern "C" {
+void ref_conductor_fields(const orc_grid_t* g, float* em, int o, int sign, int tags) {
+  if (g->dim != 2) throw std::runtime_error("ref conductor: 2D only");
+  if (o == 0) {
+    if (sign > 0) conductor_run<in::x1, true>(g, em, tags); else conductor_run<in::x1, false>(g, em, tags);
+  } else {
+    if (sign > 0) conductor_run<in::x2, true>(g, em, tags); else conductor_run<in::x2, false>(g, em, tags);
+  }
+}
+void ref_axis_fields(const orc_grid_t* g, float* em, int sign, int tags) {
+  if (sign > 0) axis_run<true>(g, em, tags); else axis_run<false>(g, em, tags);
+}
 int ref_bc_tag_e() { return (int)BC::E; }
 int ref_bc_tag_b() { return (int)BC::B; }
 void ref_match_fields(const orc_grid_t* g, float* em, const float* coef, int b_only, float dx,
