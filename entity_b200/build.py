@@ -32,6 +32,7 @@ UNITS = [
     ("sort.cu", "one", []),
     ("stats.cu", "one", ["--fmad=false"]),
     ("bcs.cu", "one", ["--fmad=false"]),
+    ("output.cu", "one", ["--fmad=false"]),
     ("comm.cu", "one", []),
     ("engine.cu", "one", []),
     ("capi.cu", "one", []),

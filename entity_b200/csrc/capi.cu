@@ -949,6 +949,48 @@ int eb200_conductor_fields(eb200_ctx_t* ctx, float* em, int o, int sign, int tag
                     "conductor_fields");
 }
 
+/* ------------------------------------------------------------------ output staging */
+int eb200_fields_to_phys(eb200_ctx_t* ctx, const float* from, int ncomp_from, float* to,
+                         int ncomp_to, const int* cf, const int* ct, int interp, int convert,
+                         eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, from && to && cf && ct, "null argument");
+  REQUIRE(ctx, ncomp_from >= 3 && ncomp_to >= 3, "FieldsToPhys_kernel: at least 3 components");
+  for (int c = 0; c < 3; ++c) {
+    REQUIRE(ctx, cf[c] >= 0 && cf[c] < ncomp_from && ct[c] >= 0 && ct[c] < ncomp_to,
+            "FieldsToPhys_kernel: Invalid component index");
+  }
+  REQUIRE(ctx, interp >= 0 && interp <= 2 && convert >= 0 && convert <= 3, "bad flags");
+  const bool mink = ctx->cfg.metric == EB200_METRIC_MINKOWSKI;
+  return check_cuda(ctx,
+                    eb200::fields_to_phys(mink ? nullptr : &ctx->metric, ctx->cfg.grid,
+                                          ctx->cfg.metric_params[0], from, ncomp_from, to, ncomp_to,
+                                          cf, ct, interp, convert, (cudaStream_t)stream),
+                    "fields_to_phys");
+}
+
+int eb200_prtls_to_phys(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart,
+                        uint32_t stride, float* x1, float* x2, float* x3, float* u1, float* u2,
+                        float* u3, float* weight, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, stride >= 1, "stride must be >= 1");
+  int rc = check_prtls(ctx, prtls, npart);
+  if (rc) return rc;
+  const bool mink = ctx->cfg.metric == EB200_METRIC_MINKOWSKI;
+  const int  dim  = ctx->cfg.grid.dim;
+  REQUIRE(ctx, x1 && u1 && u2 && u3 && weight, "Invalid buffer size");
+  REQUIRE(ctx, dim < 2 || x2, "Invalid buffer size");
+  REQUIRE(ctx, !((dim == 2 && !mink) || dim == 3) || x3, "Invalid buffer size");
+  REQUIRE(ctx, mink || prtls->phi != nullptr, "phi is required on curvilinear meshes");
+  const uint32_t nout = (npart + stride - 1) / stride;
+  return check_cuda(ctx,
+                    eb200::prtls_to_phys(mink ? nullptr : &ctx->metric, ctx->cfg.grid,
+                                         ctx->cfg.metric_params[0], ctx->cfg.metric_params + 1, *prtls,
+                                         stride, nout, x1, x2, x3, u1, u2, u3, weight,
+                                         (cudaStream_t)stream),
+                    "prtls_to_phys");
+}
+
 int eb200_time_average(eb200_ctx_t* ctx, float* a, const float* b, int ncomp,
                        eb200_stream_t stream) {
   ENTER(ctx);

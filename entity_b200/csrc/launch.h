@@ -97,11 +97,20 @@ namespace eb200 {
   EB200_DECLARE_VARIANT(strict_fp)
   EB200_DECLARE_VARIANT(fast_fp)
 
+  // output staging (output.cu)
+  struct MetricParams;
+  cudaError_t fields_to_phys(const MetricParams* mp, const eb200_grid_t& g, float dx,
+                             const float* from, int ncomp_from, float* to, int ncomp_to,
+                             const int* cf, const int* ct, int interp, int conv, cudaStream_t st);
+  cudaError_t prtls_to_phys(const MetricParams* mp, const eb200_grid_t& g, float dx,
+                            const float* xmin, const eb200_prtls_t& S, uint32_t stride,
+                            uint32_t nout, float* x1, float* x2, float* x3, float* u1, float* u2,
+                            float* u3, float* w, cudaStream_t st);
+
   cudaError_t conductor_fields2d(const eb200_grid_t& g, float* em, int o, bool pos, int tags,
                                  cudaStream_t st);
 
   // curvilinear SR and GR kernels: curv.cu (one build, IEEE division, no FMA contraction)
-  struct MetricParams;
   namespace curv {
     // field boundaries (bcs.cu)
     cudaError_t axis_fields(const eb200_grid_t& g, float* fld, bool pos, int tags, cudaStream_t st);

@@ -603,6 +603,26 @@ int eb200_grpic_step(eb200_ctx_t* ctx, const eb200_grpic_params_t* prm, float** 
                      const float* match_target, eb200_species_t* species, int nspecies,
                      uint32_t step, double time, eb200_stream_t stream);
 
+/* ------------------------------------------------ output staging */
+/* kernel::FieldsToPhys_kernel<M, N1, N2> over Mesh::rangeActiveCells (src/kernels/
+ * fields_to_phys.hpp:33-239; what the writer launches per output field, src/output/
+ * fields.cpp): three components comps_from[3] of `from` (ncomp_from planes) are interpolated to
+ * the cell centre and / or converted to another basis and stored in components comps_to[3] of
+ * `to`. interp: 0 none, 1 InterpToCellCenterFromEdges (E, D, J), 2 ...FromFaces (B, H);
+ * convert: 0 none, 1 ConvertToHat (U -> T), 2 ConvertToPhysCntrv (U -> PU), 3 ConvertToPhysCov
+ * (D -> PD). Any metric of the context; 1D / 2D / 3D for Minkowski. */
+int eb200_fields_to_phys(eb200_ctx_t* ctx, const float* from, int ncomp_from, float* to,
+                         int ncomp_to, const int* comps_from, const int* comps_to, int interp,
+                         int convert, eb200_stream_t stream);
+/* kernel::PrtlToPhys_kernel<S, M, false> (src/kernels/prtls_to_phys.hpp:30-218): every stride-th
+ * particle (nout = ceil(npart / stride) samples) -> physical coordinates (x3 = phi on 2D
+ * curvilinear meshes; unused buffers may be NULL), velocities in the orthonormal frame (SRPIC)
+ * or physical covariant components (GRPIC), and the weight. Payload columns are plain strided
+ * copies and stay with the host's writer. */
+int eb200_prtls_to_phys(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart,
+                        uint32_t stride, float* x1, float* x2, float* x3, float* u1, float* u2,
+                        float* u3, float* weight, eb200_stream_t stream);
+
 /* Host-side evaluation of the metric functions the kernels use (same source, compiled for the
  * host): what the reference's setup code gets from metric.h_<i,j>() etc. (src/metrics/*.h).
  * n_active[2], metric_params[8] as in eb200_config_t. out[nq][16] for the SR metrics:
