@@ -12,4 +12,6 @@ from .lib import (  # noqa: F401
     PBC_NONE, PBC_PERIODIC, PBC_ABSORB, PBC_REFLECT, PBC_AXIS,
     FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC,
     DEPOSIT_ATOMIC, DEPOSIT_ORDERED, DEPOSIT_AGGREGATED, EB200Error,
+    STATS_NPART, STATS_N, STATS_RHO, STATS_CHARGE, STATS_T,
+    SDIST_UNIFORM, SDIST_TABLE, SDIST_REPLENISH,
 )

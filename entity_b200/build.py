@@ -33,6 +33,7 @@ UNITS = [
     ("stats.cu", "one", ["--fmad=false"]),
     ("bcs.cu", "one", ["--fmad=false"]),
     ("output.cu", "one", ["--fmad=false"]),
+    ("inject.cu", "one", ["--fmad=false"]),
     ("comm.cu", "one", []),
     ("engine.cu", "one", []),
     ("capi.cu", "one", []),

@@ -949,6 +949,80 @@ int eb200_conductor_fields(eb200_ctx_t* ctx, float* em, int o, int sign, int tag
                     "conductor_fields");
 }
 
+/* ------------------------------------------------ injection and particle moments */
+int eb200_inject_nonuniform(eb200_ctx_t* ctx, eb200_species_t* sp1, eb200_species_t* sp2, float ppc,
+                            const eb200_spatial_dist_t* sd, const eb200_maxwellian_t* ed1,
+                            const eb200_maxwellian_t* ed2, const int* rmin, const int* rmax,
+                            uint64_t seed, uint32_t step, uint32_t call, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, sp1 && sp2 && sd && ed1 && ed2 && rmin && rmax, "null argument");
+  REQUIRE_MINK(ctx, "eb200_inject_nonuniform");
+  REQUIRE(ctx, ppc >= 0.0f, "ppc < 0");
+  REQUIRE(ctx, ed1->temperature >= 0.0f && ed2->temperature >= 0.0f,
+          "Maxwellian: Temperature must be non-negative");
+  REQUIRE(ctx, sd->kind == EB200_SDIST_UNIFORM || sd->kind == EB200_SDIST_TABLE ||
+                 sd->kind == EB200_SDIST_REPLENISH, "unknown spatial distribution");
+  REQUIRE(ctx, sd->kind == EB200_SDIST_UNIFORM || (sd->field != nullptr && sd->comp >= 0),
+          "spatial distribution: null field");
+  const eb200_grid_t& g = ctx->cfg.grid;
+  for (int a = 0; a < g.dim; ++a) {
+    REQUIRE(ctx, rmin[a] >= 0 && rmax[a] <= g.n[a] + 2 * g.ng, "inject: range outside the array");
+  }
+  int rc = check_prtls(ctx, &sp1->arrays, sp1->npart);
+  if (rc) return rc;
+  rc = check_prtls(ctx, &sp2->arrays, sp2->npart);
+  if (rc) return rc;
+  size_t plane = 1;
+  for (int a = 0; a < g.dim; ++a) plane *= (size_t)(g.n[a] + 2 * g.ng);
+  const float* field = sd->field ? sd->field + (size_t)sd->comp * plane : nullptr;
+  uint32_t     n_inj = 0;
+  int          overflow = 0;
+  rc = check_cuda(ctx,
+                  eb200::inject_nonuniform(g, sp1->arrays, sp1->npart, sp1->maxnpart, sp2->arrays,
+                                           sp2->npart, sp2->maxnpart, ppc, sd->kind, field,
+                                           sd->target_density, *ed1, *ed2, rmin, rmax, seed, step,
+                                           call, &n_inj, &overflow, ctx->scratch, (cudaStream_t)stream),
+                  "inject_nonuniform");
+  if (rc) return rc;
+  if (overflow) return fail(ctx, EB200_ERR_CAPACITY, "inject: npart + injected > maxnpart");
+  sp1->npart += n_inj;
+  sp2->npart += n_inj;
+  return EB200_OK;
+}
+
+int eb200_particle_moment(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, float mass,
+                          float charge, int use_weights, int what, float inv_n0, float* buff,
+                          int ncomp, int comp, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE_MINK(ctx, "eb200_particle_moment");
+  REQUIRE(ctx, buff != nullptr && comp >= 0 && comp < ncomp, "Invalid buffer index");
+  REQUIRE(ctx, what == EB200_STATS_N || what == EB200_STATS_RHO || what == EB200_STATS_CHARGE ||
+                 what == EB200_STATS_NPART, "eb200_particle_moment: N, Rho, Charge or Nppc");
+  REQUIRE(ctx, !((what == EB200_STATS_RHO || what == EB200_STATS_CHARGE) && mass == 0.0f),
+          "Rho & Charge for massless particles not defined");
+  int rc = check_prtls(ctx, prtls, npart);
+  if (rc) return rc;
+  const eb200_grid_t& g  = ctx->cfg.grid;
+  const float         dx = ctx->cfg.metric_params[0];
+  float               sqrt_det_h = 1.0f; // minkowski.h: dx^D
+  size_t              plane      = 1;
+  for (int a = 0; a < g.dim; ++a) {
+    sqrt_det_h *= dx;
+    plane *= (size_t)(g.n[a] + 2 * g.ng);
+  }
+  float coeff = (what == EB200_STATS_RHO) ? mass : ((what == EB200_STATS_CHARGE) ? charge : 1.0f);
+  bool  uw    = use_weights != 0;
+  if (what != EB200_STATS_NPART) {
+    coeff *= inv_n0 / sqrt_det_h;
+  } else {
+    uw = false; // Nppc: no volume, weights or smoothing (particle_moments.hpp:306-309)
+  }
+  return check_cuda(ctx,
+                    eb200::particle_moment(g, *prtls, npart, coeff, uw, buff + (size_t)comp * plane,
+                                           (cudaStream_t)stream),
+                    "particle_moment");
+}
+
 /* ------------------------------------------------------------------ output staging */
 int eb200_fields_to_phys(eb200_ctx_t* ctx, const float* from, int ncomp_from, float* to,
                          int ncomp_to, const int* cf, const int* ct, int interp, int convert,

@@ -1,0 +1,336 @@
+// entity_b200 -- particle injection and per-cell particle moments.
+//
+//  * eb200_inject_nonuniform = arch::InjectNonUniform (src/archetypes/particle_injector.h:
+//    296-387) with kernel::NonUniformInjector_kernel (src/kernels/injectors.hpp:526-859): in
+//    every cell of a range, ppc = ppc0 * spatial_dist(cell centre) pairs (stochastic rounding of
+//    the fraction), each pair at one uniformly drawn position of the cell, velocities drawn
+//    independently for the two species from their energy distributions, weight from the
+//    spatial distribution (x sqrt_det_h / V0 on curvilinear meshes). It covers the archetypes'
+//    uniform injector too (spatial_dist = 1: InjectUniform draws the same expected number).
+//  * spatial distributions that cannot cross a C ABI as functors arrive as a per-cell table;
+//    arch::spatial_dist::ReplenishUniform (spatial_dist.h:87-125) is built in: it reads the
+//    density moment this file also computes.
+//  * energy distributions: arch::energy_dist::Maxwellian (energy_dist.h:77-290): Box-Muller
+//    below T = 1/2, Sobol's method above, drift by the flipping method.
+//  * eb200_particle_moment = arch::ComputeMomentWithSpecies / kernel::ParticleMoments_kernel
+//    (src/kernels/particle_moments.hpp:37-419) for N, Rho, Charge and Nppc on Minkowski
+//    meshes, smoothing order 0 (the archetypes' default).
+//
+// RNG: the reference draws from a Kokkos random pool (one XorShift stream per thread, so the
+// particles differ between backends and thread counts). Here every cell owns a counter-based
+// Philox4x32-10 stream keyed by (seed, step, call id, cell): the injected particles are a pure
+// function of the inputs -- same on any GPU, any launch shape -- and land in the arrays in
+// cell order (the reference's atomic slot counter makes the order non-deterministic).
+#include "common.cuh"
+#include "launch.h"
+
+#include <cub/device/device_scan.cuh>
+
+namespace eb200 {
+  namespace {
+    struct Philox {
+      uint32_t key[2], ctr[4], out[4];
+      int      have;
+
+      __device__ Philox(uint64_t seed, uint32_t step, uint32_t call, uint32_t cell) {
+        key[0] = (uint32_t)seed;
+        key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = 0, ctr[1] = cell, ctr[2] = call, ctr[3] = step;
+        have   = 0;
+      }
+
+      __device__ void round(uint32_t (&c)[4], const uint32_t (&k)[2]) const {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
+        c[0] = n0, c[1] = lo1, c[2] = n2, c[3] = lo0;
+      }
+
+      __device__ uint32_t next() {
+        if (have == 0) {
+          uint32_t c[4] = { ctr[0], ctr[1], ctr[2], ctr[3] };
+          uint32_t k[2] = { key[0], key[1] };
+#pragma unroll
+          for (int r = 0; r < 10; ++r) {
+            round(c, k);
+            k[0] += 0x9E3779B9u;
+            k[1] += 0xBB67AE85u;
+          }
+          out[0] = c[0], out[1] = c[1], out[2] = c[2], out[3] = c[3];
+          ++ctr[0];
+          have = 4;
+        }
+        return out[--have];
+      }
+
+      // Random<real_t>: uniform in [0, 1)
+      __device__ float uniform() { return (float)(next() >> 8) * 5.9604645e-08f; }
+    };
+
+    struct Maxwell {
+      float temperature;
+      float drift_4vel, drift_3vel, dir[3];
+      int   drift_dir; // 0 none, +-1..3 principal axes, 4 arbitrary (energy_dist.h:199-222)
+    };
+
+    // JuttnerSinge (energy_dist.h:77-131)
+    __device__ void juttner_synge(Philox& g, float temp, float* v) {
+      if (temp < 0.5f) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float x1 = g.uniform();
+          while (fabsf(x1) <= 1.1920929e-07f) x1 = g.uniform();
+          x1             = sqrtf(-TWO * logf(x1));
+          const float x2 = 6.2831855f * g.uniform();
+          v[c]           = x1 * cosf(x2) * sqrtf(temp);
+        }
+      } else {
+        float randu = ONE, randeta = g.uniform(), x1, x2;
+        while (SQR(randeta) <= SQR(randu) + ONE) {
+          x1 = g.uniform() * g.uniform() * g.uniform();
+          while (fabsf(x1) <= 1.1920929e-07f) x1 = g.uniform() * g.uniform() * g.uniform();
+          randu = -temp * logf(x1);
+          x2    = g.uniform();
+          while (fabsf(x2) <= 1.1920929e-07f) x2 = g.uniform();
+          randeta = -temp * logf(x1 * x2);
+        }
+        x1   = g.uniform();
+        x2   = g.uniform();
+        v[0] = randu * (TWO * x1 - ONE);
+        v[2] = TWO * randu * sqrtf(x1 * (ONE - x1));
+        v[1] = v[2] * cosf(6.2831855f * x2);
+        v[2] = v[2] * sinf(6.2831855f * x2);
+      }
+    }
+
+    // Maxwellian::operator() (energy_dist.h:223-268), Cartesian drift included
+    __device__ void sample(Philox& g, const Maxwell& m, float* v) {
+      if (fabsf(m.temperature) <= 1.1920929e-07f) {
+        v[0] = v[1] = v[2] = ZERO;
+      } else {
+        juttner_synge(g, m.temperature, v);
+      }
+      if (m.drift_dir != 0) {
+        const float gamma = sqrtf(ONE + SQR(v[0]) + SQR(v[1]) + SQR(v[2]));
+        if (-m.drift_3vel * v[0] > gamma * g.uniform()) v[0] = -v[0];
+        v[0] = sqrtf(ONE + SQR(m.drift_4vel)) * (v[0] + m.drift_3vel * gamma);
+        const int d = m.drift_dir;
+        if (d == -1) {
+          v[0] = -v[0];
+        } else if (d == 2 || d == -2) {
+          const float t = v[1];
+          v[1]          = d > 0 ? v[0] : -v[0];
+          v[0]          = t;
+        } else if (d == 3 || d == -3) {
+          const float t = v[2];
+          v[2]          = d > 0 ? v[0] : -v[0];
+          v[0]          = t;
+        } else if (d == 4) {
+          const float o0 = v[0], o1 = v[1], o2 = v[2];
+          const float d1 = m.dir[0], d2 = m.dir[1], d3 = m.dir[2];
+          v[0] = o0 * d1 - o1 * d2 - o2 * d3;
+          v[1] = (o0 * d2 * (d1 + ONE) + o1 * (SQR(d1) + d1 + SQR(d3)) - o2 * d2 * d3) / (d1 + ONE);
+          v[2] = (o0 * d3 * (d1 + ONE) - o1 * d2 * d3 - o2 * (-d1 + SQR(d3) - ONE)) / (d1 + ONE);
+        }
+      }
+    }
+
+    struct InjArgs {
+      int      lo[3], n[3]; // ghost-inclusive start and extent of the cell range
+      int      dim, G;
+      long     N1, N12;
+      float    ppc0;
+      int      sd_kind;     // EB200_SDIST_*
+      const float* field;   // table / density moment, component plane `comp` selected by the host
+      float    target;
+      uint64_t seed;
+      uint32_t step, call;
+    };
+
+    // spatial_dist(cell centre) of the built-in kinds
+    __device__ float spatial_value(const InjArgs& A, long node) {
+      if (A.sd_kind == EB200_SDIST_UNIFORM) return ONE;
+      const float f = A.field[node];
+      if (A.sd_kind == EB200_SDIST_TABLE) return f;
+      // ReplenishUniform (spatial_dist.h:104-124)
+      return (0.9f * A.target > f) ? (A.target - f) / A.target : ZERO;
+    }
+
+    __device__ void cell_of_range(const InjArgs& A, long t, int* c, long& node) {
+      c[0] = (int)(t % A.n[0]) + A.lo[0];
+      c[1] = (A.dim > 1) ? (int)((t / A.n[0]) % A.n[1]) + A.lo[1] : 0;
+      c[2] = (A.dim > 2) ? (int)(t / ((long)A.n[0] * A.n[1])) + A.lo[2] : 0;
+      node = c[0] + (long)c[1] * A.N1 + (long)c[2] * A.N12;
+    }
+
+    // pass 1: NonUniformInjector_kernel::injected_ppc (injectors.hpp:616-633) per cell
+    __global__ void __launch_bounds__(256)
+      inject_count_kernel(const __grid_constant__ InjArgs A, uint32_t* __restrict__ counts) {
+      const long t     = (long)blockIdx.x * blockDim.x + threadIdx.x;
+      const long total = (long)A.n[0] * A.n[1] * A.n[2];
+      if (t >= total) return;
+      int  c[3];
+      long node;
+      cell_of_range(A, t, c, node);
+      const float ppc_real = A.ppc0 * spatial_value(A, node);
+      uint32_t    ppc      = (uint32_t)ppc_real;
+      Philox      g(A.seed, A.step, A.call, (uint32_t)t);
+      if (g.uniform() < ppc_real - (float)ppc) ppc += 1;
+      counts[t] = ppc;
+    }
+
+    // pass 2: the particles of every cell, at the cell's offset of the exclusive scan
+    __global__ void __launch_bounds__(256)
+      inject_fill_kernel(const __grid_constant__ InjArgs A, const uint32_t* __restrict__ counts,
+                         const uint32_t* __restrict__ offsets, eb200_prtls_t S1, eb200_prtls_t S2,
+                         uint32_t off1, uint32_t off2, Maxwell m1, Maxwell m2) {
+      const long t     = (long)blockIdx.x * blockDim.x + threadIdx.x;
+      const long total = (long)A.n[0] * A.n[1] * A.n[2];
+      if (t >= total) return;
+      const uint32_t ppc = counts[t];
+      if (ppc == 0) return;
+      int  c[3];
+      long node;
+      cell_of_range(A, t, c, node);
+      Philox g(A.seed, A.step, A.call, (uint32_t)t);
+      (void)g.uniform(); // the draw pass 1 used for the rounding
+      const uint32_t base = offsets[t];
+      int*           i1[2] = { S1.i1, S2.i1 }, *i2[2] = { S1.i2, S2.i2 }, *i3[2] = { S1.i3, S2.i3 };
+      float*         d1[2] = { S1.dx1, S2.dx1 }, *d2[2] = { S1.dx2, S2.dx2 }, *d3[2] = { S1.dx3, S2.dx3 };
+      float*         u1[2] = { S1.ux1, S2.ux1 }, *u2[2] = { S1.ux2, S2.ux2 }, *u3[2] = { S1.ux3, S2.ux3 };
+      int*           p1[2] = { S1.i1_prev, S2.i1_prev }, *p2[2] = { S1.i2_prev, S2.i2_prev },
+          *p3[2] = { S1.i3_prev, S2.i3_prev };
+      float*         q1[2] = { S1.dx1_prev, S2.dx1_prev }, *q2[2] = { S1.dx2_prev, S2.dx2_prev },
+            *q3[2] = { S1.dx3_prev, S2.dx3_prev };
+      float*         w[2]   = { S1.weight, S2.weight };
+      short*         tag[2] = { S1.tag, S2.tag };
+      const uint32_t off[2] = { off1, off2 };
+      const Maxwell* mm[2]  = { &m1, &m2 };
+      for (uint32_t k = 0; k < ppc; ++k) {
+        float dx[3] = { ZERO, ZERO, ZERO };
+        for (int a = 0; a < A.dim; ++a) dx[a] = g.uniform();
+        for (int s = 0; s < 2; ++s) {
+          float v[3];
+          sample(g, *mm[s], v);
+          const size_t p = (size_t)off[s] + base + k;
+          i1[s][p] = c[0] - A.G, d1[s][p] = dx[0];
+          p1[s][p] = c[0] - A.G, q1[s][p] = dx[0];
+          if (A.dim > 1) {
+            i2[s][p] = c[1] - A.G, d2[s][p] = dx[1];
+            p2[s][p] = c[1] - A.G, q2[s][p] = dx[1];
+          }
+          if (A.dim > 2) {
+            i3[s][p] = c[2] - A.G, d3[s][p] = dx[2];
+            p3[s][p] = c[2] - A.G, q3[s][p] = dx[2];
+          }
+          u1[s][p] = v[0], u2[s][p] = v[1], u3[s][p] = v[2];
+          w[s][p]   = ONE;
+          tag[s][p] = 1;
+        }
+      }
+    }
+
+    // ParticleMoments_kernel<S, Minkowski<D>, F, N>::operator() with window 0
+    // (particle_moments.hpp:293-345): contrib * inv_n0 / sqrt_det_h (* weight) into the cell
+    __global__ void __launch_bounds__(256)
+      moment_kernel(eb200_prtls_t S, uint32_t npart, int dim, int G, long N1, long N12, float coeff,
+                    bool use_weights, float* __restrict__ plane) {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      if (p >= npart) return;
+      if (S.tag[p] == 0) return;
+      float c = coeff;
+      if (use_weights) c *= S.weight[p];
+      long node = S.i1[p] + G;
+      if (dim > 1) node += (long)(S.i2[p] + G) * N1;
+      if (dim > 2) node += (long)(S.i3[p] + G) * N12;
+      atomicAdd(plane + node, c);
+    }
+  } // namespace
+
+  static Maxwell make_maxwell(const eb200_maxwellian_t& e) {
+    Maxwell m {};
+    m.temperature = e.temperature;
+    const float n = std::sqrt(e.drift_u[0] * e.drift_u[0] + e.drift_u[1] * e.drift_u[1] +
+                              e.drift_u[2] * e.drift_u[2]);
+    m.drift_4vel  = n;
+    const float eps = 1.1920929e-07f;
+    if (std::fabs(n) <= eps) {
+      m.drift_dir = 0;
+      return m;
+    }
+    m.drift_3vel = n / std::sqrt(1.0f + n * n);
+    for (int a = 0; a < 3; ++a) m.dir[a] = e.drift_u[a] / n;
+    m.drift_dir = 4;
+    for (int d = 0; d < 3; ++d) {
+      const int dp = (d + 2) % 3, dn = (d + 1) % 3;
+      if (std::fabs(e.drift_u[dp]) <= eps && std::fabs(e.drift_u[dn]) <= eps) {
+        m.drift_dir = (e.drift_u[d] > 0 ? 1 : -1) * (d + 1);
+        break;
+      }
+    }
+    return m;
+  }
+
+  cudaError_t inject_nonuniform(const eb200_grid_t& g, const eb200_prtls_t& S1, uint32_t npart1,
+                                uint32_t cap1, const eb200_prtls_t& S2, uint32_t npart2,
+                                uint32_t cap2, float ppc0, int sd_kind, const float* field,
+                                float target, const eb200_maxwellian_t& e1,
+                                const eb200_maxwellian_t& e2, const int* rmin, const int* rmax,
+                                uint64_t seed, uint32_t step, uint32_t call, uint32_t* n_inj_host,
+                                int* overflow, Scratch& scratch, cudaStream_t st) {
+    InjArgs A;
+    long    total = 1;
+    for (int a = 0; a < 3; ++a) {
+      A.lo[a] = (a < g.dim) ? rmin[a] : 0;
+      A.n[a]  = (a < g.dim) ? rmax[a] - rmin[a] : 1;
+      if (A.n[a] <= 0) {
+        *n_inj_host = 0;
+        return cudaSuccess;
+      }
+      total *= A.n[a];
+    }
+    A.dim = g.dim, A.G = g.ng;
+    A.N1 = g.n[0] + 2 * g.ng;
+    A.N12 = (g.dim > 1) ? A.N1 * (g.n[1] + 2 * g.ng) : 0;
+    A.ppc0 = ppc0, A.sd_kind = sd_kind, A.field = field, A.target = target;
+    A.seed = seed, A.step = step, A.call = call;
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)total + 1, st);
+    const size_t nb4 = ((size_t)(total + 1) * 4 + 255) / 256 * 256;
+    cudaError_t  e   = scratch.reserve(2 * nb4 + tmp + 256);
+    if (e != cudaSuccess) return e;
+    uint32_t* counts  = (uint32_t*)scratch.ptr;
+    uint32_t* offsets = (uint32_t*)((char*)scratch.ptr + nb4);
+    void*     ws      = (char*)scratch.ptr + 2 * nb4;
+    const unsigned nb = (unsigned)((total + 255) / 256);
+    e = cudaMemsetAsync(counts + total, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    inject_count_kernel<<<nb, 256, 0, st>>>(A, counts);
+    count_launch();
+    e = cub::DeviceScan::ExclusiveSum(ws, tmp, counts, offsets, (int)total + 1, st);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    uint32_t n_inj = 0;
+    e = cudaMemcpyAsync(&n_inj, offsets + total, 4, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st); // the new particle count is a host-visible result
+    if (e != cudaSuccess) return e;
+    *n_inj_host = n_inj;
+    *overflow   = ((uint64_t)npart1 + n_inj > cap1) || ((uint64_t)npart2 + n_inj > cap2);
+    if (*overflow || n_inj == 0) return cudaSuccess;
+    inject_fill_kernel<<<nb, 256, 0, st>>>(A, counts, offsets, S1, S2, npart1, npart2,
+                                           make_maxwell(e1), make_maxwell(e2));
+    count_launch();
+    return cudaGetLastError();
+  }
+
+  cudaError_t particle_moment(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
+                              float coeff, bool use_weights, float* plane, cudaStream_t st) {
+    if (npart == 0) return cudaSuccess;
+    const long N1 = g.n[0] + 2 * g.ng, N12 = (g.dim > 1) ? N1 * (g.n[1] + 2 * g.ng) : 0;
+    moment_kernel<<<(npart + 255) / 256, 256, 0, st>>>(S, npart, g.dim, g.ng, N1, N12, coeff,
+                                                       use_weights, plane);
+    count_launch();
+    return cudaGetLastError();
+  }
+} // namespace eb200

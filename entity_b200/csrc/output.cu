@@ -62,7 +62,14 @@ namespace eb200 {
     struct GrOut { // Kerr-Schild family
       MetricParams m;
       __device__ void hat(float x1, float x2, const float* v, float* o) const {
-        gr_cntrv_to_tetrad<M>(m, x1, x2, v, o);
+        if constexpr (M::kind == EB200_METRIC_KERR_SCHILD_0) {
+          // kerr_schild_0.h:457-463: no h_13 term (it would be 0 / 0 on the axis)
+          o[0] = v[0] / sqrtf(M::h11(m, x1, x2));
+          o[1] = v[1] * sqrtf(M::h_22(m, x1, x2));
+          o[2] = v[2] * sqrtf(M::h_33(m, x1, x2));
+        } else {
+          gr_cntrv_to_tetrad<M>(m, x1, x2, v, o);
+        }
       }
       __device__ void pu(float x1, float x2, const float* v, float* o) const {
         if constexpr (M::kind == EB200_METRIC_QKERR_SCHILD) {

@@ -104,6 +104,20 @@ class MatchFaceC(C.Structure):
                 ("range_min", C.c_int * 3), ("range_max", C.c_int * 3)]
 
 
+SDIST_UNIFORM, SDIST_TABLE, SDIST_REPLENISH = 0, 1, 2
+
+
+class MaxwellianC(C.Structure):
+    """eb200_maxwellian_t"""
+    _fields_ = [("temperature", C.c_float), ("drift_u", C.c_float * 3)]
+
+
+class SpatialDistC(C.Structure):
+    """eb200_spatial_dist_t"""
+    _fields_ = [("kind", C.c_int), ("field", C.c_void_p), ("comp", C.c_int),
+                ("target_density", C.c_float)]
+
+
 MAX_MODES = 16
 
 

@@ -153,6 +153,54 @@ class Simulation:
         self._field_bcs = (arr, [b["target"] for b in bcs])
         self.ctx._check(self.ctx.lib.eb200_srpic_set_field_bcs(self.ctx.handle, arr, len(bcs)))
 
+    # ------------------------------------------------------------ injection / moments
+    def particle_moment(self, what, species_indices, buff=None, comp=0, use_weights=False):
+        """arch::ComputeMomentWithSpecies: zeroes `buff` (default: self.buff) and adds the moment
+        of the listed species (0-based) into component comp"""
+        buff = self.buff if buff is None else buff
+        buff.zero_()
+        inv_n0 = 1.0 / self.scales["n0"]
+        for k in species_indices:
+            sp = self.species[k]
+            s = L.Context.prtls_struct(sp.arrays)
+            self.ctx._check(self.ctx.lib.eb200_particle_moment(
+                self.ctx.handle, C.byref(s), sp.npart, C.c_float(sp.mass), C.c_float(sp.charge),
+                int(use_weights), what, C.c_float(inv_n0), C.c_void_p(buff.data_ptr()),
+                int(buff.shape[0]), comp, L.Context._stream(None)))
+        return buff
+
+    def inject_nonuniform(self, pair, ppc, sdist_kind=L.SDIST_UNIFORM, field=None, comp=0,
+                          target=1.0, temperatures=(0.0, 0.0), drifts=((0, 0, 0), (0, 0, 0)),
+                          range_min=None, range_max=None, seed=0x123456789abcdef0, call=0):
+        """arch::InjectNonUniform for the species pair (0-based indices); returns the number of
+        pairs injected. ppc = number_density * ppc0 / 2."""
+        if self._species_c is None:
+            self._species_c = self._pack_species()
+        arr = self._species_c
+        for k, sp in enumerate(self.species):
+            arr[k].npart = sp.npart
+        g = self.grid
+        rmin = range_min or [g.ng] * self.dim
+        rmax = range_max or [g.ng + g.n[a] for a in range(self.dim)]
+        sd = L.SpatialDistC()
+        sd.kind, sd.comp, sd.target_density = sdist_kind, comp, target
+        sd.field = field.data_ptr() if field is not None else None
+        eds = []
+        for t, d in zip(temperatures, drifts):
+            e = L.MaxwellianC()
+            e.temperature = t
+            e.drift_u = (C.c_float * 3)(*d)
+            eds.append(e)
+        n0 = int(arr[pair[0]].npart)
+        self.ctx._check(self.ctx.lib.eb200_inject_nonuniform(
+            self.ctx.handle, C.byref(arr[pair[0]]), C.byref(arr[pair[1]]), C.c_float(ppc),
+            C.byref(sd), C.byref(eds[0]), C.byref(eds[1]), (C.c_int * 3)(*(list(rmin) + [0] * 3)[:3]),
+            (C.c_int * 3)(*(list(rmax) + [1] * 3)[:3]), C.c_uint64(seed), self.step_index, call,
+            L.Context._stream(None)))
+        for k in pair:
+            self.species[k].npart = int(arr[k].npart)
+        return int(arr[pair[0]].npart) - n0
+
     def set_ext_current(self, table):
         """The pgen's ext_current as a table of Fourier modes (eb200_ext_current_t; see
         lib.ExtCurrentC.from_table); None clears it. The host refills it whenever the pgen

@@ -603,6 +603,51 @@ int eb200_grpic_step(eb200_ctx_t* ctx, const eb200_grpic_params_t* prm, float** 
                      const float* match_target, eb200_species_t* species, int nspecies,
                      uint32_t step, double time, eb200_stream_t stream);
 
+/* --------------------------------- injection and particle moments */
+/* arch::energy_dist::Maxwellian (src/archetypes/energy_dist.h:170-290): temperature in m c^2
+ * (0 = cold), drift four-velocity (Cartesian meshes only; any direction) */
+typedef struct {
+  float temperature;
+  float drift_u[3];
+} eb200_maxwellian_t;
+/* spatial distributions: the functor of arch::InjectNonUniform cannot cross a C ABI */
+enum {
+  EB200_SDIST_UNIFORM   = 0, /* spatial_dist = 1 (what arch::InjectUniform draws in expectation) */
+  EB200_SDIST_TABLE     = 1, /* field = the functor's value at every cell centre */
+  EB200_SDIST_REPLENISH = 2  /* arch::spatial_dist::ReplenishUniform (spatial_dist.h:87-125):
+                                field = density moment, refilled up to target_density where it
+                                fell below 0.9 of it */
+};
+typedef struct {
+  int          kind;
+  const float* field; /* device: component plane(s) in the mesh layout (ghost-inclusive) */
+  int          comp;  /* component of `field` to read */
+  float        target_density;
+} eb200_spatial_dist_t;
+/* arch::InjectNonUniform (src/archetypes/particle_injector.h:296-387) with
+ * kernel::NonUniformInjector_kernel (src/kernels/injectors.hpp:526-859) on a Minkowski domain:
+ * in every cell of the ghost-inclusive range, ppc = number_density * ppc0 / 2 * spatial_dist pairs
+ * (the fraction rounded stochastically), both species of a pair at the same position, velocities
+ * from ed1 / ed2, weight 1, appended at npart of either species (both npart grow by the same
+ * number; returns EB200_ERR_CAPACITY and injects nothing when maxnpart would be exceeded).
+ * Every cell draws from its own counter-based Philox4x32-10 stream keyed by (seed, step, call,
+ * cell): the result is a pure function of the arguments, identical on every device and for
+ * every launch shape; `call` distinguishes several injections of one step. Synchronises the
+ * stream once (the new particle count). */
+int eb200_inject_nonuniform(eb200_ctx_t* ctx, eb200_species_t* species1, eb200_species_t* species2,
+                            float ppc, const eb200_spatial_dist_t* sdist,
+                            const eb200_maxwellian_t* ed1, const eb200_maxwellian_t* ed2,
+                            const int* range_min, const int* range_max, uint64_t seed,
+                            uint32_t step, uint32_t call, eb200_stream_t stream);
+/* arch::ComputeMomentWithSpecies / kernel::ParticleMoments_kernel (src/archetypes/utils.h:
+ * 136-169, src/kernels/particle_moments.hpp:37-419) on a Minkowski domain for the scalar
+ * moments what = EB200_STATS_N | RHO | CHARGE | NPART (Nppc), smoothing order 0 (the
+ * archetypes' default): adds one species into component comp of buff (ncomp planes; the host
+ * zeroes it once, as ComputeMomentWithSpecies does before its species loop). */
+int eb200_particle_moment(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, float mass,
+                          float charge, int use_weights, int what, float inv_n0, float* buff,
+                          int ncomp, int comp, eb200_stream_t stream);
+
 /* ------------------------------------------------ output staging */
 /* kernel::FieldsToPhys_kernel<M, N1, N2> over Mesh::rangeActiveCells (src/kernels/
  * fields_to_phys.hpp:33-239; what the writer launches per output field, src/output/

@@ -3,7 +3,7 @@ FieldsToPhys_kernel / PrtlToPhys_kernel compiled in place (tests/golden/out_gold
 tests/golden/make_out_golden.py), Minkowski and the five curvilinear metrics.
 
 Interpolation and the Minkowski conversions are bit-exact; the curvilinear conversions go
-through expf / sinf / cosf / sqrtf of the metric (CUDA vs glibc, last ulp): 2e-6 relative."""
+through expf / sinf / cosf / sqrtf of the metric (CUDA vs glibc, last ulp): 5e-6 relative."""
 import ctypes as C
 import os
 
@@ -53,7 +53,7 @@ def test_fields_to_phys(eb, kind):
         if kind == 0 or conv == 0:
             assert np.array_equal(out[act], ref[act]), f"metric {kind} case {k}"
         else:
-            np.testing.assert_allclose(out[act], ref[act], rtol=2e-6, atol=1e-30,
+            np.testing.assert_allclose(out[act], ref[act], rtol=5e-6, atol=1e-30,
                                        err_msg=f"metric {kind} case {k}")
     ctx.close()
 
