@@ -291,7 +291,7 @@ def run_ours(args):
         sim = workloads.reconnection(size, ppc0=args.ppc, nfilter=args.filters, fused=not args.unfused,
                                      sort_interval=args.sort_interval, device=local,
                                      deposit_mode=dmode, seed=0x5678 + rank, walls=args.walls,
-                                     capacity_factor=1.0 if world == 1 else 1.1)
+                                     capacity_factor=(1.05 if args.replenish else 1.0) if world == 1 else 1.1)
     decomposition = [1] * len(size)
     if world > 1:
         # spatial block decomposition as the reference's reconnection.toml asks ([-1, 2]); every
@@ -352,7 +352,15 @@ def run_ours(args):
     barrier()
     t_first = sim.step_index
     ev0.record()
-    sim.step(K)
+    n_replenished = 0
+    if args.replenish:
+        # the reconnection pgen's CustomPostStep after every step (density moment + two
+        # ReplenishUniform injections), as the reference's time loop runs it
+        for _ in range(K):
+            sim.step()
+            n_replenished += sim.replenish(sim.replenish_boxes)
+    else:
+        sim.step(K)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -387,6 +395,7 @@ def run_ours(args):
     timing = {"window_ms": ms_raw, "sorts_in_window": int(sorts_in), "sort_ms": sort_ms,
               "sort_interval": si, "sort_charge_ms_per_step": sort_ms / si if si > 0 else 0.0,
               "ms_per_step_raw": ms_raw / K, "alignment_steps": pre,
+              "pairs_replenished_per_step": n_replenished / K,
               "note": "ms_per_step = (window - sorts inside) / steps + sort_ms / sort_interval"}
 
     # roofline of the dominant kernel (fused push+deposit), from the in-step CUDA events
@@ -465,7 +474,9 @@ def run_ours(args):
                                     if turb else
                                     WORKLOAD if size == (4096, 2048) and args.ppc == 32 else
                                     f"reconnection 2D {size[0]}x{size[1]} cells, {args.ppc} ppc (reduced)")
-                       + (" [x2 walls: fields MATCH ds=20, particles ABSORB, no injector]"
+                       + ((" [x2 walls: fields MATCH ds=20, particles ABSORB, replenishing injector every step]"
+                           if args.replenish else
+                           " [x2 walls: fields MATCH ds=20, particles ABSORB, no injector]")
                           if args.walls else ""),
                        "cells_per_gpu": list(size),
                        "ppc0": ((8 if args.ppc == 32 else args.ppc) if other == "wald" else
@@ -531,6 +542,9 @@ def main():
     ap.add_argument("--walls", action="store_true",
                     help="x2 boundaries of reconnection.toml (fields MATCH, particles ABSORB) instead "
                          "of the periodic core; single GPU, no replenishing injector")
+    ap.add_argument("--replenish", action="store_true",
+                    help="with --walls: run the reconnection pgen's replenishing injector (density "
+                         "moment + ReplenishUniform in the two 10-cell boxes) after every step")
     ap.add_argument("--decomp", type=int, nargs="+", default=None,
                     help="override the block decomposition request (default -1 2, as reconnection.toml)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -541,6 +555,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.replenish:
+        args.walls = True
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

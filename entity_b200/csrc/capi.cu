@@ -45,6 +45,7 @@ struct eb200_ctx {
   eb200::EngineState* engine = nullptr;
   eb200::Comm*   comm = nullptr; // attached by eb200_comm_init (multi-domain exchange)
   eb200::Scratch scratch;
+  uint32_t       sort_cap = 0; // high-water mark of the sort's capacity (see eb200_sort_particles)
   std::string    err;
   uint64_t       launches_at_init;
   int            pd_kernel = 0; // eb200_set_pd_kernel
@@ -1145,7 +1146,16 @@ int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t*
   int rc = check_prtls(ctx, prtls, *npart_inout);
   if (rc) return rc;
   uint32_t    n_alive = *npart_inout;
-  cudaError_t e = eb200::sort_particles(ctx->cfg.grid, *prtls, *npart_inout, ctx->cfg.maxnpart,
+  // The scratch layout follows a capacity, not npart: with migration npart moves from sort to
+  // sort, and every growth of the 5 GB scratch is a cudaFree + cudaMalloc (13 ms per sort measured
+  // at 4 x B200). Without a configured capacity keep a high-water mark with 1/8 headroom.
+  {
+    const uint32_t n    = *npart_inout;
+    const uint64_t want = (uint64_t)n + n / 8;
+    if (ctx->cfg.maxnpart > ctx->sort_cap) ctx->sort_cap = ctx->cfg.maxnpart;
+    if (n > ctx->sort_cap) ctx->sort_cap = (uint32_t)(want < 0xFFFFFFFFull ? want : 0xFFFFFFFFull);
+  }
+  cudaError_t e = eb200::sort_particles(ctx->cfg.grid, *prtls, *npart_inout, ctx->sort_cap,
                                         remove_dead, &n_alive, ctx->scratch, (cudaStream_t)stream);
   if (e != cudaSuccess) return check_cuda(ctx, e, "sort_particles");
   if (remove_dead & 1) *npart_inout = n_alive;

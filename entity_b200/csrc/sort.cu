@@ -11,6 +11,9 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace eb200 {
 
   template <int D>
@@ -167,6 +170,16 @@ namespace eb200 {
     uint32_t* count = (uint32_t*)(base + 8 * n4); // tmp holds four arrays: 4 * n4 .. 8 * n4
     void*     cubws = (void*)(base + 8 * n4 + 256);
 
+    // EB200_SORT_TRACE=1: stage times on stderr (synchronises; diagnosis only)
+    static const bool trace = getenv("EB200_SORT_TRACE") != nullptr;
+    cudaEvent_t       tev[5] = {};
+    auto              mark   = [&](int k) {
+      if (trace) {
+        if (!tev[k]) cudaEventCreate(&tev[k]);
+        cudaEventRecord(tev[k], st);
+      }
+    };
+    mark(0);
     const unsigned nb = (npart + 255) / 256;
     switch (g.dim) {
       case 1:
@@ -181,10 +194,12 @@ namespace eb200 {
       default: return cudaErrorInvalidValue;
     }
     count_launch();
+    mark(1);
     err = cub::DeviceRadixSort::SortPairs(cubws, tmp_bytes, k0, k1, i0, perm, (size_t)npart, 0,
                                           bits, st);
     if (err != cudaSuccess) return err;
     count_launch();
+    mark(2);
     if (remove_dead && n_alive_out) {
       count_alive_kernel<<<1, 1, 0, st>>>(k1, npart, ncells, count);
       count_launch();
@@ -215,7 +230,17 @@ namespace eb200 {
       }
       permute_words(w, nw, perm, npart, (char*)tmp, n4, st);
     }
+    mark(3);
     permute(S.tag, perm, npart, tmp, st);
+    mark(4);
+    if (trace) {
+      cudaEventSynchronize(tev[4]);
+      float t[4];
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[k], tev[k + 1]);
+      fprintf(stderr, "[eb200 sort] npart %u cap %zu bits %d: keys %.2f radix %.2f gather %.2f tag %.2f ms\n",
+              npart, ncap, bits, t[0], t[1], t[2], t[3]);
+      for (auto& e : tev) cudaEventDestroy(e);
+    }
 
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;

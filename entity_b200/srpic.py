@@ -201,6 +201,18 @@ class Simulation:
             self.species[k].npart = int(arr[k].npart)
         return int(arr[pair[0]].npart) - n0
 
+    def replenish(self, boxes, pair=(0, 1), temperature=1e-4, target=1.0):
+        """pgens/reconnection/pgen.hpp:222-278 (CustomPostStep): the mass density of the pair into
+        buff[0], then arch::InjectNonUniform with ReplenishUniform(target) and a Maxwellian of the
+        background temperature in each box (ghost-inclusive cell ranges); returns pairs injected"""
+        self.particle_moment(L.STATS_RHO, list(pair), comp=0)
+        n = 0
+        for k, (rmin, rmax) in enumerate(boxes):
+            n += self.inject_nonuniform(pair, 0.5 * self.scales["ppc0"], L.SDIST_REPLENISH, self.buff,
+                                        comp=0, target=target, temperatures=(temperature, temperature),
+                                        range_min=rmin, range_max=rmax, call=k)
+        return n
+
     def set_ext_current(self, table):
         """The pgen's ext_current as a table of Fourier modes (eb200_ext_current_t; see
         lib.ExtCurrentC.from_table); None clears it. The host refills it whenever the pgen

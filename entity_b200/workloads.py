@@ -138,6 +138,11 @@ def reconnection(n=(4096, 2048), ppc0=32, nfilter=8, seed=0x5678, sheets=True,
         ymax = float(np.float32(ymin) + np.float32(dx) * np.float32(n[1]))
         sim.set_match([(1, ymin, ds, [0, 0], [ext[0], g.ng + nds]),
                        (1, ymax, ds, [0, g.ng + n[1] - nds], [ext[0], ext[1]])], target, 63)
+        # the replenishing injector's boxes (pgen.hpp:236-241): 10 cells wide, inj_ypad = 50 (scaled
+        # with the box) inside either x2 boundary, all of x1
+        pad = max(1, int(round(50.0 * (n[0] / 4096.0) / dx)))
+        sim.replenish_boxes = [([g.ng, g.ng + n[1] - pad - 10], [g.ng + n[0], g.ng + n[1] - pad]),
+                               ([g.ng, g.ng + pad], [g.ng + n[0], g.ng + pad + 10])]
     gen = _gen(sim, seed)
     ncell = n[0] * n[1]
     n_bg = ncell * (ppc0 // 2)

@@ -101,6 +101,12 @@ def main(decomp2d=None, decomp3d=None):
         ctx.comm_init(L.make_metadomain(rank, extents), fresh_uid())
         arr = to_device(sets[rank])
         npart = counts[rank]
+        # payload planes (pld_r x2, pld_i x1) derived from the particle's weight, which nothing on this
+        # path modifies: after every migration each alive particle must still carry its own payloads
+        # (records carry them: src/kernels/comm.hpp:75-105)
+        w_ = arr["weight"]
+        arr["pld_r"] = torch.stack([2.0 * w_, w_ + 1.0]).contiguous()
+        arr["pld_i"] = w_.view(torch.int32).clone().reshape(1, -1).contiguous()
         em0 = torch.zeros(ctx.grid.shape(6), dtype=torch.float32, device="cuda")
         for step in range(3):
             lb = mdcomm.Loopback()
@@ -138,6 +144,12 @@ def main(decomp2d=None, decomp3d=None):
                 if nm != "tag":
                     a, b = a[alive], b[alive]
                 check(np.array_equal(a, b), f"migration dim {dim} step {step}: array {nm}")
+            wv = arr["weight"][:npart][torch.from_numpy(alive).to("cuda")]
+            sel_ = torch.from_numpy(alive).to("cuda")
+            check(bool(torch.equal(arr["pld_r"][0, :npart][sel_], 2.0 * wv))
+                  and bool(torch.equal(arr["pld_r"][1, :npart][sel_], wv + 1.0))
+                  and bool(torch.equal(arr["pld_i"][0, :npart][sel_], wv.view(torch.int32))),
+                  f"migration dim {dim} step {step}: payloads did not travel with their particles")
         ctx.close()
 
     # ------------------------------------------------ whole step against the global oracle

@@ -227,6 +227,36 @@ def test_sort_particles(eb, orc_mod, dim):
         assert np.array_equal(getattr(q, nm), getattr(p, nm)[perm]), nm
 
 
+def test_sort_payloads_and_skip_prev(eb, orc_mod):
+    """Payload planes are permuted with their particle (particles_sort.cpp:150-160, 239-247);
+    EB200_SORT_SKIP_PREV permutes everything except i_prev / dx_prev."""
+    import torch
+    g = orc_mod.Grid.make(DIMS[2], 2)
+    ctx = eb.Context(DIMS[2], order=0)
+    n = 7000
+    p = random_particles(g, n, 11, dead_frac=0.15)
+    for flags in (1, 1 | 2):
+        arr = to_device(p)
+        w = arr["weight"]
+        arr["pld_r"] = torch.stack([2.0 * w, w + 1.0, -w]).contiguous()
+        arr["pld_i"] = torch.stack([w.view(torch.int32), torch.arange(n, dtype=torch.int32, device="cuda")]).contiguous()
+        prev0 = {k: arr[k].clone() for k in ("i1_prev", "i2_prev", "dx1_prev", "dx2_prev")}
+        n_alive = ctx.sort_particles(arr, n, remove_dead=flags)
+        assert n_alive == int((p.tag == 1).sum())
+        key0 = p.i1.astype(np.int64) + g.n[0] * p.i2.astype(np.int64)
+        key0[p.tag != 1] = np.iinfo(np.int64).max
+        perm = np.argsort(key0, kind="stable")
+        assert np.array_equal(arr["pld_i"][1].cpu().numpy(), perm.astype(np.int32))
+        w2 = arr["weight"]
+        assert torch.equal(arr["pld_r"][0], 2.0 * w2) and torch.equal(arr["pld_r"][1], w2 + 1.0)
+        assert torch.equal(arr["pld_r"][2], -w2) and torch.equal(arr["pld_i"][0], w2.view(torch.int32))
+        for k, v in prev0.items():
+            if flags & 2:
+                assert torch.equal(arr[k], v), k  # untouched
+            else:
+                assert np.array_equal(arr[k].cpu().numpy(), getattr(p, k)[perm]), k
+
+
 def test_errors(eb):
     with pytest.raises(eb.EB200Error):
         eb.Context((8, 8), order=7)
