@@ -281,13 +281,15 @@ def run_ours(args):
         # configs[2]-shaped block (3D, T = 1 pair plasma, 3rd-order shapes, 4 filter passes) at the
         # n^3 given: a second bench line for the Esirkepov path, single GPU, not the headline
         size = (args.turbulence,) * 3
-        if args.sort_interval == 40:
+        if args.sort_interval is None:
             args.sort_interval = 5  # hot plasma, wide windows: the order decays within a few steps
         sim = workloads.turbulence(size, ppc0=args.ppc if args.ppc != 32 else 16, order=3, nfilter=4,
                                    fused=not args.unfused, sort_interval=args.sort_interval,
                                    device=local, deposit_mode=dmode, seed=0x9abc + rank,
                                    capacity_factor=1.0 if world == 1 else 1.25)
     else:
+        if args.sort_interval is None:
+            args.sort_interval = 20
         sim = workloads.reconnection(size, ppc0=args.ppc, nfilter=args.filters, fused=not args.unfused,
                                      sort_interval=args.sort_interval, device=local,
                                      deposit_mode=dmode, seed=0x5678 + rank, walls=args.walls,
@@ -330,7 +332,8 @@ def run_ours(args):
     def sort_all():
         for sp in sim.species:
             if sp.npart:
-                sim.ctx.sort_particles(sp.arrays, sp.npart, remove_dead=2)  # EB200_SORT_SKIP_PREV, as the step sorts
+                # EB200_SORT_SKIP_PREV | EB200_SORT_UNSTABLE: as the step sorts on a fast-build context
+                sim.ctx.sort_particles(sp.arrays, sp.npart, remove_dead=2 | 4)
 
     pre = 0
     if si > 0:
@@ -531,7 +534,9 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=[4096, 2048])
     ap.add_argument("--ppc", type=int, default=32)
     ap.add_argument("--filters", type=int, default=8)
-    ap.add_argument("--sort-interval", type=int, default=40)
+    ap.add_argument("--sort-interval", type=int, default=None,
+                    help="cell sort every N steps (default 20 for the 2D workloads: the measured optimum "
+                         "with the 12 ms counting sort, profiles/bench_r2k_sort_interval_*.json; 5 for --turbulence)")
     ap.add_argument("--deposit", default="aggregated", choices=["atomic", "aggregated", "ordered"])
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--turbulence", type=int, default=None, metavar="N",

@@ -13,5 +13,5 @@ from .lib import (  # noqa: F401
     FBC_NONE, FBC_PERIODIC, FBC_CONDUCTOR, FBC_AXIS, FBC_SYNC,
     DEPOSIT_ATOMIC, DEPOSIT_ORDERED, DEPOSIT_AGGREGATED, EB200Error,
     STATS_NPART, STATS_N, STATS_RHO, STATS_CHARGE, STATS_T,
-    SDIST_UNIFORM, SDIST_TABLE, SDIST_REPLENISH,
+    SDIST_UNIFORM, SDIST_TABLE, SDIST_REPLENISH, SDIST_REPLENISH_TABLE, SDIST_ATMOSPHERE,
 )

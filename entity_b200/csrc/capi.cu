@@ -49,6 +49,7 @@ struct eb200_ctx {
   std::string    err;
   uint64_t       launches_at_init;
   int            pd_kernel = 0; // eb200_set_pd_kernel
+  int            sort_mode = -1; // eb200_set_sort_mode
   eb200::Scratch packed;        // E/B repacked node by node for the fused 2D zig-zag kernel
   eb200::Scratch packed_j;      // J as 16-byte nodes {jx1, jx2, jx3, -}: target of kernel 8's flushes
   void*          packed_j_zeroed = nullptr; // the allocation that has been cleared
@@ -951,21 +952,49 @@ int eb200_conductor_fields(eb200_ctx_t* ctx, float* em, int o, int sign, int tag
 }
 
 /* ------------------------------------------------ injection and particle moments */
+// metric argument of the injection / moment kernels: null on Minkowski contexts
+static const eb200::MetricParams* metric_or_null(const eb200_ctx_t* ctx) {
+  return ctx->cfg.metric == EB200_METRIC_MINKOWSKI ? nullptr : &ctx->metric;
+}
+
 int eb200_inject_nonuniform(eb200_ctx_t* ctx, eb200_species_t* sp1, eb200_species_t* sp2, float ppc,
                             const eb200_spatial_dist_t* sd, const eb200_maxwellian_t* ed1,
                             const eb200_maxwellian_t* ed2, const int* rmin, const int* rmax,
                             uint64_t seed, uint32_t step, uint32_t call, eb200_stream_t stream) {
   ENTER(ctx);
   REQUIRE(ctx, sp1 && sp2 && sd && ed1 && ed2 && rmin && rmax, "null argument");
-  REQUIRE_MINK(ctx, "eb200_inject_nonuniform");
+  const int  metric = ctx->cfg.metric;
+  const bool mink   = metric == EB200_METRIC_MINKOWSKI;
+  REQUIRE(ctx, mink || metric == EB200_METRIC_SPHERICAL || metric == EB200_METRIC_QSPHERICAL,
+          "eb200_inject_nonuniform: Minkowski and (q)spherical SRPIC meshes");
   REQUIRE(ctx, ppc >= 0.0f, "ppc < 0");
   REQUIRE(ctx, ed1->temperature >= 0.0f && ed2->temperature >= 0.0f,
           "Maxwellian: Temperature must be non-negative");
-  REQUIRE(ctx, sd->kind == EB200_SDIST_UNIFORM || sd->kind == EB200_SDIST_TABLE ||
-                 sd->kind == EB200_SDIST_REPLENISH, "unknown spatial distribution");
+  REQUIRE(ctx, sd->kind >= EB200_SDIST_UNIFORM && sd->kind <= EB200_SDIST_ATMOSPHERE,
+          "unknown spatial distribution");
   REQUIRE(ctx, sd->kind == EB200_SDIST_UNIFORM || (sd->field != nullptr && sd->comp >= 0),
           "spatial distribution: null field");
+  REQUIRE(ctx, sd->kind != EB200_SDIST_REPLENISH_TABLE || (sd->target_field && sd->target_max > 0.0f),
+          "Replenish: null target table or target_max <= 0");
   const eb200_grid_t& g = ctx->cfg.grid;
+  if (sd->kind == EB200_SDIST_ATMOSPHERE) {
+    REQUIRE(ctx, sd->atm_dim >= 0 && sd->atm_dim < g.dim && sd->atm_sign != 0 &&
+                   sd->atm_nmax > 0.0f && sd->atm_height > 0.0f,
+            "atmosphere: bad direction, density or height");
+    // utils.h:59-63, particle_injector.h:161-168
+    REQUIRE(ctx, mink || (sd->atm_dim == 0 && sd->atm_sign < 0),
+            "For non-cartesian coordinates atmosphere BCs is possible only in -x1 (@ rmin)");
+  }
+  if (!mink) {
+    REQUIRE(ctx, g.dim == 2, "curvilinear injection: 2D");
+    REQUIRE(ctx, sd->inv_V0 > 0.0f, "curvilinear injection: inv_V0 must be set (weights)");
+    for (const eb200_maxwellian_t* e : { ed1, ed2 }) {
+      REQUIRE(ctx, e->drift_u[0] == 0.0f && e->drift_u[1] == 0.0f && e->drift_u[2] == 0.0f,
+              "Maxwellian: drift on Cartesian meshes only");
+    }
+    REQUIRE(ctx, sp1->arrays.weight && sp2->arrays.weight,
+            "Weights must be used for non-Cartesian coordinates");
+  }
   for (int a = 0; a < g.dim; ++a) {
     REQUIRE(ctx, rmin[a] >= 0 && rmax[a] <= g.n[a] + 2 * g.ng, "inject: range outside the array");
   }
@@ -978,11 +1007,13 @@ int eb200_inject_nonuniform(eb200_ctx_t* ctx, eb200_species_t* sp1, eb200_specie
   const float* field = sd->field ? sd->field + (size_t)sd->comp * plane : nullptr;
   uint32_t     n_inj = 0;
   int          overflow = 0;
+  const float  xmin[3] = { ctx->cfg.metric_params[1], ctx->cfg.metric_params[2], ctx->cfg.metric_params[3] };
   rc = check_cuda(ctx,
-                  eb200::inject_nonuniform(g, sp1->arrays, sp1->npart, sp1->maxnpart, sp2->arrays,
-                                           sp2->npart, sp2->maxnpart, ppc, sd->kind, field,
-                                           sd->target_density, *ed1, *ed2, rmin, rmax, seed, step,
-                                           call, &n_inj, &overflow, ctx->scratch, (cudaStream_t)stream),
+                  eb200::inject_nonuniform(g, metric_or_null(ctx), ctx->cfg.metric_params[0], xmin,
+                                           sp1->arrays, sp1->npart, sp1->maxnpart, sp2->arrays,
+                                           sp2->npart, sp2->maxnpart, ppc, *sd, field, *ed1, *ed2,
+                                           rmin, rmax, seed, step, call, &n_inj, &overflow,
+                                           ctx->scratch, (cudaStream_t)stream),
                   "inject_nonuniform");
   if (rc) return rc;
   if (overflow) return fail(ctx, EB200_ERR_CAPACITY, "inject: npart + injected > maxnpart");
@@ -995,7 +1026,6 @@ int eb200_particle_moment(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t
                           float charge, int use_weights, int what, float inv_n0, float* buff,
                           int ncomp, int comp, eb200_stream_t stream) {
   ENTER(ctx);
-  REQUIRE_MINK(ctx, "eb200_particle_moment");
   REQUIRE(ctx, buff != nullptr && comp >= 0 && comp < ncomp, "Invalid buffer index");
   REQUIRE(ctx, what == EB200_STATS_N || what == EB200_STATS_RHO || what == EB200_STATS_CHARGE ||
                  what == EB200_STATS_NPART, "eb200_particle_moment: N, Rho, Charge or Nppc");
@@ -1003,7 +1033,9 @@ int eb200_particle_moment(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t
           "Rho & Charge for massless particles not defined");
   int rc = check_prtls(ctx, prtls, npart);
   if (rc) return rc;
-  const eb200_grid_t& g  = ctx->cfg.grid;
+  const eb200_grid_t& g    = ctx->cfg.grid;
+  const bool          mink = ctx->cfg.metric == EB200_METRIC_MINKOWSKI;
+  REQUIRE(ctx, mink || g.dim == 2, "curvilinear moments: 2D");
   const float         dx = ctx->cfg.metric_params[0];
   float               sqrt_det_h = 1.0f; // minkowski.h: dx^D
   size_t              plane      = 1;
@@ -1011,17 +1043,59 @@ int eb200_particle_moment(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t
     sqrt_det_h *= dx;
     plane *= (size_t)(g.n[a] + 2 * g.ng);
   }
-  float coeff = (what == EB200_STATS_RHO) ? mass : ((what == EB200_STATS_CHARGE) ? charge : 1.0f);
-  bool  uw    = use_weights != 0;
+  float coeff  = (what == EB200_STATS_RHO) ? mass : ((what == EB200_STATS_CHARGE) ? charge : 1.0f);
+  bool  uw     = use_weights != 0;
+  bool  volume = true;
   if (what != EB200_STATS_NPART) {
-    coeff *= inv_n0 / sqrt_det_h;
+    coeff *= inv_n0;
+    if (mink) coeff /= sqrt_det_h;
   } else {
-    uw = false; // Nppc: no volume, weights or smoothing (particle_moments.hpp:306-309)
+    uw = false, volume = false; // Nppc: no volume, weights or smoothing (particle_moments.hpp:306-309)
   }
   return check_cuda(ctx,
-                    eb200::particle_moment(g, *prtls, npart, coeff, uw, buff + (size_t)comp * plane,
-                                           (cudaStream_t)stream),
+                    eb200::particle_moment(g, metric_or_null(ctx), *prtls, npart, coeff, uw, volume,
+                                           buff + (size_t)comp * plane, (cudaStream_t)stream),
                     "particle_moment");
+}
+
+int eb200_atmosphere_particles(eb200_ctx_t* ctx, const eb200_atmosphere_t* atm,
+                               eb200_species_t* species, int nspecies, float* plane,
+                               int assume_empty, uint32_t step, eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, atm && species && plane, "null argument");
+  REQUIRE(ctx, atm->species[0] >= 0 && atm->species[0] < nspecies && atm->species[1] >= 0 &&
+                 atm->species[1] < nspecies && atm->species[0] != atm->species[1],
+          "atmosphere: bad species pair");
+  const eb200_grid_t& g = ctx->cfg.grid;
+  size_t              n = 1;
+  for (int a = 0; a < g.dim; ++a) n *= (size_t)(g.n[a] + 2 * g.ng);
+  // particles_bcs.h:56-119: the density of the two species (Rho, weights on curvilinear meshes)
+  if (cudaMemsetAsync(plane, 0, n * sizeof(float), (cudaStream_t)stream) != cudaSuccess) {
+    return fail(ctx, EB200_ERR_CUDA, "atmosphere: memset");
+  }
+  const int use_weights = ctx->cfg.metric != EB200_METRIC_MINKOWSKI;
+  if (!assume_empty) {
+    for (int k = 0; k < 2; ++k) {
+      eb200_species_t& sp = species[atm->species[k]];
+      if (sp.npart == 0) continue;
+      int rc = eb200_particle_moment(ctx, &sp.arrays, sp.npart, sp.mass, sp.charge, use_weights,
+                                     EB200_STATS_RHO, atm->inv_n0, plane, 1, 0, stream);
+      if (rc) return rc;
+    }
+  }
+  // :121-152: InjectNonUniform<Replenish<AtmosphereDensityProfile>>, number_density = nmax
+  eb200_spatial_dist_t sd {};
+  sd.kind = EB200_SDIST_ATMOSPHERE, sd.field = plane, sd.comp = 0;
+  sd.atm_dim = atm->dim, sd.atm_sign = atm->sign;
+  sd.atm_nmax = atm->density, sd.atm_height = atm->height;
+  sd.atm_xsurf = atm->x_surf, sd.atm_ds = atm->ds;
+  sd.inv_V0 = atm->inv_V0;
+  const eb200_maxwellian_t mw { atm->temperature, { 0.0f, 0.0f, 0.0f } };
+  int rmin[3] = { 0, 0, 0 }, rmax[3] = { 1, 1, 1 };
+  for (int a = 0; a < g.dim; ++a) rmin[a] = g.ng, rmax[a] = g.ng + g.n[a];
+  return eb200_inject_nonuniform(ctx, &species[atm->species[0]], &species[atm->species[1]],
+                                 atm->density * atm->ppc0 * 0.5f, &sd, &mw, &mw, rmin, rmax,
+                                 atm->seed, step, /*call*/ 0x41544du, stream);
 }
 
 /* ------------------------------------------------------------------ output staging */
@@ -1100,6 +1174,19 @@ int eb200_set_pd_kernel(eb200_ctx_t* ctx, int which) {
           "pd kernel: 0 auto, 1 per-thread, 2 TMA stream, 3 vec4, 4 shared-memory tiles, 5 vec4 + packed nodes, 6 pipelined, 7 shared-memory resident, 8 vec4 + packed nodes + moment deposit, 9 3D O=3 shared-memory J tile");
   ctx->pd_kernel = which;
   return EB200_OK;
+}
+
+int eb200_set_sort_mode(eb200_ctx_t* ctx, int mode) {
+  ENTER(ctx);
+  REQUIRE(ctx, mode >= -1 && mode <= 1, "sort mode: -1 by build, 0 radix (stable), 1 counting");
+  ctx->sort_mode = mode;
+  return EB200_OK;
+}
+
+// the sort flags of the step mirrors (engine.cu)
+int eb200_ctx_sort_flags(const eb200_ctx_t* ctx) {
+  const int mode = ctx->sort_mode >= 0 ? ctx->sort_mode : (ctx->cfg.strict_fp ? 0 : 1);
+  return mode == 1 ? EB200_SORT_UNSTABLE : 0;
 }
 
 int eb200_zero_currents(eb200_ctx_t* ctx, float* cur, eb200_stream_t stream) {

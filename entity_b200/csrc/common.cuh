@@ -75,4 +75,37 @@ namespace eb200 {
 
   struct LaunchCounter; // capi.cu
 
+#ifdef __CUDACC__
+  // Runs of consecutive lanes with the same key (particles arrive nearly cell-sorted): the head
+  // lane of a run acts for the whole run. All 32 lanes must call.
+  struct LaneRun {
+    bool head;
+    int  first, last; // lanes of this lane's run
+  };
+
+  __device__ __forceinline__ LaneRun lane_run(long long key) {
+    const unsigned  lane  = threadIdx.x & 31u;
+    const long long prev  = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool      head  = (lane == 0u) || (prev != key);
+    const unsigned  heads = __ballot_sync(0xffffffffu, head);
+    const unsigned  above = (lane == 31u) ? 0u : (heads & ~((2u << lane) - 1u));
+    LaneRun         r;
+    r.head  = head;
+    r.last  = above ? (__ffs(above) - 2) : 31;
+    r.first = 31 - __clz(heads & ((2u << lane) - 1u));
+    return r;
+  }
+
+  // sum of v over the lanes lane .. run.last; the run's total on its head lane
+  __device__ __forceinline__ float lane_run_sum(float v, const LaneRun& r) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_down_sync(0xffffffffu, v, d);
+      if (lane + d <= r.last) v += o;
+    }
+    return v;
+  }
+#endif
+
 } // namespace eb200

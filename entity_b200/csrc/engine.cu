@@ -84,6 +84,9 @@ namespace eb200 {
     // the pgen's ext_current as a mode table (eb200_srpic_set_ext_current)
     bool                has_ext = false;
     eb200_ext_current_t ext {};
+    // srpic::ParticleInjector for an ATMOSPHERE face (eb200_srpic_set_atmosphere_injector)
+    bool               has_atm = false;
+    eb200_atmosphere_t atm {};
   };
 
   struct PhaseScope {
@@ -111,6 +114,7 @@ namespace eb200 {
 extern "C" eb200::EngineState* eb200_ctx_engine_state(eb200_ctx_t* ctx);
 extern "C" int                 eb200_ctx_metric(const eb200_ctx_t* ctx);
 extern "C" int                 eb200_ctx_has_comm(const eb200_ctx_t* ctx);
+extern "C" int                 eb200_ctx_sort_flags(const eb200_ctx_t* ctx);
 
 namespace eb200 {
   namespace srpic {
@@ -357,7 +361,7 @@ namespace eb200 {
         if (sp.npart == 0) continue;
         uint32_t n = sp.npart;
         // i*_prev / dx*_prev are dead values here (rewritten by the next push before any read)
-        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | EB200_SORT_SKIP_PREV,
+        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | EB200_SORT_SKIP_PREV | eb200_ctx_sort_flags(dom.ctx),
                                  dom.stream));
         sp.npart = n;
       }
@@ -402,6 +406,15 @@ namespace eb200 {
     }
 
     // SRPICEngine::step_forward, srpic.hpp:65-188
+    // srpic::ParticleInjector (particles_bcs.h:155-166): the atmosphere face registered with
+    // the context; buff component 0 is the density plane (the reference uses bckp)
+    int ParticleInjector(Domain& dom, uint32_t step) {
+      EngineState* e = eb200_ctx_engine_state(dom.ctx);
+      if (!e->has_atm) return EB200_OK;
+      return eb200_atmosphere_particles(dom.ctx, &e->atm, dom.species, dom.nspecies, dom.buff, 0,
+                                        step, dom.stream);
+    }
+
     int step_forward(Domain& dom, uint32_t step, double time) {
       const eb200_srpic_params_t& p = *dom.prm;
       if (step == 0) {
@@ -410,6 +423,7 @@ namespace eb200 {
           TRY(eb200_comm_fields(dom.ctx, dom.em, 6, 0, 6, p.fbc, dom.stream));
         }
         TRY(FieldBoundaries(dom, EB200_BC_B | EB200_BC_E));
+        TRY(ParticleInjector(dom, step)); // srpic.hpp:81
       }
       if (p.fieldsolver_enabled) {
         {
@@ -472,6 +486,7 @@ namespace eb200 {
         }
         TRY(FieldBoundaries(dom, EB200_BC_E));
       }
+      TRY(ParticleInjector(dom, step)); // srpic.hpp:179-183
       {
         PHASE(dom, EB200_PHASE_SORT);
         TRY(SortParticles(dom, step));
@@ -651,7 +666,7 @@ namespace eb200 {
         eb200_species_t& sp = dom.species[s];
         if (sp.npart == 0) continue;
         uint32_t n = sp.npart;
-        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | EB200_SORT_SKIP_PREV,
+        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | EB200_SORT_SKIP_PREV | eb200_ctx_sort_flags(dom.ctx),
                                  dom.stream));
         sp.npart = n;
       }
@@ -858,6 +873,21 @@ extern "C" int eb200_srpic_set_ext_current(eb200_ctx_t* ctx, const eb200_ext_cur
   if (ext->nmodes < 0 || ext->nmodes > EB200_MAX_MODES) return EB200_ERR_ARG;
   e->ext     = *ext;
   e->has_ext = true;
+  return EB200_OK;
+}
+
+extern "C" int eb200_srpic_set_atmosphere_injector(eb200_ctx_t* ctx, const eb200_atmosphere_t* atm) {
+  if (!ctx) return EB200_ERR_ARG;
+  eb200::EngineState* e = eb200_ctx_engine_state(ctx);
+  if (atm == nullptr) {
+    e->has_atm = false;
+    return EB200_OK;
+  }
+  if (atm->dim < 0 || atm->dim > 2 || atm->sign == 0 || atm->density <= 0.0f || atm->height <= 0.0f) {
+    return EB200_ERR_ARG;
+  }
+  e->atm     = *atm;
+  e->has_atm = true;
   return EB200_OK;
 }
 

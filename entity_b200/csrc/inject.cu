@@ -23,6 +23,7 @@
 // cell order (the reference's atomic slot counter makes the order non-deterministic).
 #include "common.cuh"
 #include "launch.h"
+#include "metrics.cuh"
 
 #include <cub/device/device_scan.cuh>
 
@@ -143,17 +144,57 @@ namespace eb200 {
       int      sd_kind;     // EB200_SDIST_*
       const float* field;   // table / density moment, component plane `comp` selected by the host
       float    target;
+      const float* target_field; // REPLENISH_TABLE
+      float    target_max;
+      int      atm_dim, atm_sign; // ATMOSPHERE
+      float    atm_nmax, atm_height, atm_xsurf, atm_ds;
+      float    dx, xmin[3];  // Minkowski: x_Ph = (cell + 1/2) dx + xmin
+      float    inv_V0;
       uint64_t seed;
       uint32_t step, call;
     };
 
-    // spatial_dist(cell centre) of the built-in kinds
-    __device__ float spatial_value(const InjArgs& A, long node) {
+    // arch::AtmosphereDensityProfile<D, C, P, O>::operator() (particle_injector.h:151-189); xi =
+    // the physical coordinate of the cell centre along the boundary's dimension
+    template <bool CURV>
+    __device__ float atmosphere_profile(const InjArgs& A, float xi) {
+      if (A.atm_sign > 0) {
+        if (xi < A.atm_xsurf - A.atm_ds || xi >= A.atm_xsurf) return ZERO;
+        return A.atm_nmax * expf(-(A.atm_xsurf - xi) / A.atm_height); // Cartesian only (checked on the host)
+      }
+      if (xi < A.atm_xsurf || xi >= A.atm_xsurf + A.atm_ds) return ZERO;
+      if constexpr (!CURV) {
+        return A.atm_nmax * expf(-(xi - A.atm_xsurf) / A.atm_height);
+      } else {
+        return A.atm_nmax * expf(-(A.atm_xsurf / A.atm_height) * (ONE - (A.atm_xsurf / xi)));
+      }
+    }
+
+    // spatial_dist(cell centre) of the built-in kinds; c = ghost-inclusive cell indices
+    template <bool CURV, class M>
+    __device__ float spatial_value(const InjArgs& A, const MetricParams& mp, const int* c, long node) {
       if (A.sd_kind == EB200_SDIST_UNIFORM) return ONE;
       const float f = A.field[node];
       if (A.sd_kind == EB200_SDIST_TABLE) return f;
-      // ReplenishUniform (spatial_dist.h:104-124)
-      return (0.9f * A.target > f) ? (A.target - f) / A.target : ZERO;
+      if (A.sd_kind == EB200_SDIST_REPLENISH) {
+        // ReplenishUniform (spatial_dist.h:104-124)
+        return (0.9f * A.target > f) ? (A.target - f) / A.target : ZERO;
+      }
+      // Replenish<M, N, T> (spatial_dist.h:56-80)
+      float target;
+      if (A.sd_kind == EB200_SDIST_REPLENISH_TABLE) {
+        target = A.target_field[node];
+      } else {
+        const float xc = static_cast<float>(c[A.atm_dim] - A.G) + HALF;
+        float       xi;
+        if constexpr (!CURV) {
+          xi = xc * A.dx + A.xmin[A.atm_dim];
+        } else {
+          xi = (A.atm_dim == 0) ? M::r(mp, xc) : M::theta(mp, xc);
+        }
+        target = atmosphere_profile<CURV>(A, xi);
+      }
+      return (0.9f * target > f) ? (target - f) / A.target_max : ZERO;
     }
 
     __device__ void cell_of_range(const InjArgs& A, long t, int* c, long& node) {
@@ -164,15 +205,17 @@ namespace eb200 {
     }
 
     // pass 1: NonUniformInjector_kernel::injected_ppc (injectors.hpp:616-633) per cell
+    template <bool CURV, class M>
     __global__ void __launch_bounds__(256)
-      inject_count_kernel(const __grid_constant__ InjArgs A, uint32_t* __restrict__ counts) {
+      inject_count_kernel(const __grid_constant__ InjArgs A, const MetricParams mp,
+                          uint32_t* __restrict__ counts) {
       const long t     = (long)blockIdx.x * blockDim.x + threadIdx.x;
       const long total = (long)A.n[0] * A.n[1] * A.n[2];
       if (t >= total) return;
       int  c[3];
       long node;
       cell_of_range(A, t, c, node);
-      const float ppc_real = A.ppc0 * spatial_value(A, node);
+      const float ppc_real = A.ppc0 * spatial_value<CURV, M>(A, mp, c, node);
       uint32_t    ppc      = (uint32_t)ppc_real;
       Philox      g(A.seed, A.step, A.call, (uint32_t)t);
       if (g.uniform() < ppc_real - (float)ppc) ppc += 1;
@@ -180,8 +223,10 @@ namespace eb200 {
     }
 
     // pass 2: the particles of every cell, at the cell's offset of the exclusive scan
+    template <bool CURV, class M>
     __global__ void __launch_bounds__(256)
-      inject_fill_kernel(const __grid_constant__ InjArgs A, const uint32_t* __restrict__ counts,
+      inject_fill_kernel(const __grid_constant__ InjArgs A, const MetricParams mp,
+                         const uint32_t* __restrict__ counts,
                          const uint32_t* __restrict__ offsets, eb200_prtls_t S1, eb200_prtls_t S2,
                          uint32_t off1, uint32_t off2, Maxwell m1, Maxwell m2) {
       const long t     = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,15 +248,31 @@ namespace eb200 {
       float*         q1[2] = { S1.dx1_prev, S2.dx1_prev }, *q2[2] = { S1.dx2_prev, S2.dx2_prev },
             *q3[2] = { S1.dx3_prev, S2.dx3_prev };
       float*         w[2]   = { S1.weight, S2.weight };
+      float*         phi[2] = { S1.phi, S2.phi };
       short*         tag[2] = { S1.tag, S2.tag };
       const uint32_t off[2] = { off1, off2 };
       const Maxwell* mm[2]  = { &m1, &m2 };
+      // curvilinear: weight *= sqrt_det_h(cell centre) / V0 (injectors.hpp:746-748); velocities are
+      // drawn in the tetrad basis and stored Cartesian at (centre, phi = 0) (:758-764)
+      float weight = ONE;
+      Trig  trig {};
+      if constexpr (CURV) {
+        const float xc[3] = { static_cast<float>(c[0] - A.G) + HALF,
+                              static_cast<float>(c[1] - A.G) + HALF, ZERO };
+        weight *= M::sqrt_det_h(mp, xc[0], xc[1]) * A.inv_V0;
+        trig = trig_at<M>(mp, xc);
+      }
       for (uint32_t k = 0; k < ppc; ++k) {
         float dx[3] = { ZERO, ZERO, ZERO };
         for (int a = 0; a < A.dim; ++a) dx[a] = g.uniform();
         for (int s = 0; s < 2; ++s) {
           float v[3];
           sample(g, *mm[s], v);
+          if constexpr (CURV) {
+            float vx[3];
+            tetrad_to_xyz(trig, v, vx);
+            v[0] = vx[0], v[1] = vx[1], v[2] = vx[2];
+          }
           const size_t p = (size_t)off[s] + base + k;
           i1[s][p] = c[0] - A.G, d1[s][p] = dx[0];
           p1[s][p] = c[0] - A.G, q1[s][p] = dx[0];
@@ -224,26 +285,44 @@ namespace eb200 {
             p3[s][p] = c[2] - A.G, q3[s][p] = dx[2];
           }
           u1[s][p] = v[0], u2[s][p] = v[1], u3[s][p] = v[2];
-          w[s][p]   = ONE;
+          w[s][p]   = weight;
           tag[s][p] = 1;
+          if constexpr (CURV) {
+            if (phi[s]) phi[s][p] = ZERO;
+          }
         }
       }
     }
 
-    // ParticleMoments_kernel<S, Minkowski<D>, F, N>::operator() with window 0
-    // (particle_moments.hpp:293-345): contrib * inv_n0 / sqrt_det_h (* weight) into the cell
+    // ParticleMoments_kernel<S, M, F, N>::operator() with window 0 (particle_moments.hpp:293-345):
+    // contrib * inv_n0 / sqrt_det_h(cell centre) (* weight) into the particle's cell.
+    // KIND 0: Minkowski (the constant volume element is folded into coeff by the host)
+    template <int KIND, class M>
     __global__ void __launch_bounds__(256)
       moment_kernel(eb200_prtls_t S, uint32_t npart, int dim, int G, long N1, long N12, float coeff,
-                    bool use_weights, float* __restrict__ plane) {
-      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-      if (p >= npart) return;
-      if (S.tag[p] == 0) return;
-      float c = coeff;
-      if (use_weights) c *= S.weight[p];
-      long node = S.i1[p] + G;
-      if (dim > 1) node += (long)(S.i2[p] + G) * N1;
-      if (dim > 2) node += (long)(S.i3[p] + G) * N12;
-      atomicAdd(plane + node, c);
+                    bool use_weights, bool volume, const MetricParams mp, float* __restrict__ plane) {
+      // whole warps stay: consecutive (nearly cell-sorted) particles of the same cell are summed
+      // with a segmented shuffle reduction and the run's head lane issues one atomic
+      const uint32_t p     = blockIdx.x * blockDim.x + threadIdx.x;
+      const bool     alive = (p < npart) && (S.tag[p] != 0);
+      float          c     = ZERO;
+      long           node  = -1 - (long)(threadIdx.x & 31u); // distinct keys for idle lanes
+      if (alive) {
+        c = coeff;
+        if constexpr (KIND != 0) {
+          if (volume) {
+            c = c / M::sqrt_det_h(mp, static_cast<float>(S.i1[p]) + HALF,
+                                  static_cast<float>(S.i2[p]) + HALF);
+          }
+        }
+        if (use_weights) c *= S.weight[p];
+        node = S.i1[p] + G;
+        if (dim > 1) node += (long)(S.i2[p] + G) * N1;
+        if (dim > 2) node += (long)(S.i3[p] + G) * N12;
+      }
+      const LaneRun r   = lane_run(node);
+      const float   sum = lane_run_sum(c, r);
+      if (r.head && alive) atomicAdd(plane + node, sum);
     }
   } // namespace
 
@@ -271,14 +350,15 @@ namespace eb200 {
     return m;
   }
 
-  cudaError_t inject_nonuniform(const eb200_grid_t& g, const eb200_prtls_t& S1, uint32_t npart1,
+  cudaError_t inject_nonuniform(const eb200_grid_t& g, const MetricParams* mp, float dx,
+                                const float* xmin, const eb200_prtls_t& S1, uint32_t npart1,
                                 uint32_t cap1, const eb200_prtls_t& S2, uint32_t npart2,
-                                uint32_t cap2, float ppc0, int sd_kind, const float* field,
-                                float target, const eb200_maxwellian_t& e1,
+                                uint32_t cap2, float ppc0, const eb200_spatial_dist_t& sd,
+                                const float* field, const eb200_maxwellian_t& e1,
                                 const eb200_maxwellian_t& e2, const int* rmin, const int* rmax,
                                 uint64_t seed, uint32_t step, uint32_t call, uint32_t* n_inj_host,
                                 int* overflow, Scratch& scratch, cudaStream_t st) {
-    InjArgs A;
+    InjArgs A {};
     long    total = 1;
     for (int a = 0; a < 3; ++a) {
       A.lo[a] = (a < g.dim) ? rmin[a] : 0;
@@ -288,11 +368,18 @@ namespace eb200 {
         return cudaSuccess;
       }
       total *= A.n[a];
+      A.xmin[a] = xmin ? xmin[a] : ZERO;
     }
     A.dim = g.dim, A.G = g.ng;
     A.N1 = g.n[0] + 2 * g.ng;
     A.N12 = (g.dim > 1) ? A.N1 * (g.n[1] + 2 * g.ng) : 0;
-    A.ppc0 = ppc0, A.sd_kind = sd_kind, A.field = field, A.target = target;
+    A.ppc0 = ppc0, A.sd_kind = sd.kind, A.field = field, A.target = sd.target_density;
+    A.target_field = sd.target_field;
+    A.target_max   = (sd.kind == EB200_SDIST_ATMOSPHERE) ? sd.atm_nmax : sd.target_max;
+    A.atm_dim = sd.atm_dim, A.atm_sign = sd.atm_sign;
+    A.atm_nmax = sd.atm_nmax, A.atm_height = sd.atm_height;
+    A.atm_xsurf = sd.atm_xsurf, A.atm_ds = sd.atm_ds;
+    A.dx = dx, A.inv_V0 = sd.inv_V0;
     A.seed = seed, A.step = step, A.call = call;
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)total + 1, st);
@@ -305,7 +392,15 @@ namespace eb200 {
     const unsigned nb = (unsigned)((total + 255) / 256);
     e = cudaMemsetAsync(counts + total, 0, 4, st);
     if (e != cudaSuccess) return e;
-    inject_count_kernel<<<nb, 256, 0, st>>>(A, counts);
+    const int          kind = mp ? mp->kind : EB200_METRIC_MINKOWSKI;
+    MetricParams       m0 {};
+    const MetricParams& m = mp ? *mp : m0;
+    switch (kind) {
+      case EB200_METRIC_MINKOWSKI: inject_count_kernel<false, Spherical><<<nb, 256, 0, st>>>(A, m, counts); break;
+      case EB200_METRIC_SPHERICAL: inject_count_kernel<true, Spherical><<<nb, 256, 0, st>>>(A, m, counts); break;
+      case EB200_METRIC_QSPHERICAL: inject_count_kernel<true, QSpherical><<<nb, 256, 0, st>>>(A, m, counts); break;
+      default: return cudaErrorInvalidValue;
+    }
     count_launch();
     e = cub::DeviceScan::ExclusiveSum(ws, tmp, counts, offsets, (int)total + 1, st);
     if (e != cudaSuccess) return e;
@@ -318,18 +413,39 @@ namespace eb200 {
     *n_inj_host = n_inj;
     *overflow   = ((uint64_t)npart1 + n_inj > cap1) || ((uint64_t)npart2 + n_inj > cap2);
     if (*overflow || n_inj == 0) return cudaSuccess;
-    inject_fill_kernel<<<nb, 256, 0, st>>>(A, counts, offsets, S1, S2, npart1, npart2,
-                                           make_maxwell(e1), make_maxwell(e2));
+    const Maxwell mx1 = make_maxwell(e1), mx2 = make_maxwell(e2);
+#define FILL(C, MM) inject_fill_kernel<C, MM><<<nb, 256, 0, st>>>(A, m, counts, offsets, S1, S2, npart1, npart2, mx1, mx2)
+    switch (kind) {
+      case EB200_METRIC_MINKOWSKI: FILL(false, Spherical); break;
+      case EB200_METRIC_SPHERICAL: FILL(true, Spherical); break;
+      case EB200_METRIC_QSPHERICAL: FILL(true, QSpherical); break;
+      default: return cudaErrorInvalidValue;
+    }
+#undef FILL
     count_launch();
     return cudaGetLastError();
   }
 
-  cudaError_t particle_moment(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
-                              float coeff, bool use_weights, float* plane, cudaStream_t st) {
+  cudaError_t particle_moment(const eb200_grid_t& g, const MetricParams* mp, const eb200_prtls_t& S,
+                              uint32_t npart, float coeff, bool use_weights, bool volume,
+                              float* plane, cudaStream_t st) {
     if (npart == 0) return cudaSuccess;
     const long N1 = g.n[0] + 2 * g.ng, N12 = (g.dim > 1) ? N1 * (g.n[1] + 2 * g.ng) : 0;
-    moment_kernel<<<(npart + 255) / 256, 256, 0, st>>>(S, npart, g.dim, g.ng, N1, N12, coeff,
-                                                       use_weights, plane);
+    const unsigned nb   = (npart + 255) / 256;
+    const int      kind = mp ? mp->kind : EB200_METRIC_MINKOWSKI;
+    MetricParams   m0 {};
+    const MetricParams& m = mp ? *mp : m0;
+#define RUN(K, MM) moment_kernel<K, MM><<<nb, 256, 0, st>>>(S, npart, g.dim, g.ng, N1, N12, coeff, use_weights, volume, m, plane)
+    switch (kind) {
+      case EB200_METRIC_MINKOWSKI: RUN(0, Spherical); break;
+      case EB200_METRIC_SPHERICAL: RUN(1, Spherical); break;
+      case EB200_METRIC_QSPHERICAL: RUN(1, QSpherical); break;
+      case EB200_METRIC_KERR_SCHILD: RUN(1, KerrSchild); break;
+      case EB200_METRIC_QKERR_SCHILD: RUN(1, QKerrSchild); break;
+      case EB200_METRIC_KERR_SCHILD_0: RUN(1, KerrSchild0); break;
+      default: return cudaErrorInvalidValue;
+    }
+#undef RUN
     count_launch();
     return cudaGetLastError();
   }

@@ -98,18 +98,20 @@ namespace eb200 {
   EB200_DECLARE_VARIANT(fast_fp)
 
   // injection and per-cell moments (inject.cu)
-  cudaError_t inject_nonuniform(const eb200_grid_t& g, const eb200_prtls_t& S1, uint32_t npart1,
+  struct MetricParams;
+  cudaError_t inject_nonuniform(const eb200_grid_t& g, const MetricParams* mp, float dx,
+                                const float* xmin, const eb200_prtls_t& S1, uint32_t npart1,
                                 uint32_t cap1, const eb200_prtls_t& S2, uint32_t npart2,
-                                uint32_t cap2, float ppc0, int sd_kind, const float* field,
-                                float target, const eb200_maxwellian_t& e1,
+                                uint32_t cap2, float ppc0, const eb200_spatial_dist_t& sd,
+                                const float* field, const eb200_maxwellian_t& e1,
                                 const eb200_maxwellian_t& e2, const int* rmin, const int* rmax,
                                 uint64_t seed, uint32_t step, uint32_t call, uint32_t* n_inj_host,
                                 int* overflow, Scratch& scratch, cudaStream_t st);
-  cudaError_t particle_moment(const eb200_grid_t& g, const eb200_prtls_t& S, uint32_t npart,
-                              float coeff, bool use_weights, float* plane, cudaStream_t st);
+  cudaError_t particle_moment(const eb200_grid_t& g, const MetricParams* mp, const eb200_prtls_t& S,
+                              uint32_t npart, float coeff, bool use_weights, bool volume,
+                              float* plane, cudaStream_t st);
 
   // output staging (output.cu)
-  struct MetricParams;
   cudaError_t fields_to_phys(const MetricParams* mp, const eb200_grid_t& g, float dx,
                              const float* from, int ncomp_from, float* to, int ncomp_to,
                              const int* cf, const int* ct, int interp, int conv, cudaStream_t st);

@@ -104,7 +104,7 @@ class MatchFaceC(C.Structure):
                 ("range_min", C.c_int * 3), ("range_max", C.c_int * 3)]
 
 
-SDIST_UNIFORM, SDIST_TABLE, SDIST_REPLENISH = 0, 1, 2
+SDIST_UNIFORM, SDIST_TABLE, SDIST_REPLENISH, SDIST_REPLENISH_TABLE, SDIST_ATMOSPHERE = 0, 1, 2, 3, 4
 
 
 class MaxwellianC(C.Structure):
@@ -115,7 +115,18 @@ class MaxwellianC(C.Structure):
 class SpatialDistC(C.Structure):
     """eb200_spatial_dist_t"""
     _fields_ = [("kind", C.c_int), ("field", C.c_void_p), ("comp", C.c_int),
-                ("target_density", C.c_float)]
+                ("target_density", C.c_float), ("target_field", C.c_void_p),
+                ("target_max", C.c_float), ("atm_dim", C.c_int), ("atm_sign", C.c_int),
+                ("atm_nmax", C.c_float), ("atm_height", C.c_float), ("atm_xsurf", C.c_float),
+                ("atm_ds", C.c_float), ("inv_V0", C.c_float)]
+
+
+class AtmosphereC(C.Structure):
+    """eb200_atmosphere_t"""
+    _fields_ = [("dim", C.c_int), ("sign", C.c_int), ("x_surf", C.c_float), ("ds", C.c_float),
+                ("height", C.c_float), ("temperature", C.c_float), ("density", C.c_float),
+                ("species", C.c_int * 2), ("inv_n0", C.c_float), ("inv_V0", C.c_float),
+                ("ppc0", C.c_float), ("seed", C.c_uint64)]
 
 
 MAX_MODES = 16

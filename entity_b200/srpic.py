@@ -171,9 +171,12 @@ class Simulation:
 
     def inject_nonuniform(self, pair, ppc, sdist_kind=L.SDIST_UNIFORM, field=None, comp=0,
                           target=1.0, temperatures=(0.0, 0.0), drifts=((0, 0, 0), (0, 0, 0)),
-                          range_min=None, range_max=None, seed=0x123456789abcdef0, call=0):
+                          range_min=None, range_max=None, seed=0x123456789abcdef0, call=0,
+                          target_field=None, target_max=0.0, atmosphere=None):
         """arch::InjectNonUniform for the species pair (0-based indices); returns the number of
-        pairs injected. ppc = number_density * ppc0 / 2."""
+        pairs injected. ppc = number_density * ppc0 / 2. target_field / target_max: the generic
+        Replenish distribution; atmosphere = dict(dim, sign, nmax, height, xsurf, ds): Replenish
+        with the AtmosphereDensityProfile."""
         if self._species_c is None:
             self._species_c = self._pack_species()
         arr = self._species_c
@@ -185,6 +188,13 @@ class Simulation:
         sd = L.SpatialDistC()
         sd.kind, sd.comp, sd.target_density = sdist_kind, comp, target
         sd.field = field.data_ptr() if field is not None else None
+        sd.target_field = target_field.data_ptr() if target_field is not None else None
+        sd.target_max = target_max
+        sd.inv_V0 = 1.0 / self.scales["V0"]
+        if atmosphere is not None:
+            sd.atm_dim, sd.atm_sign = atmosphere["dim"], atmosphere["sign"]
+            sd.atm_nmax, sd.atm_height = atmosphere["nmax"], atmosphere["height"]
+            sd.atm_xsurf, sd.atm_ds = atmosphere["xsurf"], atmosphere["ds"]
         eds = []
         for t, d in zip(temperatures, drifts):
             e = L.MaxwellianC()
@@ -200,6 +210,41 @@ class Simulation:
         for k in pair:
             self.species[k].npart = int(arr[k].npart)
         return int(arr[pair[0]].npart) - n0
+
+    def _atmosphere_c(self, atm, seed=0x123456789abcdef0):
+        """dict(dim, sign, x_surf, ds, height, temperature, density, species) -> eb200_atmosphere_t"""
+        a = L.AtmosphereC()
+        a.dim, a.sign = atm["dim"], atm["sign"]
+        a.x_surf, a.ds, a.height = atm["x_surf"], atm["ds"], atm["height"]
+        a.temperature, a.density = atm["temperature"], atm["density"]
+        a.species = (C.c_int * 2)(*atm["species"])
+        a.inv_n0, a.inv_V0 = 1.0 / self.scales["n0"], 1.0 / self.scales["V0"]
+        a.ppc0, a.seed = self.scales["ppc0"], atm.get("seed", seed)
+        return a
+
+    def atmosphere_particles(self, atm, plane=None, assume_empty=False):
+        """srpic::AtmosphereParticlesIn (eb200_atmosphere_particles); returns pairs injected"""
+        if self._species_c is None:
+            self._species_c = self._pack_species()
+        arr = self._species_c
+        for k, sp in enumerate(self.species):
+            arr[k].npart = sp.npart
+        plane = self.buff if plane is None else plane
+        a = self._atmosphere_c(atm)
+        k0 = atm["species"][0]
+        n0 = int(arr[k0].npart)
+        self.ctx._check(self.ctx.lib.eb200_atmosphere_particles(
+            self.ctx.handle, C.byref(a), arr, len(self.species), C.c_void_p(plane.data_ptr()),
+            int(assume_empty), self.step_index, L.Context._stream(None)))
+        for k, sp in enumerate(self.species):
+            sp.npart = int(arr[k].npart)
+        return int(arr[k0].npart) - n0
+
+    def set_atmosphere_injector(self, atm):
+        """Registers the atmosphere injector of the step (None clears it)"""
+        self._atm_c = self._atmosphere_c(atm) if atm is not None else None
+        self.ctx._check(self.ctx.lib.eb200_srpic_set_atmosphere_injector(
+            self.ctx.handle, C.byref(self._atm_c) if atm is not None else None))
 
     def replenish(self, boxes, pair=(0, 1), temperature=1e-4, target=1.0):
         """pgens/reconnection/pgen.hpp:222-278 (CustomPostStep): the mass density of the pair into

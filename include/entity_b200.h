@@ -298,8 +298,20 @@ int eb200_comm_init(eb200_ctx_t* ctx, const eb200_metadomain_t* md, const char* 
  * (srpic.hpp:184-186): eb200_srpic_step sorts this way; a host that reads them after a sort
  * (a checkpoint of the raw arrays) passes the plain flags. */
 #define EB200_SORT_SKIP_PREV 2
+/* remove_dead | EB200_SORT_UNSTABLE: counting sort by cell (histogram, scan, slot assignment: 18 B
+ * per particle for the permutation instead of the radix sort's 60 B). Particles are grouped by
+ * cell as before and not-alive ones go last, but the order INSIDE a cell is unspecified and not
+ * reproducible from run to run -- as in the reference, whose sort assigns slots with atomics
+ * (particles_sort.cpp:118-147). eb200_srpic_step sorts this way on fast-build contexts
+ * (strict_fp = 0), whose deposit sums are unordered anyway; strict contexts keep the stable
+ * radix sort (bit-reproducible ORDERED deposit). eb200_set_sort_mode overrides. */
+#define EB200_SORT_UNSTABLE 4
 int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls,
                          uint32_t* npart_inout_host, int remove_dead, eb200_stream_t stream);
+
+/* Sort used by the step mirrors: -1 = by build (default: counting on fast, radix on strict),
+ * 0 = stable radix sort, 1 = counting sort. */
+int eb200_set_sort_mode(eb200_ctx_t* ctx, int mode);
 
 /* ------------------------------------------------------------- field boundaries */
 /* kernel::bc::MatchBoundaries_kernel<SRPIC, Minkowski<D>, FS, o> (src/kernels/fields_bcs.hpp:
@@ -614,22 +626,37 @@ typedef struct {
 enum {
   EB200_SDIST_UNIFORM   = 0, /* spatial_dist = 1 (what arch::InjectUniform draws in expectation) */
   EB200_SDIST_TABLE     = 1, /* field = the functor's value at every cell centre */
-  EB200_SDIST_REPLENISH = 2  /* arch::spatial_dist::ReplenishUniform (spatial_dist.h:87-125):
+  EB200_SDIST_REPLENISH = 2, /* arch::spatial_dist::ReplenishUniform (spatial_dist.h:87-125):
                                 field = density moment, refilled up to target_density where it
                                 fell below 0.9 of it */
+  EB200_SDIST_REPLENISH_TABLE = 3, /* arch::spatial_dist::Replenish<M, N, T> (spatial_dist.h:
+                                28-81): (target - density) / target_max where density < 0.9
+                                target; target_field = the target functor at every cell centre */
+  EB200_SDIST_ATMOSPHERE = 4 /* Replenish with arch::AtmosphereDensityProfile (particle_injector.h:
+                                141-190) evaluated in the kernel: atm_* below, target_max =
+                                atm_nmax */
 };
 typedef struct {
   int          kind;
   const float* field; /* device: component plane(s) in the mesh layout (ghost-inclusive) */
   int          comp;  /* component of `field` to read */
   float        target_density;
+  const float* target_field; /* REPLENISH_TABLE: one plane, mesh layout */
+  float        target_max;
+  int          atm_dim, atm_sign; /* ATMOSPHERE: direction of the boundary (dim 0..2, sign -1 / +1) */
+  float        atm_nmax, atm_height, atm_xsurf, atm_ds;
+  float        inv_V0; /* 1 / scales.V0: weight = sqrt_det_h(cell centre) * inv_V0 on curvilinear
+                          meshes (injectors.hpp:746-748); unused on Minkowski meshes */
 } eb200_spatial_dist_t;
 /* arch::InjectNonUniform (src/archetypes/particle_injector.h:296-387) with
- * kernel::NonUniformInjector_kernel (src/kernels/injectors.hpp:526-859) on a Minkowski domain:
- * in every cell of the ghost-inclusive range, ppc = number_density * ppc0 / 2 * spatial_dist pairs
- * (the fraction rounded stochastically), both species of a pair at the same position, velocities
- * from ed1 / ed2, weight 1, appended at npart of either species (both npart grow by the same
- * number; returns EB200_ERR_CAPACITY and injects nothing when maxnpart would be exceeded).
+ * kernel::NonUniformInjector_kernel (src/kernels/injectors.hpp:526-859) on a Minkowski or a 2D
+ * (q)spherical SRPIC domain: in every cell of the ghost-inclusive range, ppc = number_density *
+ * ppc0 / 2 * spatial_dist pairs (the fraction rounded stochastically), both species of a pair at
+ * the same position, velocities from ed1 / ed2 (curvilinear: drawn in the tetrad basis at the
+ * cell centre and stored Cartesian, transform_xyz<T, XYZ> with phi = 0; phi = 0), weight 1
+ * (curvilinear: sqrt_det_h(cell centre) / V0), appended at npart of either species (both npart
+ * grow by the same number; returns EB200_ERR_CAPACITY and injects nothing when maxnpart would be
+ * exceeded).
  * Every cell draws from its own counter-based Philox4x32-10 stream keyed by (seed, step, call,
  * cell): the result is a pure function of the arguments, identical on every device and for
  * every launch shape; `call` distinguishes several injections of one step. Synchronises the
@@ -640,13 +667,38 @@ int eb200_inject_nonuniform(eb200_ctx_t* ctx, eb200_species_t* species1, eb200_s
                             const int* range_min, const int* range_max, uint64_t seed,
                             uint32_t step, uint32_t call, eb200_stream_t stream);
 /* arch::ComputeMomentWithSpecies / kernel::ParticleMoments_kernel (src/archetypes/utils.h:
- * 136-169, src/kernels/particle_moments.hpp:37-419) on a Minkowski domain for the scalar
- * moments what = EB200_STATS_N | RHO | CHARGE | NPART (Nppc), smoothing order 0 (the
- * archetypes' default): adds one species into component comp of buff (ncomp planes; the host
- * zeroes it once, as ComputeMomentWithSpecies does before its species loop). */
+ * 136-169, src/kernels/particle_moments.hpp:37-419) for the scalar moments what =
+ * EB200_STATS_N | RHO | CHARGE | NPART (Nppc), smoothing order 0 (the archetypes' default), any
+ * metric of the context (the volume element is sqrt_det_h at the particle's cell centre,
+ * particle_moments.hpp:306-327): adds one species into component comp of buff (ncomp planes; the
+ * host zeroes it once, as ComputeMomentWithSpecies does before its species loop). */
 int eb200_particle_moment(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, float mass,
                           float charge, int use_weights, int what, float inv_n0, float* buff,
                           int ncomp, int comp, eb200_stream_t stream);
+
+/* srpic::AtmosphereParticlesIn (src/engines/srpic/particles_bcs.h:33-153), what
+ * srpic::ParticleInjector runs for a face whose particle boundary is ATMOSPHERE: the Rho moment
+ * of the two species into one plane, then InjectNonUniform<Replenish<AtmosphereDensityProfile>>
+ * with two Maxwellians of the atmosphere's temperature over the active cells. */
+typedef struct {
+  int      dim, sign;        /* the face: direction.get_dim(), direction.get_sign() */
+  float    x_surf, ds;       /* GetAtmosphereExtent (src/engines/srpic/utils.h:47-103): x_surf =
+                                xg_min (sign > 0) or xg_max; grid.boundaries.atmosphere.ds */
+  float    height, temperature, density; /* grid.boundaries.atmosphere.{height, temperature, density} */
+  int      species[2];       /* 0-based indices of grid.boundaries.atmosphere.species */
+  float    inv_n0, inv_V0, ppc0; /* 1 / scales.n0, 1 / scales.V0, particles.ppc0 */
+  uint64_t seed;             /* of the counter-based streams (eb200_inject_nonuniform) */
+} eb200_atmosphere_t;
+/* plane: scratch of one component plane (the reference uses bckp component 0). assume_empty =
+ * Inj::AssumeEmpty (density taken as zero). npart of both species updated in place. */
+int eb200_atmosphere_particles(eb200_ctx_t* ctx, const eb200_atmosphere_t* atm,
+                               eb200_species_t* species, int nspecies, float* plane,
+                               int assume_empty, uint32_t step, eb200_stream_t stream);
+/* Registers (atm != NULL) or clears the atmosphere injector of eb200_srpic_step: it then runs
+ * where SRPICEngine::step_forward calls srpic::ParticleInjector (srpic.hpp:81, 179-183: at step 0
+ * after the first FieldBoundaries, and at the end of every step before the sort), with buff
+ * component 0 as the density plane. */
+int eb200_srpic_set_atmosphere_injector(eb200_ctx_t* ctx, const eb200_atmosphere_t* atm);
 
 /* ------------------------------------------------ output staging */
 /* kernel::FieldsToPhys_kernel<M, N1, N2> over Mesh::rangeActiveCells (src/kernels/

@@ -257,6 +257,34 @@ def test_sort_payloads_and_skip_prev(eb, orc_mod):
                 assert np.array_equal(arr[k].cpu().numpy(), getattr(p, k)[perm]), k
 
 
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_sort_particles_counting(eb, orc_mod, dim):
+    """EB200_SORT_UNSTABLE: grouped by cell (i1 fastest), not-alive last, the same multiset of
+    particles with every array and payload still attached to its particle; the order inside a
+    cell is unspecified. Also through the fallback (more cells than twice the particles)."""
+    import torch
+    g = orc_mod.Grid.make(DIMS[dim], 2)
+    for n in (50000, 64):  # 64: fewer particles than cells / 2 -> the radix fallback
+        ctx = eb.Context(DIMS[dim], order=0)
+        p = random_particles(g, n, 13 + n % 7, dead_frac=0.2)
+        arr = to_device(p)
+        arr["pld_i"] = torch.arange(n, dtype=torch.int32, device="cuda").reshape(1, -1).contiguous()
+        n_alive = ctx.sort_particles(arr, n, remove_dead=1 | 4)
+        assert n_alive == int((p.tag == 1).sum())
+        q = to_host(arr, n)
+        assert (q.tag[:n_alive] == 1).all() and (q.tag[n_alive:] != 1).all()
+        key = q.i1.astype(np.int64)
+        if dim > 1:
+            key = key + g.n[0] * q.i2.astype(np.int64)
+        if dim > 2:
+            key = key + g.n[0] * g.n[1] * q.i3.astype(np.int64)
+        assert (np.diff(key[:n_alive]) >= 0).all(), "not grouped by cell"
+        src = arr["pld_i"][0].cpu().numpy()  # where every particle came from
+        assert np.array_equal(np.sort(src), np.arange(n))
+        for nm in p.names():
+            assert np.array_equal(getattr(q, nm), getattr(p, nm)[src]), nm
+
+
 def test_errors(eb):
     with pytest.raises(eb.EB200Error):
         eb.Context((8, 8), order=7)
