@@ -187,8 +187,12 @@ int eb200_init(const eb200_config_t* cfg, eb200_ctx_t** out) {
                 "eb200_init: no CUDA device available (this library has no CPU fallback)");
   }
   if (cfg->grid.dim < 1 || cfg->grid.dim > 3) return fail(nullptr, EB200_ERR_ARG, "eb200_init: dim must be 1..3");
-  if (cfg->shape_order < 0 || cfg->shape_order > 3) {
-    return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_init: shape_order must be 0..3");
+  if (cfg->shape_order < 0 || cfg->shape_order > 11) {
+    return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_init: shape_order must be 0..11");
+  }
+  if (cfg->shape_order > 3 && cfg->metric != EB200_METRIC_MINKOWSKI) {
+    return fail(nullptr, EB200_ERR_UNSUPPORTED,
+                "eb200_init: shape orders 4..11 are built for Minkowski domains");
   }
   if (cfg->metric < EB200_METRIC_MINKOWSKI || cfg->metric > EB200_METRIC_KERR_SCHILD_0) {
     return fail(nullptr, EB200_ERR_UNSUPPORTED, "eb200_init: unknown metric");
@@ -553,6 +557,12 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
   rc = check_prtls(ctx, prtls, npart);
   if (rc) return rc;
   REQUIRE(ctx, em != nullptr && cur != nullptr, "null field");
+  if (ctx->cfg.shape_order > 3) {
+    // shape orders 4..11 have no fused kernel: the same two kernels the unfused step runs
+    rc = eb200_push_sr(ctx, pusher, prtls, npart, em, stream);
+    if (rc) return rc;
+    return eb200_deposit(ctx, prtls, npart, pusher->charge, pusher->dt, cur, mode, stream);
+  }
   float* packed  = nullptr;
   bool   do_pack = false;
   if (uses_packed_nodes(ctx, mode)) {

@@ -35,10 +35,62 @@ namespace eb200 {
     return ZERO;
   }
 
+  // S4 .. S11 (particle_shapes.hpp:60-542): centred cardinal B-splines of degree O. The tables
+  // (scripts/gen_bspline.py, exact rational arithmetic from the closed form) hold every piece
+  // as a polynomial in t = |x| - (left end of the piece), 0 <= t < 1, coefficients of magnitude
+  // <= 1: Horner in fp32 is then accurate to an ulp or two. The reference sums the monomials in
+  // |x| itself, whose terms reach ~9 for a result of ~1e-5 at O = 11: its own weights carry a
+  // cancellation error of up to ~1e-5 there (tests/test_gpu_hiorder.py measures both against
+  // the fp64 closed form).
+  template <int O>
+  struct BSplineCoef;
+#include "bspline_coef.inc"
+
+  template <int O>
+  __device__ __forceinline__ float bspline(float x) {
+    constexpr float first = (O % 2 == 0) ? HALF : ONE;
+    const int       p     = (x < first) ? 0 : static_cast<int>(x - first) + 1;
+    if (p >= BSplineCoef<O>::NP) return ZERO;
+    const float t = (p == 0) ? x : x - (first + static_cast<float>(p - 1));
+    float       r = BSplineCoef<O>::c(p, O);
+#pragma unroll
+    for (int k = O - 1; k >= 0; --k) {
+      r = r * t + BSplineCoef<O>::c(p, k);
+    }
+    return r;
+  }
+
   template <bool STAG, int O>
   __device__ __forceinline__ void shape_w(int i, float di, int& i_min, float (&S)[O + 1]) {
-    static_assert(O >= 1 && O <= 3, "shape orders 1..3");
-    if constexpr (O == 1) {
+    static_assert(O >= 1 && O <= 11, "shape orders 1..11");
+    if constexpr (O >= 4) {
+      // order<STAGGERED, O> for O >= 4 (particle_shapes.hpp:608-932): the window of O + 1 nodes
+      // starts O/2 (rounded by the parity of O, the staggering and di < 1/2) nodes below i
+      float base;
+      if constexpr (O % 2 == 1) {
+        if constexpr (!STAG) {
+          i_min = i - (O - 1) / 2;
+          base  = static_cast<float>((O - 1) / 2) + di;
+        } else {
+          const bool lo = di < HALF;
+          i_min         = lo ? i - (O + 1) / 2 : i - (O - 1) / 2;
+          base          = (lo ? static_cast<float>(O) * HALF : static_cast<float>(O) * HALF - ONE) + di;
+        }
+      } else {
+        if constexpr (!STAG) {
+          const bool lo = di < HALF;
+          i_min         = lo ? i - O / 2 : i - O / 2 + 1;
+          base          = static_cast<float>(lo ? O / 2 : O / 2 - 1) + di;
+        } else {
+          i_min = i - O / 2;
+          base  = static_cast<float>(O - 1) * HALF + di;
+        }
+      }
+#pragma unroll 1
+      for (int n = 0; n <= O; n++) {
+        S[n] = bspline<O>(fabsf(base - static_cast<float>(n)));
+      }
+    } else if constexpr (O == 1) {
       if constexpr (!STAG) {
         i_min = i;
         S[0]  = ONE - di;
@@ -224,6 +276,51 @@ namespace eb200 {
       b0[0] = lerp(bx1, false, true, true, true);
       b0[1] = lerp(bx2, true, false, true, false);
       b0[2] = lerp(bx3, true, true, false, D != 3);
+    } else if constexpr (O > 3) {
+      // orders 4..11: the same sums with rolled loops (up to 12^3 nodes per component)
+      int   pmin[3] = { 0, 0, 0 }, dmin[3] = { 0, 0, 0 };
+      float Sp[3][O + 1], Sd[3][O + 1];
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        shape_w<false, O>(P.i[a] + ng, P.d[a], pmin[a], Sp[a]);
+        shape_w<true, O>(P.i[a] + ng, P.d[a], dmin[a], Sd[a]);
+      }
+      auto spline = [&](int c, bool sx, bool sy, bool sz) -> float {
+        const float* S1  = sx ? Sd[0] : Sp[0];
+        const int    m1  = sx ? dmin[0] : pmin[0];
+        const float* S2  = (D > 1) ? (sy ? Sd[1] : Sp[1]) : S1;
+        const int    m2  = (D > 1) ? (sy ? dmin[1] : pmin[1]) : 0;
+        const float* S3w = (D > 2) ? (sz ? Sd[2] : Sp[2]) : S1;
+        const int    m3  = (D > 2) ? (sz ? dmin[2] : pmin[2]) : 0;
+        float        r   = ZERO;
+#pragma unroll 1
+        for (int q = 0; q < ((D > 2) ? O + 1 : 1); q++) {
+          float c0 = ZERO;
+#pragma unroll 1
+          for (int b = 0; b < ((D > 1) ? O + 1 : 1); b++) {
+            float c00 = ZERO;
+#pragma unroll 1
+            for (int a = 0; a < O + 1; a++) c00 += S1[a] * F(m1 + a, m2 + b, m3 + q, c);
+            if constexpr (D > 1) {
+              c0 += c00 * S2[b];
+            } else {
+              c0 = c00;
+            }
+          }
+          if constexpr (D > 2) {
+            r += c0 * S3w[q];
+          } else {
+            r = c0;
+          }
+        }
+        return r;
+      };
+      e0[0] = spline(ex1, true, false, false);
+      e0[1] = spline(ex2, false, true, false);
+      e0[2] = spline(ex3, false, false, true);
+      b0[0] = spline(bx1, false, true, true);
+      b0[1] = spline(bx2, true, false, true);
+      b0[2] = spline(bx3, true, true, false);
     } else {
       int   pmin[3] = { 0, 0, 0 }, dmin[3] = { 0, 0, 0 };
       float Sp[3][O + 1], Sd[3][O + 1];
@@ -915,6 +1012,118 @@ namespace eb200 {
           J(ci[s] + 1, cj[s], ck[s], jx3, Fl[2][s] * W[0][s] * (ONE - W[1][s]));
           J(ci[s], cj[s] + 1, ck[s], jx3, Fl[2][s] * (ONE - W[0][s]) * W[1][s]);
           J(ci[s] + 1, cj[s] + 1, ck[s], jx3, Fl[2][s] * W[0][s] * W[1][s]);
+        }
+      }
+    } else if constexpr (O > 3) {
+      // orders 4..11: the decomposition below with rolled loops (windows of up to 13^3 nodes)
+      constexpr int N = O + 2;
+      float         iS[3][N], fS[3][N];
+      int           mn[3] = { 0, 0, 0 }, dd[3] = { 0, 0, 0 };
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        int mx;
+        deposit_shapes<O>(P.ip[a], P.dp[a], P.i[a], P.d[a], mn[a], mx, iS[a], fS[a]);
+        mn[a] += G;
+        dd[a] = mx + G - mn[a];
+      }
+      const float Q = coeff * inv_dt;
+      if constexpr (D == 1) {
+        const float QV2 = coeff * vp[1], QV3 = coeff * vp[2];
+        float       acc = ZERO;
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+          acc = (i == 0) ? (-Q * (fS[0][0] - iS[0][0])) : (acc - Q * (fS[0][i] - iS[0][i]));
+          J(mn[0] + i, 0, 0, jx1, acc, i < dd[0]);
+        }
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+          J(mn[0] + i, 0, 0, jx2, QV2 * (HALF * (fS[0][i] + iS[0][i])), i <= dd[0]);
+        }
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+          J(mn[0] + i, 0, 0, jx3, QV3 * (HALF * (fS[0][i] + iS[0][i])), i <= dd[0]);
+        }
+      } else if constexpr (D == 2) {
+        const float QV3 = coeff * vp[2];
+        {
+          float acc[N];
+#pragma unroll 1
+          for (int i = 0; i < N; ++i) {
+#pragma unroll 1
+            for (int j = 0; j < N; ++j) {
+              const float w = HALF * (fS[0][i] - iS[0][i]) * (fS[1][j] + iS[1][j]);
+              acc[j]        = (i == 0) ? (-Q * w) : (acc[j] - Q * w);
+              J(mn[0] + i, mn[1] + j, 0, jx1, acc[j], i < dd[0] && j <= dd[1]);
+            }
+          }
+        }
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+          float acc = ZERO;
+#pragma unroll 1
+          for (int j = 0; j < N; ++j) {
+            const float w = HALF * (fS[0][i] + iS[0][i]) * (fS[1][j] - iS[1][j]);
+            acc           = (j == 0) ? (-Q * w) : (acc - Q * w);
+            J(mn[0] + i, mn[1] + j, 0, jx2, acc, i <= dd[0] && j < dd[1]);
+          }
+        }
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+#pragma unroll 1
+          for (int j = 0; j < N; ++j) {
+            const float w = THIRD * (fS[1][j] * (HALF * iS[0][i] + fS[0][i]) +
+                                     iS[1][j] * (HALF * fS[0][i] + iS[0][i]));
+            J(mn[0] + i, mn[1] + j, 0, jx3, QV3 * w, i <= dd[0] && j <= dd[1]);
+          }
+        }
+      } else {
+        {
+          float acc[N][N];
+#pragma unroll 1
+          for (int i = 0; i < N; ++i) {
+#pragma unroll 1
+            for (int j = 0; j < N; ++j) {
+#pragma unroll 1
+              for (int k = 0; k < N; ++k) {
+                const float w = THIRD * (fS[0][i] - iS[0][i]) *
+                                ((iS[1][j] * iS[2][k] + fS[1][j] * fS[2][k]) +
+                                 HALF * (iS[2][k] * fS[1][j] + iS[1][j] * fS[2][k]));
+                acc[j][k] = (i == 0) ? (-Q * w) : (acc[j][k] - Q * w);
+                J(mn[0] + i, mn[1] + j, mn[2] + k, jx1, acc[j][k],
+                  i < dd[0] && j <= dd[1] && k <= dd[2]);
+              }
+            }
+          }
+        }
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+          float acc[N];
+#pragma unroll 1
+          for (int j = 0; j < N; ++j) {
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) {
+              const float w = THIRD * (fS[1][j] - iS[1][j]) *
+                              (iS[0][i] * iS[2][k] + fS[0][i] * fS[2][k] +
+                               HALF * (iS[2][k] * fS[0][i] + iS[0][i] * fS[2][k]));
+              acc[k] = (j == 0) ? (-Q * w) : (acc[k] - Q * w);
+              J(mn[0] + i, mn[1] + j, mn[2] + k, jx2, acc[k], i <= dd[0] && j < dd[1] && k <= dd[2]);
+            }
+          }
+        }
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+#pragma unroll 1
+          for (int j = 0; j < N; ++j) {
+            float acc = ZERO;
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) {
+              const float w = THIRD * (fS[2][k] - iS[2][k]) *
+                              (iS[0][i] * iS[1][j] + fS[0][i] * fS[1][j] +
+                               HALF * (iS[0][i] * fS[1][j] + iS[1][j] * fS[0][i]));
+              acc = (k == 0) ? (-Q * w) : (acc - Q * w);
+              J(mn[0] + i, mn[1] + j, mn[2] + k, jx3, acc, i <= dd[0] && j <= dd[1] && k < dd[2]);
+            }
+          }
         }
       }
     } else {

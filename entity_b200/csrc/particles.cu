@@ -2377,6 +2377,38 @@ namespace eb200 {
     default: return cudaErrorInvalidValue;                                                     \
   }
 
+// shape orders 4..11: the unfused push and the per-lane atomic deposit only
+#define EB200_DISPATCH_HI_D(D, order, CALL)                                                    \
+  switch (order) {                                                                             \
+    case 4: return CALL(D, 4);                                                                 \
+    case 5: return CALL(D, 5);                                                                 \
+    case 6: return CALL(D, 6);                                                                 \
+    case 7: return CALL(D, 7);                                                                 \
+    case 8: return CALL(D, 8);                                                                 \
+    case 9: return CALL(D, 9);                                                                 \
+    case 10: return CALL(D, 10);                                                               \
+    case 11: return CALL(D, 11);                                                               \
+    default: return cudaErrorInvalidValue;                                                     \
+  }
+#define EB200_DISPATCH_HI(dim, order, CALL)                                                    \
+  switch (dim) {                                                                               \
+    case 1: EB200_DISPATCH_HI_D(1, order, CALL)                                                \
+    case 2: EB200_DISPATCH_HI_D(2, order, CALL)                                                \
+    case 3: EB200_DISPATCH_HI_D(3, order, CALL)                                                \
+    default: return cudaErrorInvalidValue;                                                     \
+  }
+
+    template <int D, int O>
+    cudaError_t launch_deposit_hi(const eb200_prtls_t& S, uint32_t npart, const eb200_grid_t& g,
+                                  float charge, float dt, float dxc, float* cur, cudaStream_t st) {
+      if (npart == 0) return cudaSuccess;
+      FieldView<D> J(g, cur);
+      deposit_atomic_kernel<D, O, false>
+        <<<(npart + 255) / 256, 256, 0, st>>>(S, npart, charge, ONE / dt, dxc, g.ng, J);
+      count_launch();
+      return cudaGetLastError();
+    }
+
     cudaError_t push_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,
                         const eb200_prtls_t& S, uint32_t npart, const float* em,
                         cudaStream_t st) {
@@ -2387,6 +2419,9 @@ namespace eb200 {
       A.inv_dx = ONE / c.dx;
       for (int a = 0; a < 3; ++a) A.ni[a] = g.n[a];
 #define CALL(D, O) launch_push<D, O>(A, S, npart, g, em, st)
+      if (order > 3) {
+        EB200_DISPATCH_HI(g.dim, order, CALL)
+      }
       EB200_DISPATCH_DO(g.dim, order, CALL)
 #undef CALL
     }
@@ -2394,6 +2429,13 @@ namespace eb200 {
     cudaError_t deposit(const eb200_grid_t& g, int order, const eb200_prtls_t& S, uint32_t npart,
                         float charge, float dt, float dxc, float* cur, int mode,
                         Scratch& scratch, cudaStream_t st) {
+      if (order > 3) {
+        // ATOMIC and AGGREGATED are hints about the order of the additions; ORDERED is a promise
+        if (mode == EB200_DEPOSIT_ORDERED) return cudaErrorNotSupported;
+#define CALL(D, O) launch_deposit_hi<D, O>(S, npart, g, charge, dt, dxc, cur, st)
+        EB200_DISPATCH_HI(g.dim, order, CALL)
+#undef CALL
+      }
 #define CALL(D, O) launch_deposit<D, O>(S, npart, g, charge, dt, dxc, cur, mode, scratch, st)
       EB200_DISPATCH_DO(g.dim, order, CALL)
 #undef CALL
@@ -2409,6 +2451,7 @@ namespace eb200 {
       A.ng  = g.ng;
       A.inv_dx = ONE / c.dx;
       for (int a = 0; a < 3; ++a) A.ni[a] = g.n[a];
+      if (order > 3) return cudaErrorNotSupported; // unfused path only (engine.cu falls back)
 #define CALL(D, O)                                                                             \
   launch_push_deposit<D, O>(A, S, npart, g, em, cur, mode, packed, do_pack, st, packed_j, packed_j_used)
       EB200_DISPATCH_DO(g.dim, order, CALL)
