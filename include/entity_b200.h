@@ -138,7 +138,8 @@ typedef struct {
   int          strict_fp;   /* 1: kernels built without FMA contraction (bit-exact with the
                                reference's baseline CPU build); 0: contraction allowed */
   eb200_grid_t grid;        /* local mesh */
-  int          shape_order; /* SHAPE_ORDER of the reference build: 0 (zig-zag), 1..3 (Esirkepov) */
+  int          shape_order; /* SHAPE_ORDER of the reference build: 0 (zig-zag), 1..11 (Esirkepov;
+                               4..11: Minkowski, unfused kernels, ATOMIC / AGGREGATED modes) */
   int          metric;      /* EB200_METRIC_* */
   float        metric_params[8]; /* Minkowski: dx, x1min, x2min, x3min;
                                     curvilinear / GR: x1min, x1max, x2min, x2max (physical extent of

@@ -287,7 +287,7 @@ def test_sort_particles_counting(eb, orc_mod, dim):
 
 def test_errors(eb):
     with pytest.raises(eb.EB200Error):
-        eb.Context((8, 8), order=7)
+        eb.Context((8, 8), order=12)
     ctx = eb.Context((8, 8), order=0)
     with pytest.raises(eb.EB200Error, match="No particle pusher"):
         ctx.push(ctx.make_pusher(dt=0.1, pusher_flags=0), {}, 0, None)
