@@ -294,6 +294,13 @@ def run_ours(args):
                                      sort_interval=args.sort_interval, device=local,
                                      deposit_mode=dmode, seed=0x5678 + rank, walls=args.walls,
                                      capacity_factor=(1.05 if args.replenish else 1.0) if world == 1 else 1.1)
+    # i*_prev / dx*_prev are scratch of one step (written by the pusher, read by the deposit of the
+    # same step, overwritten by the next push before any read: sr.hpp:137-153). The caller of the
+    # step mirror says so (eb200_set_lean_prev) unless --keep-prev asks for the reference's state
+    # of those arrays after every step. Only the fused 2D zig-zag kernel makes use of it.
+    lean_prev = (not args.keep_prev) and not turb and not other and not args.unfused
+    if lean_prev:
+        sim.ctx.set_lean_prev(True)
     decomposition = [1] * len(size)
     if world > 1:
         # spatial block decomposition as the reference's reconnection.toml asks ([-1, 2]); every
@@ -408,11 +415,15 @@ def run_ours(args):
     b_p = 102.0 if turb else B_P_2D  # 78 B (2D), 102 B (3D) per particle-step
     if other:
         b_p = 86.0  # 2D + phi carried (read 4 + write 4)
+    if lean_prev:
+        b_p = B_P_2D - 16.0  # i_prev / dx_prev (4 + 4 B per dimension) are not written: 62 B
     achieved = n_pushed * b_p / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
     with_sort_s = per_launch_s + 1e-3 * timing["sort_charge_ms_per_step"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
                 "frac_with_sort_charged": (n_pushed * b_p / with_sort_s / 1e9 / peak) if with_sort_s > 0 else 0.0,
+                "bytes_per_particle_step": b_p,
+                "frac_at_78B": (n_pushed * B_P_2D / per_launch_s / 1e9 / peak) if (lean_prev and per_launch_s > 0) else None,
                 "kernel": "push_deposit (all species of one step)", "peak_source": peak_src,
                 "phase_ms_per_step": {k: v[0] / max(args.steps, 1) for k, v in prof.items()}}
     # DRAM bytes of one launch from the ncu full capture of THIS workload's kernel, else null
@@ -421,7 +432,8 @@ def run_ours(args):
         with open(tr) as f:
             roofline["traffic"] = json.load(f).get(
                 f"{other}_push_deposit_bytes_per_launch" if other else
-                "turbulence_push_deposit_bytes_per_launch" if turb else "push_deposit_bytes_per_launch")
+                "turbulence_push_deposit_bytes_per_launch" if turb else
+                "push_deposit_lean_bytes_per_launch" if lean_prev else "push_deposit_bytes_per_launch")
     if other:
         roofline["note"] = ("two passes (push, deposit), ALU bound: the metric's transcendental functions "
                             "per particle (x pusher_niter for GRPIC), see DESIGN.md")
@@ -490,6 +502,8 @@ def run_ours(args):
                        "particles_per_gpu": n_pushed0,
                        "fused_push_deposit": (not args.unfused) and not other,
                        "sort_interval": args.sort_interval,
+                       "prev_arrays": ("scratch of one step, not stored (eb200_set_lean_prev): 62 B per particle-step"
+                                       if lean_prev else "left as the reference leaves them"),
                        "deposit": "atomic" if other else args.deposit,
                        "parallelism": (f"domain decomposition {'x'.join(str(n_) for n_ in decomposition)}, "
                                        f"one block per GPU, NCCL halo + particle exchange")
@@ -552,6 +566,9 @@ def main():
                          "moment + ReplenishUniform in the two 10-cell boxes) after every step")
     ap.add_argument("--decomp", type=int, nargs="+", default=None,
                     help="override the block decomposition request (default -1 2, as reconnection.toml)")
+    ap.add_argument("--keep-prev", action="store_true",
+                    help="leave i*_prev / dx*_prev after every step exactly as the reference does (78 B per "
+                         "particle-step instead of 62; default: the caller declares them scratch, eb200_set_lean_prev)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")

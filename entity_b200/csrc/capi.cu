@@ -50,6 +50,7 @@ struct eb200_ctx {
   uint64_t       launches_at_init;
   int            pd_kernel = 0; // eb200_set_pd_kernel
   int            sort_mode = -1; // eb200_set_sort_mode
+  int            lean_prev = 0;  // eb200_set_lean_prev
   eb200::Scratch packed;        // E/B repacked node by node for the fused 2D zig-zag kernel
   eb200::Scratch packed_j;      // J as 16-byte nodes {jx1, jx2, jx3, -}: target of kernel 8's flushes
   void*          packed_j_zeroed = nullptr; // the allocation that has been cleared
@@ -598,7 +599,8 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
   rc = check_cuda(ctx,
                   VARIANT_CALL(ctx, push_deposit_sr(ctx->cfg.grid, ctx->cfg.shape_order, *pusher,
                                                     *prtls, npart, em, cur,
-                                                    mode | (ctx->pd_kernel << 8), packed, do_pack,
+                                                    mode | (ctx->pd_kernel << 8) | (ctx->lean_prev << 16),
+                                                    packed, do_pack,
                                                     (cudaStream_t)stream, pj, &pj_used)),
                   "push_deposit_sr");
   if (rc) return rc;
@@ -1193,11 +1195,19 @@ int eb200_set_sort_mode(eb200_ctx_t* ctx, int mode) {
   return EB200_OK;
 }
 
+int eb200_set_lean_prev(eb200_ctx_t* ctx, int on) {
+  ENTER(ctx);
+  ctx->lean_prev = on != 0;
+  return EB200_OK;
+}
+
 // the sort flags of the step mirrors (engine.cu)
 int eb200_ctx_sort_flags(const eb200_ctx_t* ctx) {
   const int mode = ctx->sort_mode >= 0 ? ctx->sort_mode : (ctx->cfg.strict_fp ? 0 : 1);
-  return mode == 1 ? EB200_SORT_UNSTABLE : 0;
+  return (mode == 1 ? EB200_SORT_UNSTABLE : 0) | (ctx->lean_prev ? EB200_SORT_SKIP_PREV : 0);
 }
+
+int eb200_ctx_lean_prev(const eb200_ctx_t* ctx) { return ctx->lean_prev; }
 
 int eb200_zero_currents(eb200_ctx_t* ctx, float* cur, eb200_stream_t stream) {
   ENTER(ctx);

@@ -1048,6 +1048,7 @@ namespace eb200 {
       rplan[s].nseg = 0;
     }
     // data message layout: per peer, per species, per direction ascending
+    bool overflow = false;
     {
       long spos = 0, rpos = 0;
       size_t ridx = 0;
@@ -1097,10 +1098,11 @@ namespace eb200 {
         R.first[R.nseg] = at;
         nrecv[s]        = at;
         const eb200_species_t& sp = species[s];
-        // particles_comm.cpp:219-221
-        if ((uint64_t)sp.npart + nrecv[s] >= (uint64_t)sp.maxnpart && nrecv[s] > 0) {
-          return fail(C, EB200_ERR_CAPACITY, "Too many particles to receive (cannot fit into maxptl)");
-        }
+        // particles_comm.cpp:219-221. The failure is reported AFTER the data exchange: the
+        // neighbours are already committed to their sends, and a rank that returned here would
+        // leave them blocked in the grouped ncclSend / ncclRecv. The message lands in the
+        // context's receive buffer (sized by the counts), nothing is unpacked.
+        if ((uint64_t)sp.npart + nrecv[s] >= (uint64_t)sp.maxnpart && nrecv[s] > 0) overflow = true;
       }
       CU(C, C.sendbuf.reserve_grow(std::max<size_t>((size_t)spos * 4, 256)));
       CU(C, C.recvbuf.reserve_grow(std::max<size_t>((size_t)rpos * 4, 256)));
@@ -1124,6 +1126,9 @@ namespace eb200 {
     int rc = exchange(C, soff, scnt, roff, rcnt, 4, st);
     if (rc != EB200_OK) return rc;
     trace.mark(); // exchange
+    if (overflow) {
+      return fail(C, EB200_ERR_CAPACITY, "Too many particles to receive (cannot fit into maxptl)");
+    }
     for (int s = 0; s < nspecies; ++s) {
       eb200_species_t& sp = species[s];
       if (nrecv[s] == 0) continue;

@@ -115,6 +115,7 @@ extern "C" eb200::EngineState* eb200_ctx_engine_state(eb200_ctx_t* ctx);
 extern "C" int                 eb200_ctx_metric(const eb200_ctx_t* ctx);
 extern "C" int                 eb200_ctx_has_comm(const eb200_ctx_t* ctx);
 extern "C" int                 eb200_ctx_sort_flags(const eb200_ctx_t* ctx);
+extern "C" int                 eb200_ctx_lean_prev(const eb200_ctx_t* ctx);
 
 namespace eb200 {
   namespace srpic {
@@ -305,8 +306,10 @@ namespace eb200 {
           cudaEvent_t pushed = H.m->event();
           cudaEventRecord(pushed, st);
           cudaStreamWaitEvent(H.m->down, pushed, 0);
+          const bool lean = eb200_ctx_lean_prev(dom.ctx) != 0;
           for (int k : kSlotsOut) {
             if (!hp[k]) continue;
+            if (lean && k >= 10 && k <= 15) continue; // i*_prev / dx*_prev: not stored, not read
             const size_t e = kSlotElem[k];
             if (cudaMemcpyAsync((char*)hp[k] + lo * e, (const char*)dp[k] + lo * e, n * e,
                                 cudaMemcpyDeviceToHost, H.m->down) != cudaSuccess) return EB200_ERR_CUDA;
@@ -360,8 +363,9 @@ namespace eb200 {
         eb200_species_t& sp = dom.species[s];
         if (sp.npart == 0) continue;
         uint32_t n = sp.npart;
-        // i*_prev / dx*_prev are dead values here (rewritten by the next push before any read)
-        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | EB200_SORT_SKIP_PREV | eb200_ctx_sort_flags(dom.ctx),
+        // flags: counting / radix sort by build; i*_prev / dx*_prev left out when the caller
+        // declared them unobserved (eb200_set_lean_prev)
+        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | eb200_ctx_sort_flags(dom.ctx),
                                  dom.stream));
         sp.npart = n;
       }
@@ -666,7 +670,7 @@ namespace eb200 {
         eb200_species_t& sp = dom.species[s];
         if (sp.npart == 0) continue;
         uint32_t n = sp.npart;
-        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | EB200_SORT_SKIP_PREV | eb200_ctx_sort_flags(dom.ctx),
+        TRY(eb200_sort_particles(dom.ctx, &sp.arrays, &n, (clear ? 1 : 0) | eb200_ctx_sort_flags(dom.ctx),
                                  dom.stream));
         sp.npart = n;
       }
@@ -1024,6 +1028,7 @@ extern "C" int eb200_srpic_step_host(eb200_ctx_t* ctx, const eb200_srpic_params_
   std::vector<eb200_species_t> dev(species_host, species_host + nspecies);
   // per species 17 candidate arrays; element sizes in ParticleArrays order
   static const size_t esz[17] = { 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 2 };
+  const bool          lean_prev = eb200_ctx_lean_prev(ctx) != 0;
   for (int s = 0; s < nspecies; ++s) {
     void** hp = (void**)&species_host[s].arrays;
     void** dp = (void**)&dev[s].arrays;
@@ -1034,6 +1039,7 @@ extern "C" int eb200_srpic_step_host(eb200_ctx_t* ctx, const eb200_srpic_params_
       void* d = mirror_get(m, 3 + (size_t)s * 17 + k, cap * esz[k]);
       if (!d) return EB200_ERR_CUDA;
       dp[k] = d;
+      if (lean_prev && k >= 10 && k <= 15) continue; // dead values on entry and on exit
       cudaMemcpyAsync(d, hp[k], n * esz[k], cudaMemcpyHostToDevice, st);
       up += n * esz[k];
     }
@@ -1050,6 +1056,7 @@ extern "C" int eb200_srpic_step_host(eb200_ctx_t* ctx, const eb200_srpic_params_
     const size_t n = dev[s].npart;
     for (int k = 0; k < 17; ++k) {
       if (!hp[k]) continue;
+      if (lean_prev && k >= 10 && k <= 15) continue;
       cudaMemcpyAsync(hp[k], dp[k], n * esz[k], cudaMemcpyDeviceToHost, st);
       down += n * esz[k];
     }

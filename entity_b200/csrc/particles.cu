@@ -1081,7 +1081,10 @@ namespace eb200 {
     #define EB200_MOM_MINBLOCKS 3
   #endif
 
-    template <bool V4>
+    // KEEP_PREV = false (eb200_set_lean_prev): i*_prev / dx*_prev are not stored. Nothing on the
+    // path reads them after this kernel (the next push overwrites them before any read,
+    // sr.hpp:137-153): 62 instead of 78 bytes per particle.
+    template <bool V4, bool KEEP_PREV = true>
     __global__ void __launch_bounds__(256, EB200_MOM_MINBLOCKS)
       push_deposit_mom_kernel(PushArgs A, eb200_prtls_t S, uint32_t ngroups, uint32_t ahead,
                               PackedEM2 EB, float charge, float inv_dt, FieldView<2> J,
@@ -1135,11 +1138,13 @@ namespace eb200 {
         ld4<float4>(S.ux3 + p0, uv[2]);
         ld4<float4>(S.weight + p0, wv);
         all_pushed = (tv[0] == 1) && (tv[1] == 1) && (tv[2] == 1) && (tv[3] == 1);
-        if (all_pushed) {
+        if constexpr (KEEP_PREV) {
+          if (all_pushed) {
   #pragma unroll
-          for (int a = 0; a < D; ++a) {
-            st4<int4>(iip[a] + p0, iv[a]);
-            st4<float4>(ddp[a] + p0, dv[a]);
+            for (int a = 0; a < D; ++a) {
+              st4<int4>(iip[a] + p0, iv[a]);
+              st4<float4>(ddp[a] + p0, dv[a]);
+            }
           }
         }
       }
@@ -1196,20 +1201,24 @@ namespace eb200 {
           if (tag != 1) {
             S.tag[p0 + k] = tag;
           }
-          if (all_pushed) {
-            // a periodic wrap shifted i_prev with i (sr.hpp:664-677)
+          if constexpr (KEEP_PREV) {
+            if (all_pushed) {
+              // a periodic wrap shifted i_prev with i (sr.hpp:664-677)
   #pragma unroll
-            for (int a = 0; a < D; ++a) {
-              if (P.ip[a] != ip[a]) iip[a][p0 + k] = P.ip[a];
+              for (int a = 0; a < D; ++a) {
+                if (P.ip[a] != ip[a]) iip[a][p0 + k] = P.ip[a];
+              }
             }
           }
           ip[0] = P.ip[0], ip[1] = P.ip[1];
         }
-        if (!all_pushed) {
+        if constexpr (KEEP_PREV) {
+          if (!all_pushed) {
   #pragma unroll
-          for (int a = 0; a < D; ++a) {
-            iip[a][p0 + k] = ip[a];
-            ddp[a][p0 + k] = dp[a];
+            for (int a = 0; a < D; ++a) {
+              iip[a][p0 + k] = ip[a];
+              ddp[a][p0 + k] = dp[a];
+            }
           }
         }
   #pragma unroll
@@ -2096,7 +2105,8 @@ namespace eb200 {
       // which fused kernel (eb200_set_pd_kernel): 0 auto, 1 one particle per thread,
       // 2 TMA-staged persistent, 3 four particles per thread (zig-zag only), 4 shared-memory
       // field tile, 5 four particles per thread gathering from packed nodes (2D zig-zag)
-      const int which = (mode >> 8) & 0xff;
+      const int  which     = (mode >> 8) & 0xff;
+      const bool lean_prev = ((mode >> 16) & 1) != 0; // eb200_set_lean_prev
       mode &= 0xff;
       if (wide_window<D, O>() && mode == EB200_DEPOSIT_AGGREGATED && which == 0) {
         mode = EB200_DEPOSIT_ATOMIC;
@@ -2224,7 +2234,12 @@ namespace eb200 {
           PK.rowb = 24u * (unsigned)EB.N1;
           const uint32_t ngroups = npart / VEC;
           const bool     v4      = packed_j != nullptr && packed_j_used != nullptr && !j4_disabled();
-          if (v4) {
+          if (v4 && lean_prev) {
+            const uint32_t wave = resident_ctas(reinterpret_cast<const void*>(push_deposit_mom_kernel<true, false>), 256);
+            push_deposit_mom_kernel<true, false><<<(ngroups + 255) / 256, 256, 0, st>>>(
+              A, S, ngroups, wave, PK, A.c.charge, inv_dt, J, reinterpret_cast<float4*>(packed_j));
+            *packed_j_used = true;
+          } else if (v4) {
             const uint32_t wave = resident_ctas(reinterpret_cast<const void*>(push_deposit_mom_kernel<true>), 256);
             push_deposit_mom_kernel<true><<<(ngroups + 255) / 256, 256, 0, st>>>(
               A, S, ngroups, wave, PK, A.c.charge, inv_dt, J, reinterpret_cast<float4*>(packed_j));

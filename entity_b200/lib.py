@@ -444,6 +444,15 @@ class Context:
         """0 auto, 1 one particle per thread, 2 TMA-staged chunks, 3 four particles per thread."""
         self._check(self.lib.eb200_set_pd_kernel(self.handle, which))
 
+    def set_lean_prev(self, on: bool):
+        """i*_prev / dx*_prev are scratch of one step: not stored by the fused kernel, not sorted,
+        not moved by step_host (eb200_set_lean_prev)"""
+        self._check(self.lib.eb200_set_lean_prev(self.handle, int(on)))
+
+    def set_sort_mode(self, mode: int):
+        """-1 by build, 0 stable radix sort, 1 counting sort (eb200_set_sort_mode)"""
+        self._check(self.lib.eb200_set_sort_mode(self.handle, mode))
+
     def close(self):
         if self.handle:
             self.lib.eb200_finalize(self.handle)

@@ -296,8 +296,7 @@ int eb200_comm_init(eb200_ctx_t* ctx, const eb200_metadomain_t* md, const char* 
  * remove_dead | EB200_SORT_SKIP_PREV: i*_prev / dx*_prev are left where they are. Between the
  * deposit of one step and the pusher of the next they are dead values (the pusher overwrites
  * them before anything reads them, sr.hpp:137-153), which is where SortParticles runs
- * (srpic.hpp:184-186): eb200_srpic_step sorts this way; a host that reads them after a sort
- * (a checkpoint of the raw arrays) passes the plain flags. */
+ * (srpic.hpp:184-186): eb200_srpic_step sorts this way after eb200_set_lean_prev(ctx, 1). */
 #define EB200_SORT_SKIP_PREV 2
 /* remove_dead | EB200_SORT_UNSTABLE: counting sort by cell (histogram, scan, slot assignment: 18 B
  * per particle for the permutation instead of the radix sort's 60 B). Particles are grouped by
@@ -310,6 +309,14 @@ int eb200_comm_init(eb200_ctx_t* ctx, const eb200_metadomain_t* md, const char* 
 int eb200_sort_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls,
                          uint32_t* npart_inout_host, int remove_dead, eb200_stream_t stream);
 
+/* on = 1: the caller declares that it does not read i*_prev / dx*_prev between calls. They are
+ * scratch of one step -- written by the pusher, read by the deposit of the same step, and
+ * overwritten by the next push before anything reads them (sr.hpp:137-153) -- so the fused
+ * push+deposit kernel then does not store them (62 instead of 78 bytes per particle-step in
+ * 2D), the step mirrors' sort does not permute them and eb200_srpic_step_host moves them in
+ * neither direction. Their content is unspecified afterwards. Default 0: the arrays are left
+ * exactly as the reference leaves them. */
+int eb200_set_lean_prev(eb200_ctx_t* ctx, int on);
 /* Sort used by the step mirrors: -1 = by build (default: counting on fast, radix on strict),
  * 0 = stable radix sort, 1 = counting sort. */
 int eb200_set_sort_mode(eb200_ctx_t* ctx, int mode);

@@ -190,6 +190,60 @@ def test_step_host_streamed_matches_device(mods, chunk, monkeypatch):
         assert abs(float(ua.astype(np.float64).sum()) - float(ub.astype(np.float64).sum())) <= 1e-3 * np.abs(ua).sum()
 
 
+@pytest.mark.parametrize("host", [False, True])
+def test_lean_prev(mods, host):
+    """eb200_set_lean_prev: the fused kernel does not store i*_prev / dx*_prev, the sort leaves
+    them out, the host step moves them in neither direction -- and nothing else changes. Two
+    fast-build simulations from the same state (stable sort in both, so that the arrays can be
+    compared element by element): particles bit-identical after the first step, fields / currents
+    within the fp32 order-of-additions tolerance over the window; the lean run's prev arrays keep
+    the poison they were given."""
+    eb, wl, orc, pic = mods
+    kw = dict(ppc0=8, nfilter=2, strict=False, fused=True, sort_interval=2, deposit_mode=eb.DEPOSIT_AGGREGATED)
+    ref, lean = wl.reconnection((128, 64), **kw), wl.reconnection((128, 64), **kw)
+    for sim in (ref, lean):
+        sim.ctx.set_sort_mode(0)
+    lean.ctx.set_lean_prev(True)
+    prev = ("i1_prev", "i2_prev", "dx1_prev", "dx2_prev")
+    hs = lean.host_state() if host else None
+    for sp in lean.species:
+        for nm in prev:
+            sp.arrays[nm].fill_(7)
+    if host:
+        for spec in hs["species"]:
+            for nm in prev:
+                spec[nm].fill_(7)
+    names = ["i1", "i2", "dx1", "dx2", "ux1", "ux2", "ux3", "weight", "tag"]
+    for step in range(5):
+        ref.step()
+        if host:
+            lean.step_host(hs)
+            cur, em = hs["cur"].numpy(), hs["em"].numpy()
+            arrays = [(c.npart, spec) for c, spec in zip(hs["c"], hs["species"])]
+        else:
+            lean.step()
+            cur, em = lean.cur.cpu().numpy(), lean.em.cpu().numpy()
+            arrays = [(sp.npart, sp.arrays) for sp in lean.species]
+        j = ref.cur.cpu().numpy()
+        assert np.abs(j - cur).max() <= 5e-4 * np.abs(j).max(), f"J at step {step}"
+        e = ref.em.cpu().numpy()
+        assert np.abs(e - em).max() <= 1e-4 * np.abs(e).max(), f"EM at step {step}"
+        for sp, (n, arr) in zip(ref.species, arrays):
+            assert sp.npart == n
+            if step == 0:
+                for nm in names:
+                    a, b = sp.arrays[nm][:n].cpu().numpy(), arr[nm][:n].cpu().numpy()
+                    assert np.array_equal(a, b), f"{nm}: {(a != b).sum()} of {n} differ"
+    # groups of four particles go through the fused kernel; a tail of < 4 takes the generic one
+    for n, arr in arrays:
+        m = n // 4 * 4
+        for nm in prev:
+            assert float((arr[nm][:m].float() - 7).abs().max()) == 0.0, f"{nm} was written"
+    for sp in ref.species:
+        assert float((sp.arrays["i1_prev"][:sp.npart].float() - 7).abs().min()) >= 0  # (reference run: real values)
+        assert not bool((sp.arrays["dx1_prev"][:sp.npart] == 7).all())
+
+
 def test_step_with_match_boundaries(mods):
     """Whole steps with the reconnection configuration's boundaries in x2 (fields MATCH,
     particles ABSORB; pgens/reconnection/reconnection.toml) against the oracle stepper with the
