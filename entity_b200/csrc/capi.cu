@@ -57,6 +57,7 @@ struct eb200_ctx {
   float*         packed_j_cur    = nullptr; // planes the pending nodes belong to (while held)
   cudaStream_t   packed_j_stream = nullptr;
   eb200::Scratch stats;         // one double: the device-side accumulator of the reductions
+  eb200::Scratch emit_count;    // one uint32: photons emitted by one eb200_push_sr_emission launch
   const float*   packed_hold = nullptr; // em the packed copy is guaranteed current for
   bool           no_filter_fusion = false; // EB200_NO_FILTER_FUSION=1: pass-by-pass filter
   eb200::MetricParams metric {}; // curvilinear / GR contexts
@@ -501,6 +502,67 @@ int eb200_push_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher, const eb200_pr
                     VARIANT_CALL(ctx, push_sr(ctx->cfg.grid, ctx->cfg.shape_order, *pusher,
                                               *prtls, npart, em, (cudaStream_t)stream)),
                     "push_sr");
+}
+
+int eb200_push_sr_emission(eb200_ctx_t* ctx, const eb200_pusher_t* pusher, const eb200_prtls_t* prtls,
+                           uint32_t npart, const float* em, eb200_emission_t* em_policy,
+                           eb200_stream_t stream) {
+  ENTER(ctx);
+  REQUIRE(ctx, em_policy != nullptr, "emission policy is null");
+  REQUIRE_MINK(ctx, "eb200_push_sr_emission");
+  REQUIRE(ctx, ctx->cfg.shape_order <= 3, "eb200_push_sr_emission: shape orders 0..3");
+  REQUIRE(ctx, em_policy->kind == EB200_EMISSION_SYNCHROTRON || em_policy->kind == EB200_EMISSION_COMPTON,
+          "unknown emission policy");
+  int rc = check_pusher(ctx, pusher);
+  if (rc) return rc;
+  REQUIRE(ctx, pusher->pusher_flags != EB200_PUSHER_PHOTON && pusher->mass > 0.0f,
+          "emission: massive emitters only");
+  rc = check_prtls(ctx, prtls, npart);
+  if (rc) return rc;
+  REQUIRE(ctx, em != nullptr, "em is null");
+  REQUIRE(ctx, em_policy->photon_npart <= em_policy->photon_maxnpart, "photon npart > maxnpart");
+  {
+    // the photon arrays are written, not read: check them as a full particle struct
+    const eb200_prtls_t& q = em_policy->photons;
+    const int            d = ctx->cfg.grid.dim;
+    bool ok = q.i1 && q.dx1 && q.i1_prev && q.dx1_prev && q.ux1 && q.ux2 && q.ux3 && q.weight && q.tag;
+    if (d > 1) ok = ok && q.i2 && q.dx2 && q.i2_prev && q.dx2_prev;
+    if (d > 2) ok = ok && q.i3 && q.dx3 && q.i3_prev && q.dx3_prev;
+    REQUIRE(ctx, ok || em_policy->photon_maxnpart == em_policy->photon_npart,
+            "a required array of the emitted species is null");
+  }
+  rc = check_cuda(ctx, ctx->emit_count.reserve(256), "emission counter");
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = check_cuda(ctx, cudaMemsetAsync(ctx->emit_count.ptr, 0, 4, st), "emission counter");
+  if (rc) return rc;
+  eb200::EmitArgs M {};
+  M.E.kind                  = em_policy->kind;
+  M.E.photon_weight         = em_policy->photon_weight;
+  M.E.energy_min            = em_policy->photon_energy_min;
+  M.E.nominal_probability   = em_policy->nominal_probability;
+  M.E.nominal_photon_energy = em_policy->nominal_photon_energy;
+  M.E.species_mass          = pusher->mass;
+  M.E.should_drag           = em_policy->should_drag;
+  M.ph      = em_policy->photons;
+  M.offset  = em_policy->photon_npart;
+  M.cap     = em_policy->photon_maxnpart;
+  M.counter = (uint32_t*)ctx->emit_count.ptr;
+  M.seed = em_policy->seed, M.step = em_policy->step, M.call = em_policy->call;
+  rc = check_cuda(ctx,
+                  VARIANT_CALL(ctx, push_sr_emission(ctx->cfg.grid, ctx->cfg.shape_order, *pusher, *prtls,
+                                                     npart, em, M, st)),
+                  "push_sr_emission");
+  if (rc) return rc;
+  uint32_t n = 0;
+  rc = check_cuda(ctx, cudaMemcpyAsync(&n, ctx->emit_count.ptr, 4, cudaMemcpyDeviceToHost, st), "emission count");
+  if (rc) return rc;
+  rc = check_cuda(ctx, cudaStreamSynchronize(st), "emission count");
+  if (rc) return rc;
+  const uint32_t room = em_policy->photon_maxnpart - em_policy->photon_npart;
+  em_policy->photon_npart += n < room ? n : room;
+  if (n > room) return fail(ctx, EB200_ERR_CAPACITY, "emission: photons do not fit into maxnpart of the emitted species");
+  return EB200_OK;
 }
 
 int eb200_deposit(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t npart, float charge,

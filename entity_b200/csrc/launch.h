@@ -8,6 +8,23 @@
 
 namespace eb200 {
 
+  // emission policy of the SR pusher (arch::emission::Synchrotron / Compton), by value
+  struct EmitParams {
+    int   kind;
+    float photon_weight, energy_min, nominal_probability, nominal_photon_energy, species_mass;
+    int   should_drag;
+  };
+
+  // kernel argument of the pusher with an emission policy
+  struct EmitArgs {
+    EmitParams    E;
+    eb200_prtls_t ph;          // the emitted (photon) species
+    uint32_t      offset, cap; // its npart before the launch, its maxnpart
+    uint32_t*     counter;     // device: photons emitted by this launch (may exceed cap - offset)
+    uint64_t      seed;
+    uint32_t      step, call;
+  };
+
   // number of kernel launches issued by this library (eb200_launch_count)
   void     count_launch();
   uint64_t launches();
@@ -65,6 +82,9 @@ namespace eb200 {
     cudaError_t push_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,            \
                         const eb200_prtls_t& S, uint32_t npart, const float* em,               \
                         cudaStream_t st);                                                      \
+    cudaError_t push_sr_emission(const eb200_grid_t& g, int order, const eb200_pusher_t& c,   \
+                                 const eb200_prtls_t& S, uint32_t npart, const float* em,      \
+                                 const EmitArgs& M, cudaStream_t st);                          \
     cudaError_t deposit(const eb200_grid_t& g, int order, const eb200_prtls_t& S,             \
                         uint32_t npart, float charge, float dt, float dxc, float* cur,         \
                         int mode, Scratch& scratch, cudaStream_t st);                          \

@@ -10,6 +10,7 @@
 // so that the EB200_STRICT build reproduces the reference bit for bit.
 #pragma once
 #include "common.cuh"
+#include "launch.h"
 
 #include <type_traits>
 
@@ -776,6 +777,44 @@ namespace eb200 {
     }
   }
 
+  /* ------------------------------------------------------------- emission policies */
+  // arch::emission::{Synchrotron, Compton}::shouldEmit (synchrotron.h:139-224, compton.h:133-164):
+  // up = (u_before + u_after) / 2, e / b the Cartesian fields at the particle. Returns the
+  // probability; delta_u = the recoil of the emitter, energy = the photon's.
+  __device__ __forceinline__ float emission_response(const EmitParams& E, const float* up,
+                                                     const float* e, const float* b,
+                                                     float* delta_u, float& energy,
+                                                     float& gamma) {
+    const float u_sqr     = nsq(up);
+    const float gamma_sqr = ONE + u_sqr;
+    energy                = gamma_sqr * E.nominal_photon_energy;
+    if (E.kind == EB200_EMISSION_COMPTON) {
+      const float du = -E.photon_weight * energy / (sqrtf(u_sqr) * E.species_mass);
+      delta_u[0] = du * up[0], delta_u[1] = du * up[1], delta_u[2] = du * up[2];
+      gamma = sqrtf(gamma_sqr);
+      return E.nominal_probability * sqrtf(u_sqr / gamma_sqr);
+    }
+    const float u_mag = sqrtf(u_sqr);
+    gamma             = sqrtf(gamma_sqr);
+    const float beta  = u_mag / gamma;
+    float       x[3];
+    cross3(up, b, x);
+    const float epb[3] = { e[0] + x[0] / gamma, e[1] + x[1] / gamma, e[2] + x[2] / gamma };
+    const float bde    = dot3(up, e) / gamma;
+    float       kap[3];
+    cross3(epb, b, kap);
+    kap[0] += bde * e[0], kap[1] += bde * e[1], kap[2] += bde * e[2];
+    const float chi = nsq(epb) - SQR(bde);
+    const float p   = E.nominal_probability * (-dot3(kap, up) / (gamma_sqr * u_mag) + beta * chi);
+    const float dir[3] = { -kap[0] + gamma * up[0] * chi, -kap[1] + gamma * up[1] * chi,
+                           -kap[2] + gamma * up[2] * chi };
+    const float du = -E.photon_weight * energy / (sqrtf(nsq(dir)) * E.species_mass);
+    delta_u[0] = du * dir[0], delta_u[1] = du * dir[1], delta_u[2] = du * dir[2];
+    return p;
+  }
+
+  struct NoEmission {};
+
   /* ------------------------------------------------------------- one full push */
   struct PushArgs {
     eb200_pusher_t c;
@@ -844,10 +883,14 @@ namespace eb200 {
     }
   }
 
-  template <int D, int O, class EM, bool LEAN = false>
+  // HOOK (emission): callable (P, u_mid, e_cart, b_cart) run between the velocity update and the
+  // position update of a massive particle (sr.hpp:323-328); with a hook the continuous radiative
+  // drag is not applied (sr.hpp:311-322)
+  template <int D, int O, class EM, bool LEAN = false, class HOOK = NoEmission>
   // returns true when the particle left [0, ni) along some axis, i.e. when the boundary block
   // ran (only then can tag, i_prev or u have been touched by a boundary condition)
-  __device__ __forceinline__ bool push_particle(const PushArgs& A, const EM& F, Prtl<D>& P) {
+  __device__ __forceinline__ bool push_particle(const PushArgs& A, const EM& F, Prtl<D>& P,
+                                                HOOK&& hook = HOOK {}) {
     const eb200_pusher_t& c  = A.c;
     const float           dt = c.dt;
     bool                  massive = true;
@@ -885,7 +928,19 @@ namespace eb200 {
           }
         }
       }
-      velocity_update(c, A.ndh, P.u, ec, bc, fext);
+      if constexpr (std::is_same<std::decay_t<HOOK>, NoEmission>::value) {
+        velocity_update(c, A.ndh, P.u, ec, bc, fext);
+      } else {
+        float       um[3] = { P.u[0], P.u[1], P.u[2] };
+        const float er[3] = { ec[0], ec[1], ec[2] }, br[3] = { bc[0], bc[1], bc[2] };
+        eb200_pusher_t nodrag = c;
+        nodrag.drag_flags     = EB200_DRAG_NONE;
+        velocity_update(nodrag, A.ndh, P.u, ec, bc, fext);
+        um[0] = HALF * (um[0] + P.u[0]);
+        um[1] = HALF * (um[1] + P.u[1]);
+        um[2] = HALF * (um[2] + P.u[2]);
+        hook(P, um, er, br);
+      }
     }
     // Cartesian i+dx position update
     const float g2 = massive ? (ONE + SQR(P.u[0]) + SQR(P.u[1]) + SQR(P.u[2]))

@@ -4,6 +4,7 @@
 // what capi.cu calls.
 #include <cstdlib>
 #include "particle.cuh"
+#include "philox.cuh"
 #include "launch.h"
 
 #include <mutex>
@@ -81,6 +82,60 @@ namespace eb200 {
       P.tag  = tag;
       auto F = [&](int i, int j, int k, int c) { return EB.ld(i, j, k, c); };
       push_particle<D, O>(A, F, P);
+      store_pushed<D>(S, p, P, tag);
+    }
+
+    // push_kernel with an emission policy (sr.hpp:290-331, 1501-1555; archetypes/emission/*.h)
+    template <int D, int O>
+    __global__ void __launch_bounds__(256)
+      push_emit_kernel(PushArgs A, eb200_prtls_t S, uint32_t npart, FieldView<D> EB, EmitArgs M) {
+      const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+      if (p >= npart) {
+        return;
+      }
+      const short tag = S.tag[p];
+      if (tag != 1) {
+        return;
+      }
+      Prtl<D> P;
+      load_prtl<D>(S, p, P, false);
+      P.tag  = tag;
+      auto F = [&](int i, int j, int k, int c) { return EB.ld(i, j, k, c); };
+      auto emit = [&](Prtl<D>& Q, const float* um, const float* er, const float* br) {
+        float       du[3], energy, gamma;
+        const float prob = emission_response(M.E, um, er, br, du, energy, gamma);
+        Philox      rng(M.seed, M.step, M.call, p);
+        // "should not emit if photon energy is above 20% of (gamma - 1) m c^2"
+        const bool should = (rng.uniform() < prob) &&
+                            (energy < M.E.species_mass * (gamma - ONE) * 0.2f);
+        if (should && M.E.should_drag) {
+          Q.u[0] += du[0];
+          Q.u[1] += du[1];
+          Q.u[2] += du[2];
+        }
+        if (should && energy >= M.E.energy_min) {
+          const uint32_t slot = atomicAdd(M.counter, 1u);
+          if (slot < M.cap - M.offset) {
+            const size_t q   = (size_t)M.offset + slot;
+            const float  mag = sqrtf(nsq(du));
+            int*         ii[3]  = { M.ph.i1, M.ph.i2, M.ph.i3 };
+            float*       dd[3]  = { M.ph.dx1, M.ph.dx2, M.ph.dx3 };
+            int*         iip[3] = { M.ph.i1_prev, M.ph.i2_prev, M.ph.i3_prev };
+            float*       ddp[3] = { M.ph.dx1_prev, M.ph.dx2_prev, M.ph.dx3_prev };
+  #pragma unroll
+            for (int a = 0; a < D; ++a) {
+              ii[a][q] = Q.i[a], dd[a][q] = Q.d[a];
+              iip[a][q] = Q.i[a], ddp[a][q] = Q.d[a];
+            }
+            M.ph.ux1[q]    = (-du[0] / mag) * energy;
+            M.ph.ux2[q]    = (-du[1] / mag) * energy;
+            M.ph.ux3[q]    = (-du[2] / mag) * energy;
+            M.ph.weight[q] = M.E.photon_weight * Q.w;
+            M.ph.tag[q]    = 1;
+          }
+        }
+      };
+      push_particle<D, O, decltype(F), false>(A, F, P, emit);
       store_pushed<D>(S, p, P, tag);
     }
 
@@ -2437,6 +2492,32 @@ namespace eb200 {
       if (order > 3) {
         EB200_DISPATCH_HI(g.dim, order, CALL)
       }
+      EB200_DISPATCH_DO(g.dim, order, CALL)
+#undef CALL
+    }
+
+    template <int D, int O>
+    cudaError_t launch_push_emit(const PushArgs& A, const eb200_prtls_t& S, uint32_t npart,
+                                 const eb200_grid_t& g, const float* em, const EmitArgs& M,
+                                 cudaStream_t st) {
+      if (npart == 0) return cudaSuccess;
+      FieldView<D> EB(g, const_cast<float*>(em));
+      push_emit_kernel<D, O><<<(npart + 255) / 256, 256, 0, st>>>(A, S, npart, EB, M);
+      count_launch();
+      return cudaGetLastError();
+    }
+
+    cudaError_t push_sr_emission(const eb200_grid_t& g, int order, const eb200_pusher_t& c,
+                                 const eb200_prtls_t& S, uint32_t npart, const float* em,
+                                 const EmitArgs& M, cudaStream_t st) {
+      PushArgs A;
+      A.c   = c;
+      A.ndh = HALF * (c.charge / c.mass) * c.omegaB0 * c.dt;
+      A.ng  = g.ng;
+      A.inv_dx = ONE / c.dx;
+      for (int a = 0; a < 3; ++a) A.ni[a] = g.n[a];
+#define CALL(D, O) launch_push_emit<D, O>(A, S, npart, g, em, M, st)
+      if (order > 3) return cudaErrorNotSupported;
       EB200_DISPATCH_DO(g.dim, order, CALL)
 #undef CALL
     }

@@ -121,6 +121,18 @@ class SpatialDistC(C.Structure):
                 ("atm_ds", C.c_float), ("inv_V0", C.c_float)]
 
 
+class EmissionC(C.Structure):
+    """eb200_emission_t"""
+    _fields_ = [("kind", C.c_int), ("photon_weight", C.c_float), ("photon_energy_min", C.c_float),
+                ("nominal_probability", C.c_float), ("nominal_photon_energy", C.c_float),
+                ("should_drag", C.c_int), ("photons", Prtls), ("photon_npart", C.c_uint32),
+                ("photon_maxnpart", C.c_uint32), ("seed", C.c_uint64), ("step", C.c_uint32),
+                ("call", C.c_uint32)]
+
+
+EMISSION_SYNCHROTRON, EMISSION_COMPTON = 1, 2
+
+
 class AtmosphereC(C.Structure):
     """eb200_atmosphere_t"""
     _fields_ = [("dim", C.c_int), ("sign", C.c_int), ("x_surf", C.c_float), ("ds", C.c_float),
@@ -263,6 +275,11 @@ def load():
     lib.eb200_comm_fields.argtypes = [ctxp, vp, C.c_int, C.c_int, C.c_int, i32p, vp]
     lib.eb200_sync_currents.argtypes = [ctxp, vp, vp, i32p, vp]
     lib.eb200_sort_particles.argtypes = [ctxp, C.POINTER(Prtls), C.POINTER(C.c_uint32), C.c_int, vp]
+    lib.eb200_push_sr_emission.argtypes = [ctxp, C.POINTER(Pusher), C.POINTER(Prtls), C.c_uint32, vp,
+                                           C.POINTER(EmissionC), vp]
+    lib.eb200_push_sr_emission.restype = C.c_int
+    lib.eb200_set_lean_prev.argtypes = [ctxp, C.c_int]
+    lib.eb200_set_sort_mode.argtypes = [ctxp, C.c_int]
     lib.eb200_srpic_step.argtypes = [ctxp, C.POINTER(ParamsC), vp, vp, vp, C.POINTER(SpeciesC),
                                      C.c_int, C.c_uint32, C.c_double, vp]
     lib.eb200_srpic_step.restype = C.c_int
@@ -593,6 +610,24 @@ class Context:
         s = self.prtls_struct(arrays)
         self._check(self.lib.eb200_push_sr(self.handle, C.byref(pusher), C.byref(s), npart,
                                            _ptr(em), self._stream(stream)))
+
+    def push_emission(self, pusher, arrays, npart, em, kind, photons, photon_npart, photon_maxnpart,
+                      photon_weight, photon_energy_min, nominal_probability, nominal_photon_energy,
+                      should_drag=False, seed=0x123456789abcdef0, step=0, call=0, stream=None):
+        """eb200_push_sr_emission; returns the new particle count of the emitted species"""
+        s = self.prtls_struct(arrays)
+        e = EmissionC()
+        e.kind, e.photon_weight, e.photon_energy_min = kind, photon_weight, photon_energy_min
+        e.nominal_probability, e.nominal_photon_energy = nominal_probability, nominal_photon_energy
+        e.should_drag = int(should_drag)
+        e.photons = self.prtls_struct(photons)
+        e.photon_npart, e.photon_maxnpart = photon_npart, photon_maxnpart
+        e.seed, e.step, e.call = seed, step, call
+        rc = self.lib.eb200_push_sr_emission(self.handle, C.byref(pusher), C.byref(s), npart, _ptr(em),
+                                             C.byref(e), self._stream(stream))
+        self.last_emission_npart = int(e.photon_npart)
+        self._check(rc)
+        return int(e.photon_npart)
 
     def deposit(self, arrays, npart, charge, dt, cur, mode=DEPOSIT_ATOMIC, stream=None):
         s = self.prtls_struct(arrays)

