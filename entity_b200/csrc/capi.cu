@@ -13,6 +13,7 @@
 #include <cmath>
 #include <algorithm>
 #include <string>
+#include <vector>
 
 namespace eb200 {
   static std::atomic<uint64_t> g_launches { 0 };
@@ -36,7 +37,8 @@ namespace eb200 {
   int         comm_unique_id(char* out, std::string& err);
   int         comm_fields(Comm&, float* fld, int c0, int c1, cudaStream_t st);
   int         comm_sync_currents(Comm&, float* cur, cudaStream_t st);
-  int         comm_particles(Comm&, eb200_species_t* species, int nspecies, cudaStream_t st);
+  int         comm_particles(Comm&, eb200_species_t* species, int nspecies, cudaStream_t st,
+                             const ExcList* exc);
   const eb200_domain_info_t* comm_info(const Comm*);
 } // namespace eb200
 
@@ -51,6 +53,15 @@ struct eb200_ctx {
   int            pd_kernel = 0; // eb200_set_pd_kernel
   int            sort_mode = -1; // eb200_set_sort_mode
   int            lean_prev = 0;  // eb200_set_lean_prev
+  // exception lists of the fused push launches of the current step, by the species' tag array
+  // (consumed and invalidated by eb200_comm_particles)
+  struct ExcTrack {
+    const short*   tag = nullptr;
+    uint32_t       npart = 0;
+    eb200::Scratch buf; // [count: 256 B][idx: cap x 4 B]
+    eb200::ExcList list;
+  };
+  std::vector<ExcTrack*> exc;
   eb200::Scratch packed;        // E/B repacked node by node for the fused 2D zig-zag kernel
   eb200::Scratch packed_j;      // J as 16-byte nodes {jx1, jx2, jx3, -}: target of kernel 8's flushes
   void*          packed_j_zeroed = nullptr; // the allocation that has been cleared
@@ -247,6 +258,11 @@ void eb200_finalize(eb200_ctx_t* ctx) {
   ctx->packed.release();
   ctx->packed_j.release();
   ctx->stats.release();
+  ctx->emit_count.release();
+  for (auto* q : ctx->exc) {
+    q->buf.release();
+    delete q;
+  }
   if (ctx->comm) eb200::comm_delete(ctx->comm);
   eb200::engine_state_delete(ctx->engine);
   delete ctx;
@@ -658,12 +674,38 @@ int eb200_push_deposit_sr(eb200_ctx_t* ctx, const eb200_pusher_t* pusher,
       }
     }
   }
+  // multi-domain: let the kernel write down who is not alive afterwards (the migration reads
+  // that list instead of scanning every tag twice)
+  eb200::ExcList* exc = nullptr;
+  static const bool exc_off = getenv("EB200_MIGRATE_SCAN") != nullptr;
+  if (ctx->comm && !exc_off && npart > 0) {
+    eb200_ctx::ExcTrack* t = nullptr;
+    for (auto* q : ctx->exc) {
+      if (q->tag == prtls->tag) t = q;
+    }
+    if (!t) {
+      t      = new eb200_ctx::ExcTrack();
+      t->tag = prtls->tag;
+      ctx->exc.push_back(t);
+    }
+    const uint32_t cap = 1u << 20;
+    if (check_cuda(ctx, t->buf.reserve(256 + (size_t)cap * 4), "exception list") == EB200_OK &&
+        cudaMemsetAsync(t->buf.ptr, 0, 4, (cudaStream_t)stream) == cudaSuccess &&
+        cudaMemsetAsync((char*)t->buf.ptr + 256, 0xFF, (size_t)cap * 4, (cudaStream_t)stream) == cudaSuccess) {
+      t->npart        = npart;
+      t->list.count   = (uint32_t*)t->buf.ptr;
+      t->list.idx     = (uint32_t*)((char*)t->buf.ptr + 256);
+      t->list.cap     = cap;
+      t->list.tracked = false;
+      exc             = &t->list;
+    }
+  }
   rc = check_cuda(ctx,
                   VARIANT_CALL(ctx, push_deposit_sr(ctx->cfg.grid, ctx->cfg.shape_order, *pusher,
                                                     *prtls, npart, em, cur,
                                                     mode | (ctx->pd_kernel << 8) | (ctx->lean_prev << 16),
                                                     packed, do_pack,
-                                                    (cudaStream_t)stream, pj, &pj_used)),
+                                                    (cudaStream_t)stream, pj, &pj_used, exc)),
                   "push_deposit_sr");
   if (rc) return rc;
   if (pj_used) {
@@ -1366,7 +1408,17 @@ int eb200_comm_particles(eb200_ctx_t* ctx, eb200_species_t* species, int nspecie
     int rc = check_prtls(ctx, &species[s].arrays, species[s].npart);
     if (rc) return rc;
   }
-  int rc = eb200::comm_particles(*ctx->comm, species, nspecies, (cudaStream_t)stream);
+  // exception lists left by this step's fused push launches, matched by tag array and count
+  std::vector<eb200::ExcList> lists(nspecies > 0 ? nspecies : 1);
+  for (int s = 0; s < nspecies; ++s) {
+    for (auto* q : ctx->exc) {
+      if (q->tag == species[s].arrays.tag && q->npart == species[s].npart && q->list.tracked) {
+        lists[s] = q->list;
+      }
+    }
+  }
+  int rc = eb200::comm_particles(*ctx->comm, species, nspecies, (cudaStream_t)stream, lists.data());
+  for (auto* q : ctx->exc) q->list.tracked = false; // the arrays have changed: lists are stale
   return rc == EB200_OK ? rc : fail(ctx, rc, eb200::comm_error(ctx->comm));
 }
 

@@ -28,6 +28,8 @@
 #include "common.cuh"
 #include "launch.h"
 
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <nccl.h> // types only; the library is resolved at run time (no link dependency)
 
@@ -459,6 +461,120 @@ namespace eb200 {
     if (threadIdx.x == 0) {
       class_base[nclass] = part[1023]; // number of holes
     }
+  }
+
+  // ---- classify from the exception list of the fused push (launch.h ExcList) ----------------
+  // The pusher already met every particle that is not alive after it and wrote its index down;
+  // sorting that short list by (class, index) gives exactly what the two scans over all tags
+  // give -- out_idx in class-major, index-ascending order and the class totals / bases.
+  __global__ void __launch_bounds__(256)
+    exc_keys_kernel(const short* __restrict__ tag, const uint32_t* __restrict__ idx, uint32_t cap,
+                    const uint32_t* __restrict__ count, uint64_t* __restrict__ keys) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cap) return;
+    uint64_t key = ~0ull; // unused slots sort last
+    if (j < min(*count, cap)) {
+      const uint32_t p = idx[j];
+      const int      t = tag[p];
+      key = ((uint64_t)(uint32_t)(t == 0 ? 0 : t - 1) << 32) | p;
+    }
+    keys[j] = key;
+  }
+
+  __global__ void __launch_bounds__(256)
+    exc_finish_kernel(const uint64_t* __restrict__ keys, uint32_t cap,
+                      const uint32_t* __restrict__ count, int nclass,
+                      uint32_t* __restrict__ class_total, uint32_t* __restrict__ class_base,
+                      uint32_t* __restrict__ out_idx, uint32_t* __restrict__ overflow) {
+    const uint32_t n = min(*count, cap);
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out_idx[j] = (uint32_t)keys[j];
+    if (blockIdx.x == 0 && (int)threadIdx.x <= nclass) {
+      // first key of class c: lower bound of (c << 32)
+      auto lower = [&](uint64_t v) {
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
+          const uint32_t mid = lo + (hi - lo) / 2;
+          if (keys[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      const int c = threadIdx.x;
+      if (c < nclass) {
+        const uint32_t b = lower((uint64_t)c << 32), e = lower((uint64_t)(c + 1) << 32);
+        class_base[c]  = b;
+        class_total[c] = e - b;
+      } else {
+        class_base[nclass] = n; // number of holes
+        if (*count > cap) atomicExch(overflow, 1u);
+      }
+    }
+  }
+
+  // the usual case -- a few hundred entries: one block sorts the list in shared memory and writes
+  // out_idx, the class totals and bases (same results as keys + radix sort + finish)
+  constexpr int EXC_SMALL = 4096;
+
+  __global__ void __launch_bounds__(1024)
+    exc_small_kernel(const short* __restrict__ tag, const uint32_t* __restrict__ idx, uint32_t n,
+                     int nclass, uint32_t* __restrict__ class_total,
+                     uint32_t* __restrict__ class_base, uint32_t* __restrict__ out_idx) {
+    using Sort = cub::BlockRadixSort<uint64_t, 1024, EXC_SMALL / 1024>;
+    __shared__ union {
+      typename Sort::TempStorage tmp;
+      uint64_t                   sorted[EXC_SMALL];
+    } sm;
+    uint64_t keys[EXC_SMALL / 1024];
+#pragma unroll
+    for (int k = 0; k < EXC_SMALL / 1024; ++k) {
+      const uint32_t j = threadIdx.x * (EXC_SMALL / 1024) + k;
+      keys[k]          = ~0ull;
+      if (j < n) {
+        const uint32_t p = idx[j];
+        const int      t = tag[p];
+        keys[k] = ((uint64_t)(uint32_t)(t == 0 ? 0 : t - 1) << 32) | p;
+      }
+    }
+    Sort(sm.tmp).Sort(keys, 0, 40);
+    __syncthreads(); // the sort's scratch is reused for the sorted list
+#pragma unroll
+    for (int k = 0; k < EXC_SMALL / 1024; ++k) {
+      const uint32_t j = threadIdx.x * (EXC_SMALL / 1024) + k;
+      sm.sorted[j]     = keys[k];
+      if (j < n) out_idx[j] = (uint32_t)keys[k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x <= nclass) {
+      auto lower = [&](uint64_t v) {
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
+          const uint32_t mid = lo + (hi - lo) / 2;
+          if (sm.sorted[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      const int c = threadIdx.x;
+      if (c < nclass) {
+        const uint32_t b = lower((uint64_t)c << 32), e = lower((uint64_t)(c + 1) << 32);
+        class_base[c]  = b;
+        class_total[c] = e - b;
+      } else {
+        class_base[nclass] = n;
+      }
+    }
+  }
+
+  // count message: slot q takes class total src_class[q] of species src_species[q]
+  struct CountGather {
+    int            n;
+    const uint32_t* tot[8];      // per species: class totals
+    unsigned char  species[256];
+    unsigned char  cls[256];
+  };
+
+  __global__ void gather_counts_kernel(const __grid_constant__ CountGather G, uint32_t* __restrict__ out) {
+    const int q = threadIdx.x;
+    if (q < G.n) out[q] = G.tot[G.species[q]][G.cls[q]];
   }
 
   __global__ void __launch_bounds__(SPLIT_THREADS)
@@ -906,7 +1022,8 @@ namespace eb200 {
   };
 
   // Particles::Communicate for every species in one round
-  int comm_particles(Comm& C, eb200_species_t* species, int nspecies, cudaStream_t st) {
+  int comm_particles(Comm& C, eb200_species_t* species, int nspecies, cudaStream_t st,
+                     const ExcList* exc) {
     const Metadomain& M   = C.M;
     const int         D   = M.D;
     const int         ctr = (M.ndir - 1) / 2;
@@ -944,14 +1061,73 @@ namespace eb200 {
     }
     const size_t off_sendcnt = work_bytes; // counts to peers / from peers (uint32)
     work_bytes += sizeof(uint32_t) * 2 * (size_t)nspecies * MAXTAG * 2;
+    work_bytes  = (work_bytes + 255) / 256 * 256;
+    // exception-list path: two key arrays + the radix sort's scratch + an overflow flag
+    uint32_t exc_cap = 0;
+    for (int s = 0; s < nspecies; ++s) {
+      if (exc && exc[s].tracked && exc[s].count) exc_cap = std::max(exc_cap, exc[s].cap);
+    }
+    size_t       exc_tmp  = 0;
+    const size_t off_keys = work_bytes;
+    if (exc_cap > 0) {
+      cub::DeviceRadixSort::SortKeys(nullptr, exc_tmp, (uint64_t*)nullptr, (uint64_t*)nullptr,
+                                     (size_t)exc_cap, 0, 40, st);
+      work_bytes += 2 * sizeof(uint64_t) * (size_t)exc_cap + exc_tmp + 512;
+    }
+    const size_t off_ovf = work_bytes;
+    work_bytes += 256;
     CU(C, C.work.reserve(work_bytes));
     char* W = (char*)C.work.ptr;
+    CU(C, cudaMemsetAsync(W + off_ovf, 0, 4, st));
+    // sizes of the exception lists (one read-back; the pushes had to finish before the classify
+    // in any case): short lists are sorted by one block, long ones by the device-wide radix sort
+    std::vector<uint32_t> exc_n(nspecies, 0);
+    {
+      bool any = false;
+      for (int s = 0; s < nspecies; ++s) {
+        if (exc && exc[s].tracked && exc[s].count && species[s].npart > 0) {
+          CU(C, cudaMemcpyAsync(C.pinned + 3000 + s, exc[s].count, 4, cudaMemcpyDeviceToHost, st));
+          any = true;
+        }
+      }
+      if (any) {
+        CU(C, cudaStreamSynchronize(st));
+        for (int s = 0; s < nspecies; ++s) {
+          if (exc && exc[s].tracked && exc[s].count && species[s].npart > 0) exc_n[s] = C.pinned[3000 + s];
+        }
+      }
+    }
     for (int s = 0; s < nspecies; ++s) {
       const eb200_species_t& sp = species[s];
       uint32_t* cnt = (uint32_t*)(W + off_cnt[s]);
       uint32_t* tot = (uint32_t*)(W + off_tot[s]);
       if (sp.npart == 0) {
         CU(C, cudaMemsetAsync(tot, 0, sizeof(uint32_t) * (2 * MAXTAG + 2), st));
+        continue;
+      }
+      // EB200_EXC_SMALL=0 sends every list through the device-wide sort (tests)
+      static const uint32_t small_max = getenv("EB200_EXC_SMALL") ? (uint32_t)atoi(getenv("EB200_EXC_SMALL"))
+                                                                  : (uint32_t)EXC_SMALL;
+      if (exc && exc[s].tracked && exc[s].count && exc_n[s] <= std::min<uint32_t>(small_max, EXC_SMALL) &&
+          small_max > 0) {
+        exc_small_kernel<<<1, 1024, 0, st>>>(sp.arrays.tag, exc[s].idx, exc_n[s], nclass, tot, tot + MAXTAG,
+                                             (uint32_t*)(W + off_idx[s]));
+        count_launch();
+        continue;
+      }
+      if (exc && exc[s].tracked && exc[s].count) {
+        uint64_t* k0  = (uint64_t*)(W + off_keys);
+        uint64_t* k1  = k0 + exc_cap;
+        void*     tmp = (void*)(k1 + exc_cap);
+        const uint32_t cap = exc[s].cap;
+        exc_keys_kernel<<<(cap + 255) / 256, 256, 0, st>>>(sp.arrays.tag, exc[s].idx, cap, exc[s].count, k0);
+        CU(C, cub::DeviceRadixSort::SortKeys(tmp, exc_tmp, k0, k1, (size_t)cap, 0, 40, st));
+        exc_finish_kernel<<<(cap + 255) / 256, 256, 0, st>>>(k1, cap, exc[s].count, nclass, tot, tot + MAXTAG,
+                                                            (uint32_t*)(W + off_idx[s]),
+                                                            (uint32_t*)(W + off_ovf));
+        count_launch();
+        count_launch();
+        count_launch();
         continue;
       }
       constexpr uint32_t CH = SPLIT_THREADS * SPLIT_VEC; // tags per block iteration
@@ -1001,12 +1177,29 @@ namespace eb200 {
       CU(C, C.sendbuf.reserve_grow(std::max<size_t>((size_t)spos * 4, 256)));
       CU(C, C.recvbuf.reserve_grow(std::max<size_t>((size_t)rpos * 4, 256)));
       long pos = 0;
-      for (size_t k = 0; k < C.peers.size(); ++k) {
-        for (const Slot& sl : sslots[k]) {
-          const uint32_t* tot = (const uint32_t*)(W + off_tot[sl.s]);
-          CU(C, cudaMemcpyAsync((uint32_t*)C.sendbuf.ptr + pos, tot + (tag_of(sl.d) - 1), 4,
-                                cudaMemcpyDeviceToDevice, st));
-          ++pos;
+      if (spos <= 256 && nspecies <= 8) {
+        CountGather G {};
+        for (int s = 0; s < nspecies; ++s) G.tot[s] = (const uint32_t*)(W + off_tot[s]);
+        for (size_t k = 0; k < C.peers.size(); ++k) {
+          for (const Slot& sl : sslots[k]) {
+            G.species[pos] = (unsigned char)sl.s;
+            G.cls[pos]     = (unsigned char)(tag_of(sl.d) - 1);
+            ++pos;
+          }
+        }
+        G.n = (int)pos;
+        if (pos > 0) {
+          gather_counts_kernel<<<1, 256, 0, st>>>(G, (uint32_t*)C.sendbuf.ptr);
+          count_launch();
+        }
+      } else {
+        for (size_t k = 0; k < C.peers.size(); ++k) {
+          for (const Slot& sl : sslots[k]) {
+            const uint32_t* tot = (const uint32_t*)(W + off_tot[sl.s]);
+            CU(C, cudaMemcpyAsync((uint32_t*)C.sendbuf.ptr + pos, tot + (tag_of(sl.d) - 1), 4,
+                                  cudaMemcpyDeviceToDevice, st));
+            ++pos;
+          }
         }
       }
       int rc = exchange(C, soff, scnt, roff, rcnt, 4, st);
@@ -1021,10 +1214,13 @@ namespace eb200 {
         CU(C, cudaMemcpyAsync(h + (size_t)nspecies * (MAXTAG + 1), C.recvbuf.ptr, (size_t)rpos * 4,
                               cudaMemcpyDeviceToHost, st));
       }
+      // (the last word of the pinned block: did an exception list overflow its capacity?)
+      CU(C, cudaMemcpyAsync(h + 4095, W + off_ovf, 4, cudaMemcpyDeviceToHost, st));
       CU(C, cudaStreamSynchronize(st));
       (void)d_sendcnt;
       (void)d_recvcnt;
     }
+    const bool exc_overflow = C.pinned[4095] != 0;
     trace.mark(); // counts
     const uint32_t* hbase = C.pinned;
     const uint32_t* hrecv = C.pinned + (size_t)nspecies * (MAXTAG + 1);
@@ -1128,6 +1324,11 @@ namespace eb200 {
     trace.mark(); // exchange
     if (overflow) {
       return fail(C, EB200_ERR_CAPACITY, "Too many particles to receive (cannot fit into maxptl)");
+    }
+    if (exc_overflow) {
+      return fail(C, EB200_ERR_CAPACITY,
+                  "migration: more dead / outgoing particles than the exception list holds; compact more "
+                  "often (clear_interval) or set EB200_MIGRATE_SCAN=1");
     }
     for (int s = 0; s < nspecies; ++s) {
       eb200_species_t& sp = species[s];

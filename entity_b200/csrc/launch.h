@@ -25,6 +25,17 @@ namespace eb200 {
     uint32_t      step, call;
   };
 
+  // Exception list of one fused push launch: the indices of the particles that are not alive
+  // afterwards (dead before, absorbed, or tagged for migration). The migration reads it instead
+  // of scanning every tag twice (comm.cu). `tracked` is set by the launcher when every particle of
+  // the launch went through a kernel that appends; count may exceed cap (then the list is unusable).
+  struct ExcList {
+    uint32_t* count   = nullptr; // device
+    uint32_t* idx     = nullptr; // device, cap entries, pre-filled with 0xFFFFFFFF
+    uint32_t  cap     = 0;
+    bool      tracked = false;
+  };
+
   // number of kernel launches issued by this library (eb200_launch_count)
   void     count_launch();
   uint64_t launches();
@@ -91,7 +102,8 @@ namespace eb200 {
     cudaError_t push_deposit_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,    \
                                 const eb200_prtls_t& S, uint32_t npart, const float* em,       \
                                 float* cur, int mode, float* packed, bool do_pack,             \
-                                cudaStream_t st, float* packed_j, bool* packed_j_used);        \
+                                cudaStream_t st, float* packed_j, bool* packed_j_used,         \
+                                ExcList* exc);                                                 \
     cudaError_t unpack_j4(const eb200_grid_t& g, float* packed_j, float* cur,                 \
                           cudaStream_t st);                                                    \
     cudaError_t pack_em2d(const eb200_grid_t& g, const float* em, float* packed,              \

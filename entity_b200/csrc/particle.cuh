@@ -822,7 +822,19 @@ namespace eb200 {
     int            ni[3];
     int            ng;
     float          inv_dx; // 1 / c.dx
+    // exception list of this launch (launch.h ExcList), null when nobody asked for it
+    uint32_t*      exc_count = nullptr;
+    uint32_t*      exc_idx   = nullptr;
+    uint32_t       exc_cap   = 0;
   };
+
+  // particle p is not alive after this launch: dead on entry, absorbed, or tagged to migrate
+  __device__ __forceinline__ void exc_append(const PushArgs& A, uint32_t p) {
+    if (A.exc_count != nullptr) {
+      const uint32_t s = atomicAdd(A.exc_count, 1u);
+      if (s < A.exc_cap) A.exc_idx[s] = p;
+    }
+  }
 
   // LEAN: the context is known (host-side check, see lean_pusher()) to be a plain Boris push
   // without drag, atmosphere or GCA; the optional branches are compiled out.

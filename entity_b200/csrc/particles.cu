@@ -185,6 +185,7 @@ namespace eb200 {
         // tag and state are requested together: one DRAM round trip, not two
         tag = S.tag[p];
         load_prtl<D>(S, p, P, false);
+        if (tag != 1) exc_append(A, p);
       }
       bool active = (tag == 1);
       if constexpr (!AGG) {
@@ -204,6 +205,7 @@ namespace eb200 {
         if (P.u[0] == 1.2345e-30f)
 #endif
         store_pushed<D>(S, p, P, tag);
+        if (P.tag != 1) exc_append(A, p);
         active = (P.tag != 0);
       }
 #ifdef EB200_X_NODEPOSIT
@@ -1213,6 +1215,7 @@ namespace eb200 {
   #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         if (tv[k] != 1) {
+          if (in_range) exc_append(A, (uint32_t)(p0 + k));
           continue;
         }
         int   ip[2] = { iv[0][k], iv[1][k] };
@@ -1255,6 +1258,7 @@ namespace eb200 {
           tag = P.tag;
           if (tag != 1) {
             S.tag[p0 + k] = tag;
+            exc_append(A, (uint32_t)(p0 + k));
           }
           if constexpr (KEEP_PREV) {
             if (all_pushed) {
@@ -2151,7 +2155,8 @@ namespace eb200 {
     cudaError_t launch_push_deposit(const PushArgs& A, const eb200_prtls_t& S, uint32_t npart,
                                     const eb200_grid_t& g, const float* em, float* cur,
                                     int mode, float* packed, bool do_pack, cudaStream_t st,
-                                    float* packed_j = nullptr, bool* packed_j_used = nullptr) {
+                                    float* packed_j = nullptr, bool* packed_j_used = nullptr,
+                                    ExcList* exc = nullptr) {
       if (npart == 0) return cudaSuccess;
       FieldView<D> EB(g, const_cast<float*>(em));
       FieldView<D> J(g, cur);
@@ -2289,6 +2294,13 @@ namespace eb200 {
           PK.rowb = 24u * (unsigned)EB.N1;
           const uint32_t ngroups = npart / VEC;
           const bool     v4      = packed_j != nullptr && packed_j_used != nullptr && !j4_disabled();
+          // this kernel and the tail kernel below both report who is not alive afterwards
+          PushArgs AX = A;
+          if (exc != nullptr && exc->count != nullptr) {
+            AX.exc_count = exc->count, AX.exc_idx = exc->idx, AX.exc_cap = exc->cap;
+            exc->tracked = true;
+          }
+          const PushArgs& A = AX; // (shadows the parameter for the launches of this branch)
           if (v4 && lean_prev) {
             const uint32_t wave = resident_ctas(reinterpret_cast<const void*>(push_deposit_mom_kernel<true, false>), 256);
             push_deposit_mom_kernel<true, false><<<(ngroups + 255) / 256, 256, 0, st>>>(
@@ -2419,12 +2431,16 @@ namespace eb200 {
         if (p_begin == npart) return cudaGetLastError();
       }
       const uint32_t nrest = npart - p_begin;
+      PushArgs       AT    = A; // the tail reports to the exception list its head reported to
+      if (exc != nullptr && exc->tracked) {
+        AT.exc_count = exc->count, AT.exc_idx = exc->idx, AT.exc_cap = exc->cap;
+      }
       if (mode == EB200_DEPOSIT_AGGREGATED) {
         push_deposit_kernel<D, O, true><<<(nrest + 255) / 256, 256, 0, st>>>(
-          A, S, p_begin, npart, EB, A.c.charge, inv_dt, J);
+          AT, S, p_begin, npart, EB, A.c.charge, inv_dt, J);
       } else {
         push_deposit_kernel<D, O, false><<<(nrest + 255) / 256, 256, 0, st>>>(
-          A, S, p_begin, npart, EB, A.c.charge, inv_dt, J);
+          AT, S, p_begin, npart, EB, A.c.charge, inv_dt, J);
       }
       count_launch();
       return cudaGetLastError();
@@ -2540,7 +2556,8 @@ namespace eb200 {
     cudaError_t push_deposit_sr(const eb200_grid_t& g, int order, const eb200_pusher_t& c,
                                 const eb200_prtls_t& S, uint32_t npart, const float* em,
                                 float* cur, int mode, float* packed, bool do_pack,
-                                cudaStream_t st, float* packed_j, bool* packed_j_used) {
+                                cudaStream_t st, float* packed_j, bool* packed_j_used,
+                                ExcList* exc) {
       PushArgs A;
       A.c   = c;
       A.ndh = HALF * (c.charge / c.mass) * c.omegaB0 * c.dt;
@@ -2549,7 +2566,7 @@ namespace eb200 {
       for (int a = 0; a < 3; ++a) A.ni[a] = g.n[a];
       if (order > 3) return cudaErrorNotSupported; // unfused path only (engine.cu falls back)
 #define CALL(D, O)                                                                             \
-  launch_push_deposit<D, O>(A, S, npart, g, em, cur, mode, packed, do_pack, st, packed_j, packed_j_used)
+  launch_push_deposit<D, O>(A, S, npart, g, em, cur, mode, packed, do_pack, st, packed_j, packed_j_used, exc)
       EB200_DISPATCH_DO(g.dim, order, CALL)
 #undef CALL
     }

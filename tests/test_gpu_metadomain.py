@@ -17,10 +17,20 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def test_single_domain_through_generic_exchange():
+@pytest.mark.parametrize("classify", ["block-sort", "device-sort", "scan"])
+def test_single_domain_through_generic_exchange(classify):
+    """classify: how the migration finds the dead / outgoing particles -- from the fused pusher's
+    exception list (sorted by one block, or by the device-wide radix sort for long lists) or by
+    scanning every tag (EB200_MIGRATE_SCAN=1, the path of kernels that keep no list)"""
     if _ngpu() < 1:
         pytest.skip("no CUDA device")
     env = dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK="0")
+    env.pop("EB200_EXC_SMALL", None)
+    env.pop("EB200_MIGRATE_SCAN", None)
+    if classify == "device-sort":
+        env["EB200_EXC_SMALL"] = "0"
+    elif classify == "scan":
+        env["EB200_MIGRATE_SCAN"] = "1"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mgpu_worker.py")], env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
