@@ -50,7 +50,7 @@ TOML = """[simulation]
 
 [particles]
   ppc0 = {ppc0}
-
+{sort_line}
   [[particles.species]]
     label    = "e-"
     mass     = 1.0
@@ -89,7 +89,7 @@ def binary(flavour: str, pgen: str = "reconnection"):
     return p if os.path.exists(p) else None
 
 
-def reconnection_toml(size, ppc0=32, nfilter=8, nsteps=30, maxnpart=None):
+def reconnection_toml(size, ppc0=32, nfilter=8, nsteps=30, maxnpart=None, sort_interval=0):
     """reconnection.toml (pgens/reconnection/reconnection.toml) at `size` cells with the cell
     size of the 4096x2048 original (dx = 1000/4096) and the named ppc0."""
     n1, n2 = size
@@ -102,6 +102,7 @@ def reconnection_toml(size, ppc0=32, nfilter=8, nsteps=30, maxnpart=None):
         maxnpart = int(ncell * ppc0 * 0.5 * 1.35 + 3.0 * 4.0 * (10.0 / dx) * n1 * ppc0 * 0.5)
     return TOML.format(runtime=f"{(nsteps + 0.5) * dt:.6f}", n1=n1, n2=n2, x0=-0.5 * lx, x1=0.5 * lx,
                        y0=-0.5 * ly, y1=0.5 * ly, nfilter=nfilter, ppc0=float(ppc0),
+                       sort_line=(f"  spatial_sorting_interval = {int(sort_interval)}\n" if sort_interval else ""),
                        maxnpart=f"{maxnpart:.4e}")
 
 
@@ -132,7 +133,8 @@ def parse_npart(count_file: str):
     return out
 
 
-def run(flavour, size, ppc0=32, nfilter=8, nsteps=30, skip=10, threads=None, timeout=1500, keep=None):
+def run(flavour, size, ppc0=32, nfilter=8, nsteps=30, skip=10, threads=None, timeout=1500, keep=None,
+        sort_interval=0):
     """Returns a dict: particle-steps/s from the reference's own timers, median over steps
     [skip, nsteps): `pushdep` = ParticlePusher + CurrentDeposit (BASELINE.md section 3 headline),
     `path` = + FieldSolver + CurrentFiltering + Communications + FieldBoundaries, `total` =
@@ -143,7 +145,7 @@ def run(flavour, size, ppc0=32, nfilter=8, nsteps=30, skip=10, threads=None, tim
     tmp = keep or tempfile.mkdtemp(prefix="eb_ref_")
     os.makedirs(tmp, exist_ok=True)
     with open(os.path.join(tmp, "rec.toml"), "w") as f:
-        f.write(reconnection_toml(size, ppc0, nfilter, nsteps))
+        f.write(reconnection_toml(size, ppc0, nfilter, nsteps, sort_interval=sort_interval))
     env = dict(os.environ, EB_COUNT_FILE=os.path.join(tmp, "counts.txt"))
     ncores = threads or len(os.sched_getaffinity(0))
     if flavour.startswith("omp"):
@@ -174,6 +176,7 @@ def run(flavour, size, ppc0=32, nfilter=8, nsteps=30, skip=10, threads=None, tim
         return {"error": f"could not parse the reference's output ({len(steps)} steps, {len(npart)} stats rows)"}
     med = lambda keys: statistics.median(sum(s.get(k, 0.0) for k in keys) for s in use)
     n = npart[-1]
+    mean = lambda keys: statistics.fmean(sum(s.get(k, 0.0) for k in keys) for s in use)
     pushdep = med(["ParticlePusher", "CurrentDeposit"])
     path = med(["ParticlePusher", "CurrentDeposit", "FieldSolver", "CurrentFiltering",
                 "Communications", "FieldBoundaries"])
@@ -184,7 +187,11 @@ def run(flavour, size, ppc0=32, nfilter=8, nsteps=30, skip=10, threads=None, tim
             "s_per_step": {"pushdep": pushdep, "path": path, "total": total,
                            "pusher": med(["ParticlePusher"]), "deposit": med(["CurrentDeposit"]),
                            "fieldsolver": med(["FieldSolver"]), "filter": med(["CurrentFiltering"]),
-                           "custom_injector": med(["Custom", "Injector"])},
+                           "custom_injector": med(["Custom", "Injector"]),
+                           "sort_mean": mean(["ParticleSort"]),
+                           "total_mean": mean(["ParticlePusher", "CurrentDeposit", "FieldSolver",
+                                               "CurrentFiltering", "Communications", "FieldBoundaries",
+                                               "Injector", "Custom", "ParticleSort", "ParticleBoundaries"])},
             "pushdep_pss": n / pushdep, "path_pss": n / path, "total_pss": n / total,
             "cores": ncores if flavour.startswith("omp") else None, "size": list(size), "ppc0": ppc0}
 
