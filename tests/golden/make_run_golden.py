@@ -37,11 +37,11 @@ CASES = {
     "turbulence2d": ("omp/entity_turbulence.xc", "turbulence2d.toml", 0, 8),
     "turbulence3d": ("omp3/entity_turbulence.xc", "turbulence3d.toml", 0, 4),
     # GRPIC: vacuum Wald solution (fields + boundaries only)
-    "wald_small": ("omp/entity_wald.xc", "wald_small.toml", 0, 6),
+    "wald_small": ("omp/entity_wald.xc", "wald_small.toml", 0, 12),
     # GRPIC with particles: pusher, deposit into cur0, AbsorbCurrents, filter, both AmpereCurrents
-    "accretion_small": ("omp/entity_accretion.xc", "accretion_small.toml", 0, 5),
+    "accretion_small": ("omp/entity_accretion.xc", "accretion_small.toml", 0, 12),
     # curvilinear SRPIC: qspherical pulsar magnetosphere with atmosphere injection
-    "magnetosphere_small": ("omp/entity_magnetosphere.xc", "magnetosphere_small.toml", 0, 5),
+    "magnetosphere_small": ("omp/entity_magnetosphere.xc", "magnetosphere_small.toml", 0, 12),
 }
 
 

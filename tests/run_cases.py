@@ -93,7 +93,7 @@ GR_CASES = {
     # pgens/accretion/accretion.toml at fixture size (run_inputs/accretion_small.toml)
     "accretion_small": dict(n=(48, 32), metric="qkerr_schild", extent=(1.0, 6.0), r0=0.0, h=0.0, a=0.95,
                             larmor0=0.025, skindepth0=0.5, ppc0=2.0, nfilter=4, deposit=True,
-                            match_ds=1.0, pushers=[2, 2], cap=8192, niter=10, eps=1e-2),
+                            match_ds=1.0, pushers=[2, 2], cap=16384, niter=10, eps=1e-2),
 }
 
 

@@ -1,6 +1,7 @@
 """Curvilinear SRPIC whole-step parity against the RUNNING reference (entity.xc, pgens/
 magnetosphere with the dump wrapper; tests/golden/run_magnetosphere_small.npz): eb200_srpic_step
-on a qspherical context started from the state after the reference's step s0.
+on a qspherical context started from the state after the reference's step s0, over a window of
+12 steps.
 
 Covers, in the order of SRPICEngine::step_forward: curvilinear Faraday / Ampere /
 CurrentsAmpere, the Boris + GCA pusher with the atmosphere's gravity and the axis / absorbing
@@ -114,4 +115,7 @@ def test_magnetosphere_window(mods):
         for a in ("dx1", "dx2", "ux1", "ux2", "ux3", "phi"):
             v, r = sp.arrays[a][:npre].cpu().numpy(), z[f"s{s1}/sp{k}_{a}"][:npre]
             err = np.abs(v - r)[~moved]
+            if a == "phi":
+                # an angle: 0 and 2 pi are the same place (atan2 decides the branch by rounding)
+                err = np.minimum(err, np.abs(np.float32(2 * np.pi) - err))
             assert err.max() <= 2e-4 * max(1.0, np.abs(r).max()), f"sp{k}.{a}: {err.max():.3e}"

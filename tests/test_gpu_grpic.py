@@ -77,7 +77,7 @@ def import_injected(mods, sim, z, s, s1):
 def test_wald_vacuum_window(mods):
     """pgens/wald (BASELINE configs[4]): vacuum Wald solution, qkerr_schild a = 0.95; the GRPIC
     field path (time averages, aux E / H, both Faraday / Ampere sub-steps, SwapFields) with its
-    HORIZON, MATCH (towards init_flds) and AXIS boundaries, 6 steps."""
+    HORIZON, MATCH (towards init_flds) and AXIS boundaries, 12 steps."""
     case = "wald_small"
     z = rc.load(case)
     s0, s1 = (int(v) for v in z["meta/steps"])
