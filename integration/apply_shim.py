@@ -5,7 +5,8 @@ and guarded by EB200_SHIM and the Minkowski branch:
 
   src/engines/srpic/fieldsolvers.h    srpic::Faraday / Ampere / CurrentsAmpere -> eb200_faraday / eb200_ampere /
                                       eb200_currents_ampere
-  src/engines/srpic/currents.h        srpic::CurrentsDeposit -> eb200_zero_currents + eb200_deposit per species
+  src/engines/srpic/currents.h        srpic::CurrentsDeposit -> eb200_zero_currents + eb200_deposit per species;
+                                      srpic::CurrentsFilter -> eb200_filter (single domain)
   src/engines/srpic/particle_pusher.h srpic::ParticlePush -> eb200_push_deposit_sr (fused, charged species) or
                                       eb200_push_sr per species (species without emission policy; pgens
                                       without per-particle functors)
@@ -161,6 +162,24 @@ def main(root):
             continue;
           }
         }
+#endif
+''')
+    patch(cu, "      // !TODO: this needs to be done more efficiently\n      for (auto i { 0u }; i < nfilter; ++i) {",
+          '''#ifdef EB200_SHIM
+      if constexpr (M::CoordType == Coord::Cartesian) {
+        if (metadomain.ndomains() == 1u and eb200shim::filter_enabled()) {
+          // all passes in one call: temporally blocked sweeps, the periodic ghost fill included
+          // (what the loop below does with deep_copy + kernel + CommunicateFields(Comm::J) per pass)
+          auto* c = eb200shim::ctx(domain);
+          int   fbc[6];
+          eb200shim::field_bcs(domain.mesh.flds_bc(), (int)M::Dim, fbc);
+          eb200shim::check(c,
+                           eb200_filter(c, domain.fields.cur.data(), domain.fields.buff.data(), (int)nfilter, fbc,
+                                        eb200shim::stream()),
+                           "eb200_filter");
+          return;
+        }
+      }
 #endif
 ''')
     so = os.path.join(root, "src/framework/domain/metadomain_sort.cpp")

@@ -15,6 +15,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -33,6 +34,12 @@ namespace eb200shim {
   inline StepState& state() {
     static StepState s;
     return s;
+  }
+
+  // srpic::CurrentsFilter through eb200_filter: opt-in at run time (EB200_SHIM_FILTER=1)
+  inline bool filter_enabled() {
+    static const bool on = std::getenv("EB200_SHIM_FILTER") != nullptr;
+    return on;
   }
 
   // kernels are enqueued on the stream of Kokkos' default execution space instance
@@ -93,6 +100,22 @@ namespace eb200shim {
     for (int a = 0; a < dim; ++a) {
       pbc[2 * a]     = code(b[a].first);
       pbc[2 * a + 1] = code(b[a].second);
+    }
+  }
+
+  // Mesh::flds_bc() as EB200_FBC_* for the filter: periodic faces wrap, conductor faces mirror
+  // (digital_filter.hpp:99-388), every other kind leaves its ghost layer alone
+  template <class BCS>
+  void field_bcs(const BCS& b, int dim, int* fbc) {
+    auto code = [](const ntt::FldsBC& x) {
+      if (x == ntt::FldsBC::PERIODIC) return (int)EB200_FBC_PERIODIC;
+      if (x == ntt::FldsBC::CONDUCTOR) return (int)EB200_FBC_CONDUCTOR;
+      return (int)EB200_FBC_NONE;
+    };
+    for (int a = 0; a < 6; ++a) fbc[a] = EB200_FBC_NONE;
+    for (int a = 0; a < dim; ++a) {
+      fbc[2 * a]     = code(b[a].first);
+      fbc[2 * a + 1] = code(b[a].second);
     }
   }
 } // namespace eb200shim

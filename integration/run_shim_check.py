@@ -28,9 +28,9 @@ INP = os.path.join(ROOT, "tests", "golden", "run_inputs", "stream2d.toml")
 STEPS = (0, 5, 10)
 
 
-def dump_run(flavour):
+def dump_run(flavour, extra_env=None):
     tmp = tempfile.mkdtemp(prefix=f"eb_shim_{flavour}_")
-    env = dict(os.environ, EB_DUMP_DIR=tmp, EB_DUMP_STEPS=",".join(str(s) for s in STEPS),
+    env = dict(os.environ, **(extra_env or {}), EB_DUMP_DIR=tmp, EB_DUMP_STEPS=",".join(str(s) for s in STEPS),
                LD_LIBRARY_PATH=os.path.join(ROOT, "entity_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([os.path.join(BIN, flavour, "entity_streaming.xc"), "-input", INP], cwd=tmp, env=env,
                        capture_output=True, text=True, timeout=900)
@@ -39,9 +39,10 @@ def dump_run(flavour):
     return {s: refdump.read(os.path.join(tmp, f"s{s}_d0.bin")) for s in STEPS}
 
 
-def parity():
+def parity(filter_too=False):
+    """filter_too: also hand srpic::CurrentsFilter to eb200_filter (EB200_SHIM_FILTER=1)"""
     out = {}
-    a, b = dump_run("cuda"), dump_run("cuda_shim")
+    a, b = dump_run("cuda"), dump_run("cuda_shim", {"EB200_SHIM_FILTER": "1"} if filter_too else None)
     for s in STEPS:
         da, db = a[s], b[s]
         rec = {}
@@ -71,7 +72,7 @@ def parity():
 
 
 def main():
-    out = {"parity": parity(), "timing": {}}
+    out = {"parity": parity(), "parity_with_filter": parity(True), "timing": {}}
     os.environ["LD_LIBRARY_PATH"] = os.path.join(ROOT, "entity_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", "")
     # the reference's default (particles.spatial_sorting_interval = 0: particles stay in injection
     # order) and with its cell sort switched on every 20 steps
@@ -79,6 +80,10 @@ def main():
         for flavour in ("cuda", "cuda_shim"):
             r = refrun.run(flavour, (4096, 2048), nsteps=45, skip=21, sort_interval=sort_interval)
             out["timing"][f"{flavour}_sort{sort_interval}"] = None if r is None else {k: r[k] for k in r if k != "raw"}
+    os.environ["EB200_SHIM_FILTER"] = "1"
+    r = refrun.run("cuda_shim", (4096, 2048), nsteps=45, skip=21, sort_interval=20)
+    out["timing"]["cuda_shim_sort20_filter"] = None if r is None else {k: r[k] for k in r if k != "raw"}
+    del os.environ["EB200_SHIM_FILTER"]
     text = json.dumps(out, indent=1, default=str)
     print(text)
     if len(sys.argv) > 1:

@@ -26,7 +26,7 @@ def test_patches_apply_to_a_scratch_copy(tmp_path):
     m.main(str(tmp_path))
     m.main(str(tmp_path))  # idempotent: starts from the pristine files
     want = {"src/engines/srpic/fieldsolvers.h": ["eb200_faraday(", "eb200_ampere(", "eb200_currents_ampere("],
-            "src/engines/srpic/currents.h": ["eb200_deposit(", "eb200_zero_currents("],
+            "src/engines/srpic/currents.h": ["eb200_deposit(", "eb200_filter("],
             "src/engines/srpic/particle_pusher.h": ["eb200_push_deposit_sr(", "eb200_push_sr("],
             "src/framework/domain/metadomain_sort.cpp": ["eb200_sort_particles("]}
     for f, calls in want.items():
