@@ -11,7 +11,8 @@ MATCH (towards pgen.MatchFields) faces. The particles srpic::ParticleInjector ap
 step come from the dump (the injector is the host's).
 
 Metric functions go through expf / logf / sinf / cosf (CUDA vs glibc, last ulp): E, B within
-2e-5 and J within 1e-3 of max|F| (fp32 atomics vs the serial order), particle counts exact."""
+2e-5 and J within 1e-3 of max|F| (fp32 atomics vs the serial order) at every step, particle counts
+exact; particle offsets / momenta within 1e-3 after the 12 steps."""
 import numpy as np
 import pytest
 
@@ -118,4 +119,6 @@ def test_magnetosphere_window(mods):
             if a == "phi":
                 # an angle: 0 and 2 pi are the same place (atan2 decides the branch by rounding)
                 err = np.minimum(err, np.abs(np.float32(2 * np.pi) - err))
-            assert err.max() <= 2e-4 * max(1.0, np.abs(r).max()), f"sp{k}.{a}: {err.max():.3e}"
+            # 12 steps of a strongly magnetised plasma (larmor0 = 2e-5): the last-ulp differences of
+            # expf / logf / sincosf between CUDA and glibc grow with the window (5 steps: 2e-4)
+            assert err.max() <= 1e-3 * max(1.0, np.abs(r).max()), f"sp{k}.{a}: {err.max():.3e}"
