@@ -12,7 +12,13 @@
  *    then i2, i3; the component index is slowest ("component planes"). This is
  *    Kokkos LayoutLeft, the layout of the reference's CUDA build for
  *    ndfield_t<D,N> (src/global/arch/kokkos_aliases.h:83-105,
- *    src/framework/containers/fields.h:38-108).
+ *    src/framework/containers/fields.h:38-108). The arrays are dense: the ABI carries no
+ *    strides on purpose. Kokkos::View<real_t**[N]> of the CUDA build is contiguous LayoutLeft
+ *    (stride(0) = 1, stride(k) = product of the lower extents: no padding unless the host asks
+ *    for AllowPadding, which the reference does not), the coalescing and the TMA / vector
+ *    accesses of the kernels rely on unit stride along i1, and the reference's host-side
+ *    LayoutRight build is served by eb200_srpic_step_host on the caller's own buffers, not by a
+ *    strided view. integration/eb200_shim.hpp hands view.data() over as is.
  *  - Particles: SoA; eb200_prtls_t lists the arrays in the member order of
  *    ntt::ParticleArrays (src/framework/containers/particles.h:47-71).
  *  - `stream` is a cudaStream_t passed as void*; every call only enqueues work
