@@ -16,9 +16,9 @@
  *    strides on purpose. Kokkos::View<real_t**[N]> of the CUDA build is contiguous LayoutLeft
  *    (stride(0) = 1, stride(k) = product of the lower extents: no padding unless the host asks
  *    for AllowPadding, which the reference does not), the coalescing and the TMA / vector
- *    accesses of the kernels rely on unit stride along i1, and the reference's host-side
- *    LayoutRight build is served by eb200_srpic_step_host on the caller's own buffers, not by a
- *    strided view. integration/eb200_shim.hpp hands view.data() over as is.
+ *    accesses of the kernels rely on unit stride along i1; a host-space (LayoutRight) build of
+ *    the reference would transpose on its side of eb200_srpic_step_host rather than ask every
+ *    kernel for strided access. integration/eb200_shim.hpp hands view.data() over as is.
  *  - Particles: SoA; eb200_prtls_t lists the arrays in the member order of
  *    ntt::ParticleArrays (src/framework/containers/particles.h:47-71).
  *  - `stream` is a cudaStream_t passed as void*; every call only enqueues work
