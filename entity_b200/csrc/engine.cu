@@ -87,6 +87,13 @@ namespace eb200 {
     // srpic::ParticleInjector for an ATMOSPHERE face (eb200_srpic_set_atmosphere_injector)
     bool               has_atm = false;
     eb200_atmosphere_t atm {};
+    // emission policies per emitting species (eb200_srpic_set_emission)
+    struct Emit {
+      bool             on = false;
+      int              photon_species = -1;
+      eb200_emission_t policy {};
+    };
+    std::vector<Emit> emission;
   };
 
   struct PhaseScope {
@@ -134,6 +141,7 @@ namespace eb200 {
       HostStreamer*               host = nullptr; // non-null: particle arrays stream from/to the host
       const EngineState*          eng  = nullptr; // MATCH faces, if any
       bool                        curv = false;   // spherical / qspherical metric
+      uint32_t                    step = 0;       // of this step_forward (streams of the emission draws)
     };
 
 #define PHASE(dom, which) PhaseScope phase_scope_((dom).prof, (which), (cudaStream_t)(dom).stream)
@@ -240,12 +248,40 @@ namespace eb200 {
 
     static bool almost_zero(float x) { return std::fabs(x) <= std::numeric_limits<float>::epsilon(); }
 
+    // the pusher of a species with an emission policy (particle_pusher.h:128-183): the photons
+    // are appended to the emitted species, whose npart grows before its own turn in the loop
+    static const EngineState::Emit* emission_of(const Domain& dom, int s) {
+      if (!dom.eng || s >= (int)dom.eng->emission.size() || !dom.eng->emission[s].on) return nullptr;
+      return &dom.eng->emission[s];
+    }
+
+    static int PushWithEmission(Domain& dom, int s, const eb200_pusher_t& c, const EngineState::Emit& e) {
+      if (e.photon_species < 0 || e.photon_species >= dom.nspecies || e.photon_species == s) {
+        return EB200_ERR_ARG;
+      }
+      eb200_species_t& sp = dom.species[s];
+      eb200_species_t& ph = dom.species[e.photon_species];
+      eb200_emission_t pol = e.policy;
+      pol.photons          = ph.arrays;
+      pol.photon_npart     = ph.npart;
+      pol.photon_maxnpart  = ph.maxnpart;
+      pol.step             = dom.step;
+      pol.call             = (uint32_t)s;
+      const int rc = eb200_push_sr_emission(dom.ctx, &c, &sp.arrays, sp.npart, dom.em, &pol, dom.stream);
+      ph.npart = pol.photon_npart;
+      return rc;
+    }
+
     // srpic::ParticlePush, particle_pusher.h:36-185
     int ParticlePush(Domain& dom, double time) {
       for (int s = 0; s < dom.nspecies; ++s) {
         eb200_species_t& sp = dom.species[s];
         if (sp.pusher_flags == EB200_PUSHER_NONE || sp.npart == 0) continue;
         const eb200_pusher_t c = pusher_context(dom, sp, time);
+        if (const EngineState::Emit* e = emission_of(dom, s)) {
+          TRY(PushWithEmission(dom, s, c, *e));
+          continue;
+        }
         TRY(eb200_push_sr(dom.ctx, &c, &sp.arrays, sp.npart, dom.em, dom.stream));
       }
       return EB200_OK;
@@ -335,14 +371,20 @@ namespace eb200 {
         eb200_species_t& sp = dom.species[s];
         if (sp.pusher_flags == EB200_PUSHER_NONE || sp.npart == 0) continue;
         const eb200_pusher_t c = pusher_context(dom, sp, time);
+        const int mode = dom.prm->deposit_mode == EB200_DEPOSIT_AGGREGATED ? EB200_DEPOSIT_AGGREGATED
+                                                                         : EB200_DEPOSIT_ATOMIC;
+        if (const EngineState::Emit* e = emission_of(dom, s)) {
+          // no fused kernel carries the emission hook: the pusher with the policy, then the deposit
+          TRY(PushWithEmission(dom, s, c, *e));
+          if (!almost_zero(sp.charge)) {
+            TRY(eb200_deposit(dom.ctx, &sp.arrays, sp.npart, sp.charge, dom.prm->dt, dom.cur, mode, dom.stream));
+          }
+          continue;
+        }
         if (almost_zero(sp.charge)) {
           TRY(eb200_push_sr(dom.ctx, &c, &sp.arrays, sp.npart, dom.em, dom.stream));
         } else {
-          TRY(eb200_push_deposit_sr(dom.ctx, &c, &sp.arrays, sp.npart, dom.em, dom.cur,
-                                    dom.prm->deposit_mode == EB200_DEPOSIT_AGGREGATED
-                                      ? EB200_DEPOSIT_AGGREGATED
-                                      : EB200_DEPOSIT_ATOMIC,
-                                    dom.stream));
+          TRY(eb200_push_deposit_sr(dom.ctx, &c, &sp.arrays, sp.npart, dom.em, dom.cur, mode, dom.stream));
         }
       }
       return EB200_OK;
@@ -421,6 +463,7 @@ namespace eb200 {
 
     int step_forward(Domain& dom, uint32_t step, double time) {
       const eb200_srpic_params_t& p = *dom.prm;
+      dom.step = step;
       if (step == 0) {
         {
           PHASE(dom, EB200_PHASE_COMM);
@@ -877,6 +920,25 @@ extern "C" int eb200_srpic_set_ext_current(eb200_ctx_t* ctx, const eb200_ext_cur
   if (ext->nmodes < 0 || ext->nmodes > EB200_MAX_MODES) return EB200_ERR_ARG;
   e->ext     = *ext;
   e->has_ext = true;
+  return EB200_OK;
+}
+
+extern "C" int eb200_srpic_set_emission(eb200_ctx_t* ctx, int species, int photon_species,
+                                        const eb200_emission_t* policy) {
+  if (!ctx || species < 0 || species >= 64) return EB200_ERR_ARG;
+  eb200::EngineState* e = eb200_ctx_engine_state(ctx);
+  if ((int)e->emission.size() <= species) e->emission.resize(species + 1);
+  if (policy == nullptr) {
+    e->emission[species].on = false;
+    return EB200_OK;
+  }
+  if ((policy->kind != EB200_EMISSION_SYNCHROTRON && policy->kind != EB200_EMISSION_COMPTON) ||
+      photon_species < 0 || photon_species == species) {
+    return EB200_ERR_ARG;
+  }
+  e->emission[species].on             = true;
+  e->emission[species].photon_species = photon_species;
+  e->emission[species].policy         = *policy;
   return EB200_OK;
 }
 

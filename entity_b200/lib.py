@@ -278,6 +278,8 @@ def load():
     lib.eb200_push_sr_emission.argtypes = [ctxp, C.POINTER(Pusher), C.POINTER(Prtls), C.c_uint32, vp,
                                            C.POINTER(EmissionC), vp]
     lib.eb200_push_sr_emission.restype = C.c_int
+    lib.eb200_srpic_set_emission.argtypes = [ctxp, C.c_int, C.c_int, C.POINTER(EmissionC)]
+    lib.eb200_srpic_set_emission.restype = C.c_int
     lib.eb200_set_lean_prev.argtypes = [ctxp, C.c_int]
     lib.eb200_set_sort_mode.argtypes = [ctxp, C.c_int]
     lib.eb200_srpic_step.argtypes = [ctxp, C.POINTER(ParamsC), vp, vp, vp, C.POINTER(SpeciesC),

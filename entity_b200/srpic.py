@@ -240,6 +240,20 @@ class Simulation:
             sp.npart = int(arr[k].npart)
         return int(arr[k0].npart) - n0
 
+    def set_emission(self, species, photon_species, kind, photon_weight, photon_energy_min,
+                     nominal_probability, nominal_photon_energy, should_drag=False,
+                     seed=0x123456789abcdef0):
+        """Emission policy of `species` (0-based) inside the step; kind None clears it"""
+        if kind is None:
+            self.ctx._check(self.ctx.lib.eb200_srpic_set_emission(self.ctx.handle, species, -1, None))
+            return
+        e = L.EmissionC()
+        e.kind, e.photon_weight, e.photon_energy_min = kind, photon_weight, photon_energy_min
+        e.nominal_probability, e.nominal_photon_energy = nominal_probability, nominal_photon_energy
+        e.should_drag, e.seed = int(should_drag), seed
+        self.ctx._check(self.ctx.lib.eb200_srpic_set_emission(self.ctx.handle, species, photon_species,
+                                                              C.byref(e)))
+
     def set_atmosphere_injector(self, atm):
         """Registers the atmosphere injector of the step (None clears it)"""
         self._atm_c = self._atmosphere_c(atm) if atm is not None else None

@@ -755,6 +755,15 @@ int eb200_push_sr_emission(eb200_ctx_t* ctx, const eb200_pusher_t* pusher, const
                            uint32_t npart, const float* em, eb200_emission_t* emission,
                            eb200_stream_t stream);
 
+/* Registers (policy != NULL) or clears the emission policy of species `species` for
+ * eb200_srpic_step: its pusher then runs eb200_push_sr_emission with the arrays of species
+ * `photon_species` as the emitted species (photons / photon_npart / photon_maxnpart / step / call of
+ * `policy` are filled per step; call = the emitter's index), followed by its deposit; the emitted
+ * species' npart grows before its own turn in the species loop, as in srpic::ParticlePush
+ * (particle_pusher.h:161-183). */
+int eb200_srpic_set_emission(eb200_ctx_t* ctx, int species, int photon_species,
+                             const eb200_emission_t* policy);
+
 /* ------------------------------------------------ output staging */
 /* kernel::FieldsToPhys_kernel<M, N1, N2> over Mesh::rangeActiveCells (src/kernels/
  * fields_to_phys.hpp:33-239; what the writer launches per output field, src/output/

@@ -157,3 +157,65 @@ def test_limits_and_capacity(mods):
     assert ctx.last_emission_npart == 10
     assert int((ph["tag"][:4] != 0).sum()) == 0 and int((ph["tag"][4:10] == 1).sum()) == 6
     assert int((ph["tag"][10:] != 0).sum()) == 0
+
+
+def test_emission_inside_the_step(mods):
+    """eb200_srpic_set_emission: the step mirror runs the emitting species through the pusher with
+    the policy (then its deposit), the photons land in the photon species and are pushed by its own
+    (massless) pusher from the same step on; a second, identical run reproduces the same set of
+    photons bit for bit (counter-based draws keyed by seed, step, emitter index, particle)."""
+    torch, eb, L, emission, orc, philox = mods
+    from entity_b200 import workloads
+
+    def run(nsteps):
+        sim = workloads.reconnection((64, 64), ppc0=8, nfilter=2, strict=False, fused=True, sort_interval=0,
+                                     deposit_mode=eb.DEPOSIT_AGGREGATED)
+        sim.alloc_species(0.0, 0.0, 400000, pusher=L.PUSHER_PHOTON)
+        sim._species_c = None
+        # hot sheet particles (gamma ~ 30) radiate, the cold background fails the 20 % rule
+        sim.set_emission(0, 2, L.EMISSION_COMPTON, 1.0, 0.0, 0.5, 1e-3, should_drag=True, seed=0xfeed)
+        counts, snap = [], None
+        for k in range(nsteps):
+            sim.step()
+            ph = sim.species[2]
+            counts.append(ph.npart)
+            if k == 0:
+                snap = {nm: ph.arrays[nm][:ph.npart].clone() for nm in ("i1", "dx1", "i2", "dx2", "ux1", "ux2", "ux3")}
+        return sim, counts, snap
+
+    sim, counts, snap = run(3)
+    n_e = [sp.npart for sp in sim.species[:2]]
+    assert counts[0] > 100 and counts[0] < counts[1] < counts[2]
+    ph = sim.species[2]
+    n1 = counts[0]
+    assert int((ph.arrays["tag"][:ph.npart] == 1).sum()) == ph.npart
+    assert int((sim.species[0].arrays["tag"][:n_e[0]] == 1).sum()) == n_e[0]
+    # photon momenta: |u| = energy > 0, unchanged by the massless pusher; positions advanced
+    e1 = torch.sqrt(snap["ux1"] ** 2 + snap["ux2"] ** 2 + snap["ux3"] ** 2)
+    assert float(e1.min()) > 0
+    for nm in ("ux1", "ux2", "ux3"):
+        assert torch.equal(ph.arrays[nm][:n1], snap[nm])
+    moved = (ph.arrays["dx1"][:n1] != snap["dx1"]) | (ph.arrays["i1"][:n1] != snap["i1"]) | \
+            (ph.arrays["dx2"][:n1] != snap["dx2"]) | (ph.arrays["i2"][:n1] != snap["i2"])
+    assert float(moved.float().mean()) > 0.99
+    # only the hot population radiates: every emitted photon energy respects the 20 % rule bound
+    assert float(e1.max()) < 0.2 * 1e4
+    sim2, counts2, snap2 = run(3)
+    assert counts2[0] == counts[0]
+    # later steps: a draw within rounding of its probability may fall the other way once the
+    # fields differ in the last bit (J summed by atomics)
+    assert all(abs(x - y) <= 3 for x, y in zip(counts2, counts)), (counts, counts2)
+    # the SET of photons is reproducible; their slots come from an atomic counter, so the order is not
+    def canon(d, m):
+        key = torch.stack([d["ux1"][:m].double(), d["ux2"][:m].double(), d["dx1"][:m].double()])
+        order = torch.argsort(key[0] * 1e6 + key[1] * 1e3 + key[2], stable=True)
+        return {nm: d[nm][:m][order] for nm in d}
+    a, b = canon(snap, n1), canon(snap2, n1)
+    for nm in a:
+        assert torch.equal(a[nm], b[nm]), nm
+    # (later steps see fields whose J was summed by atomics in another order: the draws are the
+    # same, the emitters' momenta agree to rounding only -- the counts above are still identical)
+    sim.set_emission(0, 2, None, 0, 0, 0, 0)
+    before = sim.species[2].npart
+    sim.step()
+    assert sim.species[2].npart == before
