@@ -2222,7 +2222,10 @@ namespace eb200 {
           const uint32_t ngroups = npart / VEC;
           const bool     lean    = lean_pusher(A.c);
           auto           kern    = lean ? push_deposit_smem_kernel<true> : push_deposit_smem_kernel<false>;
-          static int     wave[2] = { 0, 0 };
+          static int wave_tbl[64][2] = {}; // per device: occupancy and function attributes are per device
+          int        wave_dev     = 0;
+          cudaGetDevice(&wave_dev);
+          int* wave = wave_tbl[wave_dev & 63];
           if (wave[lean] == 0) {
             int dev = 0, nsm = 0, per_sm = 0;
             cudaGetDevice(&dev);
@@ -2250,7 +2253,10 @@ namespace eb200 {
           const uint32_t ngroups = npart / VEC;
           const bool     lean    = lean_pusher(A.c);
           auto           kern    = lean ? push_deposit_pipe_kernel<true> : push_deposit_pipe_kernel<false>;
-          static int     slots[2] = { 0, 0 };
+          static int slots_tbl[64][2] = {}; // per device: occupancy and function attributes are per device
+          int        slots_dev     = 0;
+          cudaGetDevice(&slots_dev);
+          int* slots = slots_tbl[slots_dev & 63];
           if (slots[lean] == 0) {
             int dev = 0, nsm = 0, per_sm = 0;
             cudaGetDevice(&dev);
@@ -2335,7 +2341,10 @@ namespace eb200 {
           const bool     lean    = lean_pusher(A.c);
           auto           kern    = lean ? push_deposit_vec_kernel<2, true, PackedEM2>
                                         : push_deposit_vec_kernel<2, false, PackedEM2>;
-          static int     wave[2] = { 0, 0 };
+          static int wave_tbl[64][2] = {}; // per device: occupancy and function attributes are per device
+          int        wave_dev     = 0;
+          cudaGetDevice(&wave_dev);
+          int* wave = wave_tbl[wave_dev & 63];
           // CTA size of the packed-node kernel (EB200_VEC_THREADS = 64 / 128 / 256, experiment)
           static const int nthr = [] {
             const char* e = getenv("EB200_VEC_THREADS");
@@ -2370,7 +2379,10 @@ namespace eb200 {
           const bool     lean    = lean_pusher(A.c);
           auto           kern    = lean ? push_deposit_tile_kernel<true>
                                         : push_deposit_tile_kernel<false>;
-          static int     wave[2] = { 0, 0 };
+          static int wave_tbl[64][2] = {}; // per device: occupancy and function attributes are per device
+          int        wave_dev     = 0;
+          cudaGetDevice(&wave_dev);
+          int* wave = wave_tbl[wave_dev & 63];
           if (wave[lean] == 0) {
             int dev = 0, nsm = 0, per_sm = 0;
             cudaGetDevice(&dev);
@@ -2392,7 +2404,10 @@ namespace eb200 {
           const bool     lean    = lean_pusher(A.c);
           auto           kern    = lean ? push_deposit_vec_kernel<D, true>
                                         : push_deposit_vec_kernel<D, false>;
-          static int wave[2] = { 0, 0 }; // resident CTAs of one wave for (full, lean)
+          static int wave_tbl[64][2] = {}; // per device: occupancy and function attributes are per device
+          int        wave_dev     = 0;
+          cudaGetDevice(&wave_dev);
+          int* wave = wave_tbl[wave_dev & 63]; // resident CTAs of one wave for (full, lean)
           if (wave[lean] == 0) {
             int dev = 0, nsm = 0, per_sm = 0;
             cudaGetDevice(&dev);
@@ -2415,7 +2430,10 @@ namespace eb200 {
         auto           kern    = lean ? push_deposit_stream_kernel<D, O, true>
                                       : push_deposit_stream_kernel<D, O, false>;
         const size_t   smem    = sizeof(StreamSmem<D>);
-        static int     slots[2] = { 0, 0 }; // resident CTAs per device for (lean, full)
+        static int slots_tbl[64][2] = {}; // per device: occupancy and function attributes are per device
+        int        slots_dev     = 0;
+        cudaGetDevice(&slots_dev);
+        int* slots = slots_tbl[slots_dev & 63]; // resident CTAs per device for (lean, full)
         if (slots[lean] == 0) {
           int dev = 0, nsm = 0, per_sm = 0;
           cudaGetDevice(&dev);
