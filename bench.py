@@ -482,7 +482,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": (f"wald-with-species: 2D GRPIC qkerr_schild a=0.95, {size[0]}x{size[1]} cells, two Boris species in r in [2, 8], pusher_niter=10"
                                     if other == "wald" else
-                                    f"magnetosphere: 2D qspherical SRPIC dipole, {size[0]}x{size[1]} cells, Boris+GCA, atmosphere gravity, ATMOSPHERE/MATCH/AXIS field boundaries"
+                                    f"magnetosphere: 2D qspherical SRPIC dipole, {size[0]}x{size[1]} cells, Boris+GCA, atmosphere gravity + injector every step, ATMOSPHERE/MATCH/AXIS field boundaries"
                                     if other == "magnetosphere" else
                                     f"turbulence-shaped 3D Cartesian SR pair plasma, {size[0]}^3 cells, "
                                     f"{16 if args.ppc == 32 else args.ppc} ppc, 3rd-order shapes (reduced from 1024^3)"

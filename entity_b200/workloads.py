@@ -289,11 +289,13 @@ def wald(n=(512, 512), ppc=8, niter=10, seed=0x77, metric=L.METRIC_QKERR_SCHILD,
     return sim
 
 
-def magnetosphere(n=(2048, 1024), ppc=10, seed=0x88, extent=(1.0, 50.0), nfilter=4, device=0):
+def magnetosphere(n=(2048, 1024), ppc=10, seed=0x88, extent=(1.0, 50.0), nfilter=4, device=0, inject=True):
     """configs[3]: pgens/magnetosphere/magnetosphere.toml (2D qspherical SR, 2048 x 1024): a
     dipole, ATMOSPHERE / MATCH / AXIS field boundaries, Boris + GCA pusher with the atmosphere's
-    gravity, weighted particles. The injector is the host's: the synthetic state carries `ppc`
-    pairs per cell throughout the domain instead of the atmosphere's outflow."""
+    gravity, weighted particles. The synthetic state carries `ppc` pairs per cell throughout the
+    domain (a filled magnetosphere instead of the start-up transient); inject = True registers the
+    atmosphere injector of the toml (temperature 0.1, density 10, height 0.02, ds 2) with the step,
+    so that srpic::ParticleInjector runs every step as in the reference."""
     import numpy as np
     import torch
     metric = L.METRIC_QSPHERICAL
@@ -336,7 +338,11 @@ def magnetosphere(n=(2048, 1024), ppc=10, seed=0x88, extent=(1.0, 50.0), nfilter
     gen.manual_seed(seed)
     per = max(1, ppc // 2)
     for charge in (-1.0, 1.0):
-        cap = n[0] * n[1] * per
+        npart0 = n[0] * n[1] * per
+        cap = int(npart0 * (1.25 if inject else 1.0))
         arrays, npart = _cell_particles(sim, torch, sim.device, cap, 0, n[0], n[1], per, gen, 0.1)
         sim.add_species(1.0, charge, arrays, npart, L.PUSHER_BORIS | L.PUSHER_GCA, cap)
+    if inject:
+        sim.set_atmosphere_injector(dict(dim=0, sign=-1, x_surf=extent[0] * math.exp(buf * dchi), ds=2.0,
+                                         height=0.02, temperature=0.1, density=10.0, species=(0, 1)))
     return sim
