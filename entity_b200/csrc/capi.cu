@@ -818,11 +818,21 @@ static int stats_finish(eb200_ctx_t* ctx, cudaError_t e, double* out_host, cudaS
 int eb200_stats_fields(eb200_ctx_t* ctx, const float* em, const float* cur, int what, int comp,
                        double* out_host, eb200_stream_t stream) {
   ENTER(ctx);
-  REQUIRE_MINK(ctx, "eb200_stats_fields");
+  const bool sph = ctx->cfg.metric == EB200_METRIC_SPHERICAL || ctx->cfg.metric == EB200_METRIC_QSPHERICAL;
+  REQUIRE(ctx, sph || ctx->cfg.metric == EB200_METRIC_MINKOWSKI,
+          "eb200_stats_fields: Minkowski and (q)spherical SRPIC meshes");
   REQUIRE(ctx, em != nullptr && out_host != nullptr, "null argument");
   REQUIRE(ctx, what >= EB200_STATS_B2 && what <= EB200_STATS_JDOTE, "unknown field statistic");
   REQUIRE(ctx, what == EB200_STATS_JDOTE || (comp >= 1 && comp <= 3), "component must be 1..3");
   REQUIRE(ctx, what != EB200_STATS_JDOTE || cur != nullptr, "J.E needs cur");
+  if (sph) {
+    int rc = check_cuda(ctx, ctx->stats.reserve(256), "stats scratch");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return stats_finish(ctx, eb200::stats_fields_curv(ctx->metric, ctx->cfg.grid, em, cur, what, comp,
+                                                      (double*)ctx->stats.ptr, st),
+                        out_host, st, "stats_fields");
+  }
   const float dx = ctx->cfg.metric_params[0];
   REQUIRE(ctx, dx > 0.0f, "metric_params[0] (dx) must be positive");
   int rc = check_cuda(ctx, ctx->stats.reserve(256), "stats scratch");
@@ -837,7 +847,9 @@ int eb200_stats_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t
                           float charge, int use_weights, int what, int c1, int c2,
                           double* out_host, eb200_stream_t stream) {
   ENTER(ctx);
-  REQUIRE_MINK(ctx, "eb200_stats_particles");
+  const bool sph = ctx->cfg.metric == EB200_METRIC_SPHERICAL || ctx->cfg.metric == EB200_METRIC_QSPHERICAL;
+  REQUIRE(ctx, sph || ctx->cfg.metric == EB200_METRIC_MINKOWSKI,
+          "eb200_stats_particles: Minkowski and (q)spherical SRPIC meshes");
   REQUIRE(ctx, out_host != nullptr, "null argument");
   REQUIRE(ctx, what >= EB200_STATS_NPART && what <= EB200_STATS_T, "unknown particle statistic");
   REQUIRE(ctx, what != EB200_STATS_T || (c1 >= 0 && c1 <= 3 && c2 >= 0 && c2 <= 3),
@@ -847,6 +859,16 @@ int eb200_stats_particles(eb200_ctx_t* ctx, const eb200_prtls_t* prtls, uint32_t
           "Rho & Charge for massless particles not defined");
   int rc = check_prtls(ctx, prtls, npart);
   if (rc) return rc;
+  if (sph) {
+    REQUIRE(ctx, npart == 0 || what != EB200_STATS_T || prtls->phi != nullptr, "curvilinear T needs prtls->phi");
+    REQUIRE(ctx, npart == 0 || prtls->phi != nullptr, "curvilinear particle statistics need prtls->phi");
+    rc = check_cuda(ctx, ctx->stats.reserve(256), "stats scratch");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return stats_finish(ctx, eb200::stats_particles_curv(ctx->metric, *prtls, npart, mass, charge, use_weights,
+                                                         what, c1, c2, (double*)ctx->stats.ptr, st),
+                        out_host, st, "stats_particles");
+  }
   const float dx = ctx->cfg.metric_params[0];
   REQUIRE(ctx, dx > 0.0f, "metric_params[0] (dx) must be positive");
   rc = check_cuda(ctx, ctx->stats.reserve(256), "stats scratch");

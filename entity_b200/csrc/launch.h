@@ -143,6 +143,13 @@ namespace eb200 {
                               uint32_t npart, float coeff, bool use_weights, bool volume,
                               float* plane, cudaStream_t st);
 
+  // reduced statistics on (q)spherical SRPIC meshes (stats.cu)
+  cudaError_t stats_fields_curv(const MetricParams& mp, const eb200_grid_t& g, const float* em,
+                                const float* cur, int what, int comp, double* out_dev, cudaStream_t st);
+  cudaError_t stats_particles_curv(const MetricParams& mp, const eb200_prtls_t& S, uint32_t npart,
+                                   float mass, float charge, int use_weights, int what, int c1, int c2,
+                                   double* out_dev, cudaStream_t st);
+
   // output staging (output.cu)
   cudaError_t fields_to_phys(const MetricParams* mp, const eb200_grid_t& g, float dx,
                              const float* from, int ncomp_from, float* to, int ncomp_to,

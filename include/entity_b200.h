@@ -345,7 +345,8 @@ int eb200_match_fields(eb200_ctx_t* ctx, float* em, const float* target, int o, 
 
 /* ------------------------------------------------------------- reduced statistics */
 /* kernel::ReducedFields_kernel (src/kernels/reduced_stats.hpp:25-386) through ReduceFields
- * (src/framework/domain/metadomain_stats.cpp:128-183), Minkowski 1D/2D/3D: the sum over the
+ * (src/framework/domain/metadomain_stats.cpp:128-183), Minkowski 1D/2D/3D and 2D (q)spherical
+ * SRPIC meshes: the sum over the
  * active cells of this domain of B_I^2, E_I^2, (E x B)_I (I = comp, 1..3) or J.E, each term
  * evaluated as the reference does (cell-centred averages, tetrad components, sqrt(det h)).
  * Returns the LOCAL sum (before the MPI reduction and the division by totVolume the reference's
@@ -355,7 +356,8 @@ enum { EB200_STATS_B2 = 0, EB200_STATS_E2 = 1, EB200_STATS_EXB = 2, EB200_STATS_
 int eb200_stats_fields(eb200_ctx_t* ctx, const float* em, const float* cur, int what, int comp,
                        double* out_host, eb200_stream_t stream);
 /* kernel::ReducedParticleMoments_kernel (reduced_stats.hpp:400-536) through ComputeMoments
- * (metadomain_stats.cpp:72-126) for ONE species of a Minkowski domain: Npart (alive count), N,
+ * (metadomain_stats.cpp:72-126) for ONE species of a Minkowski or 2D (q)spherical SRPIC domain
+ * (dV = sqrt_det_h at the particle; momenta to the tetrad basis at (x, phi)): Npart (alive count), N,
  * Rho, Charge (sum of dV * (use_weights ? weight : 1 | mass | charge)) or the stress-energy
  * component T^{c1 c2} (c = 0: energy, 1..3: u_c; sum of dV * coeff / energy -- the reference
  * applies no weight there). LOCAL sum of one species; the caller adds species and normalises by

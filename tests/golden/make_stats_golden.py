@@ -30,6 +30,11 @@ def load():
                                         C.c_float, C.c_float, C.c_int, C.c_float, C.c_int,
                                         C.c_int, C.c_int]
     lib.ref_stats_particles.restype = C.c_float
+    lib.ref_stats_fields_curv.argtypes = [C.c_int, C.POINTER(orc.Grid), f32p, f32p, f32p, C.c_int, C.c_int]
+    lib.ref_stats_fields_curv.restype = C.c_float
+    lib.ref_stats_particles_curv.argtypes = [C.c_int, C.POINTER(orc.Grid), f32p, C.POINTER(orc.Prtls), C.c_uint32,
+                                             C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ref_stats_particles_curv.restype = C.c_float
     return lib
 
 
@@ -47,6 +52,21 @@ def run_all(lib):
         v = lib.ref_stats_particles(C.byref(g), C.byref(s), n, mass, charge, int(use_w), sc.DX,
                                     what, c1, c2)
         out[f"p_{dim}d_s{k}_{name}_w{int(use_w)}_{c1}{c2}"] = np.float32(v)
+    # 2D curvilinear SRPIC meshes: the same kernels instantiated with the reference's own
+    # metric::Spherical / metric::QSpherical
+    for mname, (kind, ext) in sc.CURV.items():
+        e = (C.c_float * 6)(*ext)
+        g, em, cur = sc.fields(2)
+        for name, what, comp in sc.curv_field_cases():
+            v = lib.ref_stats_fields_curv(kind, C.byref(g), e, em.ctypes.data_as(f32p), cur.ctypes.data_as(f32p),
+                                          what, max(comp, 1))
+            out[f"fc_{mname}_{name}_{comp}"] = np.float32(v)
+        for k, mass, charge, name, what, use_w, c1, c2 in sc.curv_particle_cases():
+            g, p, n = sc.curv_particles(k)
+            s = p.struct()
+            v = lib.ref_stats_particles_curv(kind, C.byref(g), e, C.byref(s), n, mass, charge, int(use_w), what,
+                                             c1, c2)
+            out[f"pc_{mname}_s{k}_{name}_w{int(use_w)}_{c1}{c2}"] = np.float32(v)
     return out
 
 

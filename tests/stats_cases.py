@@ -49,3 +49,28 @@ def particle_cases():
                 for use_w in ((False, True) if name in ("N", "Rho", "Charge") else (False,)):
                     for c1, c2 in (T_COMPONENTS if name == "T" else [(0, 0)]):
                         yield dim, k, mass, charge, name, what, use_w, c1, c2
+
+
+# ---------------------------------------------------------------- 2D curvilinear SRPIC meshes
+# kind (ref driver): 1 spherical, 2 qspherical; ext = x1min, x1max, x2min, x2max, r0, h
+CURV = {"spherical": (1, [1.0, 20.0, 0.0, float(np.float32(np.pi)), 0.0, 0.0]),
+        "qspherical": (2, [1.0, 20.0, 0.0, float(np.float32(np.pi)), 0.2, 0.4])}
+
+
+def curv_particles(k):
+    g, p, n = particles(2, k)
+    rng = np.random.default_rng(700 + k)
+    p.phi[:n] = rng.uniform(0.0, 2 * np.pi, n).astype(np.float32)
+    return g, p, n
+
+
+def curv_field_cases():
+    for name, what in FIELD_STATS.items():
+        for comp in ((0,) if name == "JdotE" else (1, 2, 3)):
+            yield name, what, comp
+
+
+def curv_particle_cases():
+    for d, k, mass, charge, name, what, use_w, c1, c2 in particle_cases():
+        if d == 2:
+            yield k, mass, charge, name, what, use_w, c1, c2

@@ -17,7 +17,9 @@ RTOL = 2e-4
 
 
 def test_golden_complete():
-    assert len(GOLD.files) == len(list(sc.field_cases())) + len(list(sc.particle_cases())) == 135
+    mink = len(list(sc.field_cases())) + len(list(sc.particle_cases()))
+    curv = len(sc.CURV) * (len(list(sc.curv_field_cases())) + len(list(sc.curv_particle_cases())))
+    assert mink == 135 and curv == 90 and len(GOLD.files) == mink + curv
 
 
 @pytest.mark.parametrize("dim", [1, 2, 3])
