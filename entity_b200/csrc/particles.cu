@@ -517,6 +517,10 @@ namespace eb200 {
       int          tile[3 * T3N];
     };
 
+    __device__ __forceinline__ void red_f32(float* p, float v) {
+      asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    }
+
     __device__ __forceinline__ void tile_add(int* p, float a, float f) {
       atomicAdd(p, __float_as_int(fmaf(a, f, T3_MAGIC)) - T3_MAGIC_BITS);
     }
@@ -728,13 +732,14 @@ namespace eb200 {
             float*    jrow = jbase + (comp * plane + kz * N12 + jy * N1);
             const int v0 = trow[0];
             const int v1 = (lane < T3X - 32) ? trow[32] : 0;
+            // (explicitly global: a generic atomicAdd carries the shared-memory CAS loop along)
             if (v0 != 0) {
               trow[0] = 0;
-              atomicAdd(jrow, static_cast<float>(v0) * inv_scale);
+              red_f32(jrow, static_cast<float>(v0) * inv_scale);
             }
             if (v1 != 0) {
               trow[32] = 0;
-              atomicAdd(jrow + 32, static_cast<float>(v1) * inv_scale);
+              red_f32(jrow + 32, static_cast<float>(v1) * inv_scale);
             }
           }
         }
